@@ -1,0 +1,88 @@
+"""Generates tests/golden/*.json by running the UNMODIFIED reference from /root/reference.
+
+Run in the build container only (the GPU box has no /root/reference):
+    python -m oracle.make_golden
+Each case records the synthetic config, seeds and weight recipe (oracle/weights.py) plus what the
+reference's own `get_framework` / `Translator_*.translate_batch` produced on CPU fp32 with those
+weights loaded through `load_state_dict(strict=True)`.  Floats are stored as JSON doubles, which
+round-trip fp32 values exactly.
+"""
+import json
+import os
+import sys
+
+import torch
+
+from oracle import ref_harness as rh
+from oracle.shapes import CONFIGS, make_feats, make_opt
+from oracle.weights import SHARP, make_state_dict, param_count
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+CASES = [
+    # name, config, opt overrides, batch, weight kwargs
+    ("cfg1_plain", "cfg1", {}, 8, dict(seed=0)),
+    ("cfg1_sharp", "cfg1", {}, 8, dict(seed=1, perturb=True, sharpen=SHARP)),
+    ("cfg2_plain", "cfg2", {}, 6, dict(seed=0)),
+    ("cfg2_sharp", "cfg2", {}, 12, dict(seed=1, perturb=True, sharpen=SHARP)),
+    ("cfg2_sharp_k3_nbest3_a07", "cfg2", dict(beam_size=3, topk=3, beam_alpha=0.7), 8,
+     dict(seed=2, perturb=True, sharpen=SHARP)),
+    ("cfg2_sharp_greedy", "cfg2", dict(beam_size=1), 8, dict(seed=3, perturb=True, sharpen=SHARP)),
+    ("cfg3_sharp", "cfg3", {}, 4, dict(seed=4, perturb=True, sharpen=SHARP)),
+    ("cfg4_sharp", "cfg4", {}, 3, dict(seed=5, perturb=True, sharpen=SHARP)),
+    ("cfg5_plain", "cfg5", {}, 4, dict(seed=0, perturb=True)),
+    ("cfg5_sharp", "cfg5", {}, 6, dict(seed=6, perturb=True, sharpen=SHARP)),
+    ("cfg5_noct_sharp", "cfg5", dict(use_ct=False, decoder="TransformerDecoder"), 4,
+     dict(seed=7, perturb=True, sharpen=SHARP)),
+]
+
+
+def run_case(name, cfg, over, bsz, wkw, feat_seed=11):
+    opt = make_opt(**{**CONFIGS[cfg], **over})
+    model = rh.build_reference_model(opt)
+    sd = make_state_dict(opt, **wkw)
+    model.load_state_dict(sd, strict=True)
+    feats = make_feats(opt, bsz, seed=feat_seed)
+    with torch.no_grad():
+        enc = model.encoding_phase([f.clone() for f in feats])
+    hyps, scores = rh.run_reference_translate(model, opt, feats)
+    rec = dict(name=name, config=cfg, overrides=over, batch=bsz, weights=wkw, feat_seed=feat_seed,
+               n_params=param_count(sd), hyps=hyps, scores=scores)
+    if "semantic_labels" in enc:
+        rec["semantic_labels"] = enc["semantic_labels"].tolist()
+        rec["preds_attr_head"] = enc["preds_attr"][:, :8].double().tolist()
+        rec["semantic_hidden_states_head"] = enc["semantic_hidden_states"][:, :8].double().tolist()
+    if "preds_length" in enc:
+        rec["preds_length"] = enc["preds_length"].double().tolist()
+    rec["memory_head"] = enc["encoder_hidden_states"][:, ::17, :4].double().tolist()
+    rec["memory_shape"] = list(enc["encoder_hidden_states"].shape)
+    return rec
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    assert rh.reference_available(), "needs /root/reference"
+    for case in CASES:
+        rec = run_case(*case)
+        with open(os.path.join(OUT, rec["name"] + ".json"), "w") as f:
+            json.dump(rec, f)
+        lens = [len(h[0]) for h in rec["hyps"]]
+        print(rec["name"], "params", rec["n_params"], "lens", lens)
+    # state_dict layout known-answers (module tree printed in notebooks/retrieval_robustness.ipynb:97-187)
+    layout = {}
+    for cfg in ("cfg1", "cfg2", "cfg5"):
+        opt = make_opt(**CONFIGS[cfg])
+        model = rh.build_reference_model(opt)
+        layout[cfg] = dict(
+            keys={k: list(v.shape) for k, v in model.state_dict().items()},
+            n_params=sum(p.numel() for p in model.parameters()),
+            input_keys_for_decoder=list(model.input_keys_for_decoder),
+            keys_to_device=list(model.get_keys_to_device()),
+        )
+    with open(os.path.join(OUT, "state_dict_layout.json"), "w") as f:
+        json.dump(layout, f, indent=0)
+    print("layout", {k: v["n_params"] for k, v in layout.items()})
+
+
+if __name__ == "__main__":
+    sys.exit(main())
