@@ -1,0 +1,91 @@
+"""ctypes binding of libcare_b200.so (the C ABI declared in include/care_b200.h).
+
+There is no fallback: if the shared library is missing or cannot be loaded this module raises,
+and every op raises if the library reports an error (e.g. no sm_100 device).
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcare_b200.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU = 0, 1
+
+
+class BeamState(Structure):
+    """Mirror of `care_beam_state` (include/care_b200.h)."""
+    _fields_ = [
+        ("B", c_int32), ("K", c_int32), ("T_max", c_int32), ("V", c_int32), ("need", c_int32),
+        ("scores", c_void_p), ("cur_tok", c_void_p), ("tok_hist", c_void_p), ("prev_ks", c_void_p),
+        ("anc", c_void_p), ("fin_score", c_void_p), ("fin_t", c_void_p), ("fin_k", c_void_p),
+        ("fin_count", c_void_p), ("done", c_void_p), ("n_done", c_void_p),
+    ]
+
+
+_SIGNATURES = {
+    "care_version": (c_int, []),
+    "care_last_error": (c_char_p, []),
+    "care_ctx_create": (c_int, [POINTER(c_void_p), c_int]),
+    "care_ctx_destroy": (None, [c_void_p]),
+    "care_ctx_sm_count": (c_int, [c_void_p]),
+    "care_ctx_launch_count": (c_int64, [c_void_p]),
+    "care_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
+                          c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "care_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "care_encoder_ln_mean": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int,
+                                     c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_void_p]),
+    "care_encoder_highway_bn_mean": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_void_p, c_int,
+                                             c_int, c_void_p, c_int64, c_int, c_void_p]),
+    "care_concept_head": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_int64, c_void_p,
+                                  c_void_p, c_int, c_int, c_void_p]),
+    "care_embed_ln": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p]),
+    "care_add_ln": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int,
+                            c_void_p, c_void_p]),
+    "care_self_attn_step": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                    c_void_p, c_void_p, c_void_p, c_void_p]),
+    "care_cross_attn_step": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int,
+                                     c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "care_beam_init": (c_int, [c_void_p, POINTER(BeamState), c_int, c_void_p]),
+    "care_beam_step": (c_int, [c_void_p, POINTER(BeamState), c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p,
+                               c_void_p]),
+    "care_beam_finalize": (c_int, [c_void_p, POINTER(BeamState), c_double, c_int, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            "care_b200: %s is missing - build it with `python -m care_b200.build` "
+            "(there is no CPU or PyTorch fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().care_last_error()
+        raise RuntimeError("care_b200 %s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def ptr(t):
+    """Raw device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

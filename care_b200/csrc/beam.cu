@@ -1,0 +1,381 @@
+// Device-resident beam search (replaces misc/Decoding/Beam.py's per-video Python objects and their
+// per-element device syncs).  One CTA per video and step:
+//   for each live beam row: max and sum-exp over V (log_softmax statistics, Translator.py:127),
+//   candidate value = ((x - max) - log(sum)) + score  (Beam.py:51),  rows ending in <eos> := -1e20 (:52-54),
+//   per-thread register top-(K+1) -> warp shuffle merge -> block merge, ordered by (value desc, flat index asc),
+//   then one thread applies Beam.advance's bookkeeping (:61-85) and maintains the KV-cache ancestry table.
+// The logits row of a beam (<= 59 KB) is read three times (max, sum-exp, select); passes two and three
+// hit L1/L2, so HBM sees each logit once.
+#include <cfloat>
+#include <climits>
+
+#include "common.cuh"
+
+namespace care {
+namespace beam {
+
+constexpr int THREADS = 512;
+constexpr int WARPS = THREADS / 32;
+
+__device__ __forceinline__ bool better(float va, int ia, float vb, int ib) {
+  return va > vb || (va == vb && ia < ib);
+}
+
+template <int KB>
+struct TopList {
+  float v[KB];
+  int i[KB];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int q = 0; q < KB; ++q) {
+      v[q] = -INFINITY;
+      i[q] = INT_MAX;
+    }
+  }
+  // keeps all KB entries sorted best-first (static indexing only: the list lives in registers)
+  __device__ __forceinline__ void insert(float x, int idx) {
+    if (!better(x, idx, v[KB - 1], i[KB - 1])) return;
+#pragma unroll
+    for (int q = KB - 1; q >= 0; --q) {
+      const bool here = better(x, idx, v[q], i[q]);
+      const bool above = (q > 0) && better(x, idx, v[q > 0 ? q - 1 : 0], i[q > 0 ? q - 1 : 0]);
+      if (here) {
+        v[q] = above ? v[q > 0 ? q - 1 : 0] : x;
+        i[q] = above ? i[q > 0 ? q - 1 : 0] : idx;
+      }
+    }
+  }
+  __device__ __forceinline__ void pop() {
+#pragma unroll
+    for (int q = 0; q < KB - 1; ++q) {
+      v[q] = v[q + 1];
+      i[q] = i[q + 1];
+    }
+    v[KB - 1] = -INFINITY;
+    i[KB - 1] = INT_MAX;
+  }
+};
+
+// KB rounds of "best head across the warp"; results land in out_v/out_i (valid in every lane)
+template <int KB>
+__device__ __forceinline__ void warp_merge(TopList<KB>& l, float (&out_v)[KB], int (&out_i)[KB]) {
+#pragma unroll
+  for (int r = 0; r < KB; ++r) {
+    float bv = l.v[0];
+    int bi = l.i[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, bv, bi)) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    out_v[r] = bv;
+    out_i[r] = bi;
+    if (l.i[0] == bi && bi != INT_MAX) l.pop();
+  }
+}
+
+__device__ __forceinline__ float block_reduce(float x, bool is_max, float* red) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  x = is_max ? warp_max(x) : warp_sum(x);
+  __syncthreads();  // protects `red` against the previous use
+  if (lane == 0) red[warp] = x;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int w = 1; w < WARPS; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+
+template <int KB>
+__global__ void __launch_bounds__(THREADS)
+beam_step_kernel(const care_beam_state st, const float* __restrict__ logits, int64_t ldv, int step, int max_len,
+                 float* __restrict__ cand_val, int32_t* __restrict__ cand_idx) {
+  __shared__ float red[WARPS];
+  __shared__ float wl_v[WARPS][KB];
+  __shared__ int wl_i[WARPS][KB];
+  __shared__ float fin_v[KB];
+  __shared__ int fin_i[KB];
+  __shared__ uint8_t old_anc[8 * 64];
+
+  const int v = blockIdx.x;
+  if (st.done[v]) return;
+  const int K = st.K, V = st.V, T = st.T_max;
+  const int nsel = K + 1;  // K winners + runner-up (audit)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  TopList<KB> mine;
+  mine.init();
+  const int n_rows = (step == 1) ? 1 : K;  // Beam.py:56: the first step only looks at beam 0
+  for (int b = 0; b < n_rows; ++b) {
+    const bool killed = (step > 1) && (st.cur_tok[v * K + b] == CARE_EOS);
+    if (killed) {
+      // Beam.py:52-54 sets the whole row to -1e20; under (value desc, index asc) only its first
+      // entries can ever be selected
+      if (tid < KB && tid < V) mine.insert(-1e20f, b * V + tid);
+      continue;
+    }
+    const float* row = logits + ((int64_t)v * K + b) * ldv;
+    const int V4 = V >> 2;
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+    float m = -INFINITY;
+    for (int c = tid; c < V4; c += THREADS) {
+      const float4 x = row4[c];
+      m = fmaxf(fmaxf(m, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
+    }
+    for (int c = V4 * 4 + tid; c < V; c += THREADS) m = fmaxf(m, row[c]);
+    m = block_reduce(m, true, red);
+    float s = 0.f;
+    for (int c = tid; c < V4; c += THREADS) {
+      const float4 x = row4[c];
+      s += expf(x.x - m) + expf(x.y - m) + expf(x.z - m) + expf(x.w - m);
+    }
+    for (int c = V4 * 4 + tid; c < V; c += THREADS) s += expf(row[c] - m);
+    s = block_reduce(s, false, red);
+    const float logsum = logf(s);
+    const float score = (step == 1) ? 0.f : st.scores[v * K + b];
+    const int base = b * V;
+    for (int c = tid; c < V4; c += THREADS) {
+      const float4 x = row4[c];
+      const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float val = (xs[e] - m) - logsum;
+        if (step > 1) val += score;
+        mine.insert(val, base + c * 4 + e);
+      }
+    }
+    for (int c = V4 * 4 + tid; c < V; c += THREADS) {
+      float val = (row[c] - m) - logsum;
+      if (step > 1) val += score;
+      mine.insert(val, base + c);
+    }
+  }
+
+  // ---- merge: warp, then block ---------------------------------------------------------------------
+  float ov[KB];
+  int oi[KB];
+  warp_merge<KB>(mine, ov, oi);
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < KB; ++r) {
+      wl_v[warp][r] = ov[r];
+      wl_i[warp][r] = oi[r];
+    }
+  }
+  // snapshot of the ancestry table (read before anyone overwrites it)
+  for (int idx = tid; idx < K * T; idx += THREADS) old_anc[idx] = st.anc[(int64_t)v * K * T + idx];
+  __syncthreads();
+  if (warp == 0) {
+    TopList<KB> l;
+    l.init();
+    if (lane < WARPS) {
+#pragma unroll
+      for (int r = 0; r < KB; ++r) {
+        l.v[r] = wl_v[lane][r];
+        l.i[r] = wl_i[lane][r];
+      }
+    }
+    warp_merge<KB>(l, ov, oi);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < KB; ++r) {
+        fin_v[r] = ov[r];
+        fin_i[r] = oi[r];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- Beam.advance bookkeeping -----------------------------------------------------------------------
+  // ancestry: new_anc[b'][p] = old_anc[parent(b')][p] for p < step-1, new_anc[b'][step-1] = parent(b')
+  for (int idx = tid; idx < K * T; idx += THREADS) {
+    const int b = idx / T, pp = idx - b * T;
+    const int parent = fin_i[b] / V;
+    uint8_t a = 0;
+    if (pp < step - 1) a = old_anc[parent * T + pp];
+    else if (pp == step - 1) a = (uint8_t)parent;
+    st.anc[(int64_t)v * K * T + idx] = a;
+  }
+  if (tid < K) {
+    const int fi = fin_i[tid];
+    const int parent = fi / V;
+    const int tok = fi - parent * V;
+    st.scores[v * K + tid] = fin_v[tid];
+    st.prev_ks[((int64_t)v * T + (step - 1)) * K + tid] = parent;
+    st.tok_hist[((int64_t)v * (T + 1) + step) * K + tid] = tok;
+    st.cur_tok[v * K + tid] = tok;
+  }
+  if (cand_val != nullptr && tid < nsel) {
+    cand_val[(int64_t)v * nsel + tid] = fin_v[tid];
+    cand_idx[(int64_t)v * nsel + tid] = fin_i[tid];
+  }
+  if (tid == 0) {
+    int count = st.fin_count[v];
+    bool done = false;
+    for (int i = 0; i < K && !done; ++i) {  // Beam.py:72-76
+      const int fi = fin_i[i];
+      const int tok = fi - (fi / V) * V;
+      if (tok == CARE_EOS) {
+        st.fin_score[v * st.need + count] = fin_v[i];
+        st.fin_t[v * st.need + count] = step;
+        st.fin_k[v * st.need + count] = i;
+        ++count;
+        done = count >= st.need;
+      }
+    }
+    if (!done && step + 1 == max_len) {  // Beam.py:79-84
+      done = true;
+      if (count == 0) {
+        for (int i = 0; i < K; ++i) {
+          st.fin_score[v * st.need + count] = fin_v[i];
+          st.fin_t[v * st.need + count] = step;
+          st.fin_k[v * st.need + count] = i;
+          ++count;
+        }
+      }
+    }
+    st.fin_count[v] = count;
+    if (done) {
+      st.done[v] = 1;
+      atomicAdd(st.n_done, 1);
+    }
+  }
+}
+
+__global__ void beam_init_kernel(const care_beam_state st, int bos) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int B = st.B, K = st.K, T = st.T_max;
+  for (int64_t i = i0; i < (int64_t)B * K; i += stride) {
+    st.scores[i] = 0.f;
+    st.cur_tok[i] = bos;
+  }
+  for (int64_t i = i0; i < (int64_t)B * (T + 1) * K; i += stride) {
+    const int64_t pos = (i / K) % (T + 1);
+    st.tok_hist[i] = pos == 0 ? bos : CARE_PAD;
+  }
+  for (int64_t i = i0; i < (int64_t)B * T * K; i += stride) {
+    st.prev_ks[i] = 0;
+    st.anc[i] = 0;
+  }
+  for (int64_t i = i0; i < (int64_t)B * st.need; i += stride) {
+    st.fin_score[i] = 0.f;
+    st.fin_t[i] = 0;
+    st.fin_k[i] = 0;
+  }
+  for (int64_t i = i0; i < B; i += stride) {
+    st.fin_count[i] = 0;
+    st.done[i] = 0;
+  }
+  if (i0 == 0) *st.n_done = 0;
+}
+
+// Translator.collect_hypothesis_and_scores + Beam.sort_finished / get_hypothesis (one thread per video)
+__global__ void beam_finalize_kernel(const care_beam_state st, double alpha, int n_best, int32_t* __restrict__ out_tok,
+                                     int32_t* __restrict__ out_len, float* __restrict__ out_score,
+                                     int32_t* __restrict__ out_t) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= st.B) return;
+  const int K = st.K, T = st.T_max, need = st.need;
+  const int n = st.fin_count[v];
+  bool used[16];
+  for (int i = 0; i < 16; ++i) used[i] = false;
+  for (int r = 0; r < n_best; ++r) {
+    int best = -1;
+    double best_key = 0.0;
+    for (int i = 0; i < n; ++i) {
+      if (used[i]) continue;
+      const double key = (double)st.fin_score[v * need + i] / pow((double)st.fin_t[v * need + i], alpha);
+      if (best < 0 || key > best_key) {  // strict '>' keeps insertion order among ties (stable sort)
+        best = i;
+        best_key = key;
+      }
+    }
+    int32_t* dst = out_tok + ((int64_t)v * n_best + r) * T;
+    for (int j = 0; j < T; ++j) dst[j] = CARE_PAD;
+    if (best < 0) {
+      out_len[v * n_best + r] = 0;
+      out_score[v * n_best + r] = 0.f;
+      out_t[v * n_best + r] = 0;
+      continue;
+    }
+    used[best] = true;
+    const int len = st.fin_t[v * need + best];
+    int k = st.fin_k[v * need + best];
+    for (int j = len - 1; j >= 0; --j) {  // Beam.py:119-132
+      dst[j] = st.tok_hist[((int64_t)v * (T + 1) + j + 1) * K + k];
+      k = st.prev_ks[((int64_t)v * T + j) * K + k];
+    }
+    out_len[v * n_best + r] = len;
+    out_score[v * n_best + r] = st.fin_score[v * need + best];
+    out_t[v * n_best + r] = len;
+  }
+}
+
+static int check_state(const care_beam_state* st, const char* who) {
+  CARE_CHECK_ARG(st != nullptr, "%s: state is NULL", who);
+  CARE_CHECK_ARG(st->B > 0 && st->K >= 1 && st->K <= 8, "%s: K=%d must be in [1,8]", who, st->K);
+  CARE_CHECK_ARG(st->T_max >= 1 && st->T_max <= 64, "%s: T_max=%d must be in [1,64]", who, st->T_max);
+  CARE_CHECK_ARG(st->need >= st->K && st->need <= 16, "%s: need=%d must be in [K,16]", who, st->need);
+  CARE_CHECK_ARG(st->V > st->K, "%s: V=%d too small", who, st->V);
+  CARE_CHECK_ARG(st->scores && st->cur_tok && st->tok_hist && st->prev_ks && st->anc && st->fin_score && st->fin_t &&
+                     st->fin_k && st->fin_count && st->done && st->n_done,
+                 "%s: NULL state buffer", who);
+  return 0;
+}
+
+}  // namespace beam
+}  // namespace care
+
+using namespace care;
+
+extern "C" {
+
+int care_beam_init(care_ctx* ctx, const care_beam_state* st, int bos, void* stream) {
+  CARE_CHECK_ARG(ctx != nullptr, "care_beam_init: ctx is NULL");
+  if (beam::check_state(st, "care_beam_init")) return -1;
+  const int64_t n = (int64_t)st->B * (st->T_max + 1) * st->K;
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
+  beam::beam_init_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*st, bos);
+  CARE_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int care_beam_step(care_ctx* ctx, const care_beam_state* st, const float* logits, int64_t ldv, int step, int max_len,
+                   float* cand_val, int32_t* cand_idx, void* stream) {
+  CARE_CHECK_ARG(ctx && logits, "care_beam_step: bad args");
+  if (beam::check_state(st, "care_beam_step")) return -1;
+  CARE_CHECK_ARG(step >= 1 && step <= st->T_max, "care_beam_step: step=%d outside [1,%d]", step, st->T_max);
+  CARE_CHECK_ARG(ldv % 4 == 0 && ldv >= st->V, "care_beam_step: ldv=%lld must be a multiple of 4 and >= V",
+                 (long long)ldv);
+  CARE_CHECK_ARG((reinterpret_cast<uintptr_t>(logits) & 15) == 0, "care_beam_step: logits must be 16-byte aligned");
+  CARE_CHECK_ARG((cand_val == nullptr) == (cand_idx == nullptr), "care_beam_step: cand_val/cand_idx must go together");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int K = st->K;
+  if (K <= 1)
+    beam::beam_step_kernel<2><<<st->B, beam::THREADS, 0, s>>>(*st, logits, ldv, step, max_len, cand_val, cand_idx);
+  else if (K <= 3)
+    beam::beam_step_kernel<4><<<st->B, beam::THREADS, 0, s>>>(*st, logits, ldv, step, max_len, cand_val, cand_idx);
+  else if (K <= 5)
+    beam::beam_step_kernel<6><<<st->B, beam::THREADS, 0, s>>>(*st, logits, ldv, step, max_len, cand_val, cand_idx);
+  else
+    beam::beam_step_kernel<9><<<st->B, beam::THREADS, 0, s>>>(*st, logits, ldv, step, max_len, cand_val, cand_idx);
+  CARE_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int care_beam_finalize(care_ctx* ctx, const care_beam_state* st, double alpha, int n_best, int32_t* out_tokens,
+                       int32_t* out_len, float* out_score, int32_t* out_t, void* stream) {
+  CARE_CHECK_ARG(ctx && out_tokens && out_len && out_score && out_t && n_best >= 1, "care_beam_finalize: bad args");
+  if (beam::check_state(st, "care_beam_finalize")) return -1;
+  beam::beam_finalize_kernel<<<(st->B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*st, alpha, n_best, out_tokens,
+                                                                                  out_len, out_score, out_t);
+  CARE_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// fp32 parity-mode GEMM: C[M,N] = act(A[M,K] * W[N,K]^T + bias), plain FFMA accumulation in fp32
+// (tcgen05 has no true-fp32 MMA; the bit-exact token parity mode must not round operands to tf32).
+// 128x128x16 CTA tile, 256 threads, 8x8 register micro-tile, k-major smem tiles (transposed on
+// the way in so the inner loop reads conflict-free float4), register double buffering.
+#include "common.cuh"
+
+namespace care {
+namespace f32 {
+
+constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8, THREADS = 256;
+
+template <typename OutT>
+__global__ void __launch_bounds__(THREADS)
+gemm_f32_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ W, int64_t ldw,
+                const float* __restrict__ bias, OutT* __restrict__ C, int64_t ldc, int M, int N, int n_store, int K,
+                int relu) {
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Ws[2][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // global->smem mapping: each thread moves 2 float4 of A and 2 of W per k-tile
+  const int lrow = tid >> 2;        // 0..63
+  const int lk = (tid & 3) * 4;     // 0,4,8,12
+  const int tx = tid & 15, ty = tid >> 4;  // 16x16 thread grid, each 8x8 outputs
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  float4 ra[2], rw[2];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = lrow + h * 64;
+      const int gm = m0 + r, gn = n0 + r, gk = k0 + lk;
+      ra[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rw[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gm < M && gk < K) ra[h] = *reinterpret_cast<const float4*>(A + (int64_t)gm * lda + gk);
+      if (gn < N && gk < K) rw[h] = *reinterpret_cast<const float4*>(W + (int64_t)gn * ldw + gk);
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = lrow + h * 64;
+      As[buf][lk + 0][r] = ra[h].x; As[buf][lk + 1][r] = ra[h].y; As[buf][lk + 2][r] = ra[h].z; As[buf][lk + 3][r] = ra[h].w;
+      Ws[buf][lk + 0][r] = rw[h].x; Ws[buf][lk + 1][r] = rw[h].y; Ws[buf][lk + 2][r] = rw[h].z; Ws[buf][lk + 3][r] = rw[h].w;
+    }
+  };
+
+  const int k_tiles = (K + BK - 1) / BK;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < k_tiles; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < k_tiles) gload((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM], w[TN];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 w0 = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&Ws[buf][k][64 + tx * 4]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    if (kt + 1 < k_tiles) {
+      sstore(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // epilogue: rows {ty*4+i, 64+ty*4+i}, cols {tx*4+j, 64+tx*4+j}
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int row = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (row >= M) continue;
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int col = n0 + jh * 64 + tx * 4;
+      if (col >= n_store) continue;
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float x = acc[i][jh * 4 + j];
+        if (bias != nullptr && col + j < N) x += __ldg(bias + col + j);
+        if (col + j >= N) x = 0.f;
+        o[j] = relu ? fmaxf(x, 0.f) : x;
+      }
+      Act<OutT>::store4(C + (int64_t)row * ldc + col, o);
+    }
+  }
+}
+
+int gemm_f32(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
+             int64_t ldc, int out_dtype, int M, int N, int K, int act, cudaStream_t stream) {
+  CARE_CHECK_ARG(lda % 4 == 0 && ldw % 4 == 0 && K % 4 == 0,
+                 "care_gemm(f32): lda, ldw, K must be multiples of 4 (got %lld, %lld, %d)", (long long)lda,
+                 (long long)ldw, K);
+  CARE_CHECK_ARG(ldc % 4 == 0, "care_gemm(f32): ldc must be a multiple of 4 (got %lld)", (long long)ldc);
+  CARE_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+                 "care_gemm(f32): A, W, C must be 16-byte aligned");
+  const int n_pad = (N + 3) & ~3;
+  CARE_CHECK_ARG(n_pad <= ldc, "care_gemm(f32): ldc %lld too small for N=%d", (long long)ldc, N);
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  if (out_dtype == CARE_F32)
+    gemm_f32_kernel<float><<<grid, THREADS, 0, stream>>>((const float*)A, lda, (const float*)W, ldw, bias, (float*)C,
+                                                         ldc, M, N, n_pad, K, act == CARE_ACT_RELU);
+  else
+    gemm_f32_kernel<__nv_bfloat16><<<grid, THREADS, 0, stream>>>((const float*)A, lda, (const float*)W, ldw, bias,
+                                                                 (__nv_bfloat16*)C, ldc, M, N, n_pad, K,
+                                                                 act == CARE_ACT_RELU);
+  CARE_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+}  // namespace f32
+
+namespace tc {
+int gemm_bf16(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
+              int64_t ldc, int out_dtype, int M, int N, int K, int act, cudaStream_t stream);
+}
+}  // namespace care
+
+extern "C" int care_gemm(care_ctx* ctx, int dtype, const void* A, int64_t lda, const void* W, int64_t ldw,
+                         const float* bias, void* C, int64_t ldc, int out_dtype, int M, int N, int K, int act,
+                         void* stream) {
+  CARE_CHECK_ARG(ctx != nullptr, "care_gemm: ctx is NULL");
+  CARE_CHECK_ARG(A && W && C, "care_gemm: NULL operand");
+  CARE_CHECK_ARG(M > 0 && N > 0 && K > 0, "care_gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  CARE_CHECK_ARG(out_dtype == CARE_F32 || out_dtype == CARE_BF16, "care_gemm: bad out_dtype %d", out_dtype);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == CARE_F32) return care::f32::gemm_f32(ctx, A, lda, W, ldw, bias, C, ldc, out_dtype, M, N, K, act, s);
+  if (dtype == CARE_BF16) return care::tc::gemm_bf16(ctx, A, lda, W, ldw, bias, C, ldc, out_dtype, M, N, K, act, s);
+  care::set_error("care_gemm: bad dtype %d", dtype);
+  return -1;
+}

@@ -1,0 +1,375 @@
+// bf16 GEMM on the 5th-gen tensor cores: C[M,N] = act(A[M,K] * W[N,K]^T + bias).
+//
+// Both operands are K-major (activations row-major [M,K], nn.Linear weights [N,K]), i.e. the
+// canonical "TN" GEMM.  Persistent, warp-specialised, one CTA per SM:
+//   warp 0  : TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B tiles, 4-8 stage mbarrier ring)
+//   warp 1  : MMA issuer     (one lane issues tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16)
+//   warp 2  : TMEM allocator (2 accumulator stages x BN fp32 columns)
+//   warps 4-7: epilogue      (tcgen05.ld 32x32b -> +bias/ReLU -> smem transpose -> coalesced 16 B stores)
+// The accumulator is double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Edges: TMA zero-fills out-of-bounds rows/columns of A and W; stores are predicated.
+#include "common.cuh"
+
+namespace care {
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARPS = 4;
+constexpr int EPI_PITCH = 144;  // bytes per staged row: 32 fp32 + 16 B pad (conflict-free v4 access)
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start address >> 4 in [0,14), LBO in [16,30) (unused for swizzled K-major, canonical value 1),
+// SBO = 1024 B (8 rows x 128 B) in [32,46), version 1 in [46,48), layout SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t sw128_kmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (1 << 4), A bf16 (1 << 7), B bf16 (1 << 10),
+// both K-major (bits 15/16 zero), N >> 3 in [17,23), M >> 4 in [24,29).
+__host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+template <int BN, typename OutT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                         const float* __restrict__ bias, OutT* __restrict__ C, int64_t ldc, int M, int N,
+                         int n_store, int K, int relu) {
+  using cfg = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - raw_addr);
+  const uint32_t epi_base = smem_base + cfg::STAGES * cfg::STAGE_BYTES;
+  const uint32_t bar_base = epi_base + cfg::EPI_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (cfg::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * cfg::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * cfg::STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * cfg::STAGES + 4);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"(static_cast<uint32_t>(cfg::TMEM_COLS))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % cfg::STAGES;
+          const uint32_t ph = (it / cfg::STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), cfg::STAGE_BYTES);
+          const uint32_t a_dst = smem_base + s * cfg::STAGE_BYTES;
+          tma_load_2d(a_dst, &tma_a, full_bar(s), kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(a_dst + cfg::A_BYTES, &tma_b, full_bar(s), kb * BLOCK_K, n_blk * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = instr_desc_bf16(BLOCK_M, BN);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % cfg::STAGES;
+          const uint32_t ph = (it / cfg::STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + s * cfg::STAGE_BYTES;
+          const uint64_t adesc = sw128_kmajor_desc(a_addr);
+          const uint64_t bdesc = sw128_kmajor_desc(a_addr + cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 32 bytes (16 bf16) inside the 128-byte swizzle atom: +2 in the >>4 address field
+            tc_mma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(empty_bar(s));  // frees the smem slot once these MMAs have read it
+        }
+        tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> (+bias, ReLU) -> smem transpose -> coalesced global stores =====
+    const int ew = warp - 4;  // == warp % 4: this warp may access TMEM lanes [32*ew, 32*ew+32)
+    uint8_t* stage_gen = smem_gen + (epi_base - smem_base) + ew * 32 * EPI_PITCH;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+      const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), aph);
+      tc_fence_after();
+      const int row_base = m_blk * BLOCK_M + ew * 32;
+      if (row_base < M) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = n_blk * BN + c * 32;
+          if (col0 >= n_store) break;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + c * 32, v);
+          float bl = 0.f;
+          if (bias != nullptr && col0 + lane < N) bl = __ldg(bias + col0 + lane);
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bl, j);
+            f[j] = relu ? fmaxf(x, 0.f) : x;
+          }
+          __syncwarp();
+          if constexpr (sizeof(OutT) == 4) {
+            float4* dst = reinterpret_cast<float4*>(stage_gen + lane * EPI_PITCH);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + (lane >> 3), ch = lane & 7;
+              const float4 val = *reinterpret_cast<const float4*>(stage_gen + r * EPI_PITCH + ch * 16);
+              const int row = row_base + r, col = col0 + ch * 4;
+              if (row < M && col < n_store)
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(C) + static_cast<int64_t>(row) * ldc + col) = val;
+            }
+          } else {
+            constexpr int PITCH16 = 80;  // 32 bf16 = 64 B + 16 B pad
+            uint4* dst = reinterpret_cast<uint4*>(stage_gen + lane * PITCH16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 pk;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
+              dst[j] = pk;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = i * 8 + (lane >> 2), ch = lane & 3;
+              const uint4 val = *reinterpret_cast<const uint4*>(stage_gen + r * PITCH16 + ch * 16);
+              const int row = row_base + r, col = col0 + ch * 8;
+              if (row < M && col < n_store)
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(C) + static_cast<int64_t>(row) * ldc + col) =
+                    val;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(cfg::TMEM_COLS))
+                 : "memory");
+  }
+}
+
+static int get_tmap(care_ctx* ctx, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                    CUtensorMap* out) {
+  TmapKey key{ptr, rows, cols, ld, box_rows, (uint32_t)BLOCK_K};
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    auto it = ctx->tmaps.find(key);
+    if (it != ctx->tmaps.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  CUtensorMap m;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ctx->encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%llu cols=%llu ld=%llu box_rows=%u", (int)r, ptr,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+    return (int)r;
+  }
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (ctx->tmaps.size() > 4096) ctx->tmaps.clear();
+    ctx->tmaps[key] = m;
+  }
+  *out = m;
+  return 0;
+}
+
+template <int BN, typename OutT>
+static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, void* C, int64_t ldc,
+                  int M, int N, int n_store, int K, int act, cudaStream_t stream) {
+  using cfg = Cfg<BN>;
+  static bool configured = false;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, OutT>;
+  if (!configured) {
+    CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + BN - 1) / BN;
+  const int grid = std::min(m_tiles * n_tiles, ctx->sm_count);
+  kern<<<grid, NUM_THREADS, cfg::SMEM_BYTES, stream>>>(ta, tb, bias, reinterpret_cast<OutT*>(C), ldc, M, N, n_store, K,
+                                                       act == CARE_ACT_RELU ? 1 : 0);
+  CARE_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int gemm_bf16(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
+              int64_t ldc, int out_dtype, int M, int N, int K, int act, cudaStream_t stream) {
+  CARE_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0, "care_gemm(bf16): lda/ldw must be multiples of 8 (got %lld, %lld)",
+                 (long long)lda, (long long)ldw);
+  CARE_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+                 "care_gemm(bf16): A, W, C must be 16-byte aligned");
+  CARE_CHECK_ARG(ldc % 8 == 0, "care_gemm(bf16): ldc must be a multiple of 8 (got %lld)", (long long)ldc);
+  const int n_pad = (N + 7) & ~7;
+  CARE_CHECK_ARG(n_pad <= ldc || N % 8 == 0, "care_gemm(bf16): ldc %lld too small for N=%d", (long long)ldc, N);
+  const int n_store = n_pad <= ldc ? n_pad : N;
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  auto tiles = [&](int bn) { return m_tiles * ((N + bn - 1) / bn); };
+  int bn = 256;
+  if (tiles(256) < ctx->sm_count) bn = 128;
+  if (bn == 128 && tiles(128) < ctx->sm_count) bn = 64;
+  CUtensorMap ta, tb;
+  int rc = get_tmap(ctx, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BLOCK_M, &ta);
+  if (rc) return rc;
+  rc = get_tmap(ctx, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn, &tb);
+  if (rc) return rc;
+#define CARE_TC_DISPATCH(BN_)                                                                          \
+  (out_dtype == CARE_F32 ? launch<BN_, float>(ctx, ta, tb, bias, C, ldc, M, N, n_store, K, act, stream) \
+                         : launch<BN_, __nv_bfloat16>(ctx, ta, tb, bias, C, ldc, M, N, n_store, K, act, stream))
+  if (bn == 256) return CARE_TC_DISPATCH(256);
+  if (bn == 128) return CARE_TC_DISPATCH(128);
+  return CARE_TC_DISPATCH(64);
+#undef CARE_TC_DISPATCH
+}
+
+}  // namespace tc
+}  // namespace care

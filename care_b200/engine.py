@@ -1,0 +1,399 @@
+"""Host-side driver of the CUDA hot path: weight preparation, workspaces and the launch sequence.
+
+PyTorch is plumbing here (device memory, streams); every arithmetic step is a call into
+libcare_b200.so through the C ABI (care_b200/_lib.py).  There is no fallback path.
+
+Precision modes
+  "fp32": activations/weights fp32, SIMT FFMA GEMMs - the bit-exact token parity mode.
+  "bf16": activations/weights bf16, tcgen05 GEMMs with fp32 accumulation; LayerNorm / softmax
+          statistics, logits and beam scores stay fp32.
+"""
+import ctypes
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_RELU, BF16, F32, BeamState, check, ptr
+
+PAD, UNK, BOS, EOS, MASK, VIS = 0, 1, 2, 3, 4, 5  # reference: config/Constants.py:1-6
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class CareEngine:
+    """One engine per (model, device, precision)."""
+
+    def __init__(self, opt: dict, state_dict: Dict[str, torch.Tensor], device, precision: str = "bf16"):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("care_b200 runs on CUDA devices only (no CPU path)")
+        self.opt = dict(opt)
+        self.precision = precision
+        self.dt = F32 if precision == "fp32" else BF16
+        self.tdtype = torch.float32 if precision == "fp32" else torch.bfloat16
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", index)
+        handle = ctypes.c_void_p()
+        check(self.lib.care_ctx_create(ctypes.byref(handle), index), "care_ctx_create")
+        self.ctx = handle
+        self.d = opt["dim_hidden"]
+        self.H = opt["num_attention_heads"]
+        self.F = opt["intermediate_size"]
+        self.V = opt["vocab_size"]
+        self.eps = float(opt["layer_norm_eps"])
+        self.modality = opt["modality"]
+        self.m_dec = opt.get("modality_for_decoder") or self.modality
+        self.m_pred = opt.get("modality_for_predictor") or self.modality
+        self.max_len = opt.get("max_len", 30)
+        self.ldv = _round_up(self.V, 8)
+        self._ws = {}
+        self._prepare_weights(state_dict)
+
+    def __del__(self):
+        try:
+            if getattr(self, "ctx", None):
+                self.lib.care_ctx_destroy(self.ctx)
+                self.ctx = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    # weights
+    # ------------------------------------------------------------------------------------------
+    def _prepare_weights(self, sd):
+        dev, T = self.device, self.tdtype
+        opt, d = self.opt, self.d
+
+        def f32(name):
+            return sd[name].detach().to(dev, torch.float32).contiguous()
+
+        def mat(t, pad_k=None):
+            t = t.detach().to(dev, torch.float32)
+            if pad_k is not None and t.shape[1] != pad_k:
+                t = torch.nn.functional.pad(t, (0, pad_k - t.shape[1]))
+            return t.to(T).contiguous()
+
+        w = {}
+        self.highway = opt["encoder"] == "EncoderWithHighWayBN"
+        if opt["encoder"] not in ("Embedder", "EncoderWithHighWayBN"):
+            raise ValueError("encoder %r is outside the accelerated hot path" % opt["encoder"])
+        self.streams = []
+        for ch in self.modality:
+            p = "encoder.Encoder_%s" % ch.upper()
+            s = dict(ch=ch, W=mat(sd[p + ".0.weight"]), b=f32(p + ".0.bias"), dim=opt["dim_" + ch])
+            if self.highway:
+                s.update(W1=mat(sd[p + ".1.w1.weight"]), b1=f32(p + ".1.w1.bias"),
+                         W2=mat(sd[p + ".1.w2.weight"]), b2=f32(p + ".1.w2.bias"),
+                         bn_mean=f32(p + ".2.bn.running_mean"), bn_var=f32(p + ".2.bn.running_var"),
+                         bn_w=f32(p + ".2.bn.weight"), bn_b=f32(p + ".2.bn.bias"))
+            else:
+                s.update(g=f32(p + ".1.weight"), beta=f32(p + ".1.bias"))
+            self.streams.append(s)
+
+        # predictor nets, ordered as the reference builds them (models/Predictor/__init__.py:26-60)
+        nets = [c for c in opt["crits"] if c != "lang"] + list(opt.get("predictors_to_be_added", []))
+        if opt.get("load_teacher_weights", False) and "length" in nets:
+            nets.remove("length")
+            nets.append("length")
+        self.nets = nets
+        self.n_attr = opt.get("attribute_prediction_k", 0)
+        self.n_concepts = opt.get("use_attr_topk", 0) if "SemanticContainer" in nets else 0
+        for i, kind in enumerate(nets):
+            p = "predictor.nets.%d" % i
+            if kind == "attribute":
+                if not (opt.get("attribute_prediction_channel_concat") and opt.get("attribute_prediction_mean_pooling")):
+                    raise ValueError("only the mean-pooling + channel-concat concept head is accelerated")
+                w["prj_W"] = mat(sd[p + ".prj.weight"])
+                w["prj_b"] = f32(p + ".prj.bias")
+            elif kind == "SemanticContainer":
+                w["attr_word"] = f32(p + ".attr_embs.word_embeddings.weight")
+                w["attr_pos"] = f32(p + ".attr_embs.position_embeddings.weight")
+                w["attr_g"] = f32(p + ".attr_embs.LayerNorm.weight")
+                w["attr_b"] = f32(p + ".attr_embs.LayerNorm.bias")
+                if "emb" in opt.get("use_attr_type", ""):
+                    w["s2h_W"] = mat(sd[p + ".semantic2hidden.weight"], pad_k=_round_up(self.n_attr, 64))
+            elif kind == "length":
+                w["len_W0"] = mat(sd[p + ".net.0.weight"]); w["len_b0"] = f32(p + ".net.0.bias")
+                w["len_W3"] = mat(sd[p + ".net.3.weight"]); w["len_b3"] = f32(p + ".net.3.bias")
+            else:
+                raise ValueError("predictor %r is outside the accelerated hot path" % kind)
+        self.use_gsg = "s2h_W" in w
+        self.concat_concepts = "concat" in opt.get("use_attr_type", "") and self.n_concepts > 0
+
+        e = "decoder.embedding"
+        w["word"] = f32(e + ".word_embeddings.weight")
+        w["pos"] = f32(e + ".position_embeddings.weight")
+        w["emb_g"] = f32(e + ".LayerNorm.weight")
+        w["emb_b"] = f32(e + ".LayerNorm.bias")
+        L = "decoder.layers.0."
+        ia, xa = L + "intra_attention.", L + "inter_attention."
+        w["Wqkv"] = mat(torch.cat([sd[ia + "SDPA.query.weight"], sd[ia + "SDPA.key.weight"],
+                                   sd[ia + "SDPA.value.weight"]], 0))
+        w["bqkv"] = torch.cat([f32(ia + "SDPA.query.bias"), f32(ia + "SDPA.key.bias"), f32(ia + "SDPA.value.bias")])
+        w["Wo"] = mat(sd[ia + "dense.weight"]); w["bo"] = f32(ia + "dense.bias")
+        w["ln1_g"] = f32(ia + "LayerNorm.weight"); w["ln1_b"] = f32(ia + "LayerNorm.bias")
+        w["Wxq"] = mat(sd[xa + "SDPA.query.weight"]); w["bxq"] = f32(xa + "SDPA.query.bias")
+        w["Wxkv"] = mat(torch.cat([sd[xa + "SDPA.key.weight"], sd[xa + "SDPA.value.weight"]], 0))
+        w["bxkv"] = torch.cat([f32(xa + "SDPA.key.bias"), f32(xa + "SDPA.value.bias")])
+        w["Wxo"] = mat(sd[xa + "dense.weight"]); w["bxo"] = f32(xa + "dense.bias")
+        w["ln2_g"] = f32(xa + "LayerNorm.weight"); w["ln2_b"] = f32(xa + "LayerNorm.bias")
+        hb = xa + "SDPA.hybrid_bias"
+        w["hybrid_bias"] = f32(hb) if hb in sd else None
+        w["W1"] = mat(sd[L + "ffn.dense1.weight"]); w["b1"] = f32(L + "ffn.dense1.bias")
+        w["W2"] = mat(sd[L + "ffn.dense2.weight"]); w["b2"] = f32(L + "ffn.dense2.bias")
+        w["ln3_g"] = f32(L + "ffn.LayerNorm.weight"); w["ln3_b"] = f32(L + "ffn.LayerNorm.bias")
+        w["Wvocab"] = mat(sd["cls_head.tgt_word_prj.weight"])
+        self.w = w
+
+        # memory layout: decoder modalities in modality order, then the concept embeddings
+        self.frames = {ch: (opt.get("retrieval_topk", 20) if ch == "r" else opt["n_frames"]) for ch in self.modality}
+        off = 0
+        self.mem_off = {}
+        for ch in self.modality:
+            if ch in self.m_dec:
+                self.mem_off[ch] = off
+                off += self.frames[ch]
+        self.enc_len = off
+        self.Lm = off + (self.n_concepts if self.concat_concepts else 0)
+        if w["hybrid_bias"] is not None and w["hybrid_bias"].shape[1] != self.Lm:
+            raise ValueError("hybrid_bias length %d != memory length %d" % (w["hybrid_bias"].shape[1], self.Lm))
+
+    # ------------------------------------------------------------------------------------------
+    # helpers
+    # ------------------------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _buf(self, name, shape, dtype):
+        key = (name, tuple(shape), dtype)
+        t = self._ws.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._ws[key] = t
+        return t
+
+    def free_workspaces(self):
+        self._ws.clear()
+
+    def launch_count(self):
+        return int(self.lib.care_ctx_launch_count(self.ctx))
+
+    def gemm(self, A, W, bias, C, M, N, K, act=ACT_NONE, lda=None, ldc=None):
+        out_dt = F32 if C.dtype == torch.float32 else BF16
+        check(self.lib.care_gemm(self.ctx, self.dt, ptr(A), lda if lda is not None else A.stride(-2), ptr(W),
+                                 W.stride(0), ptr(bias), ptr(C), ldc if ldc is not None else C.stride(-2), out_dt,
+                                 M, N, K, act, self._stream()), "care_gemm")
+
+    # ------------------------------------------------------------------------------------------
+    # encoding phase  (reference: models/Framework.py:150-187)
+    # ------------------------------------------------------------------------------------------
+    def encode(self, feats: List[torch.Tensor]) -> Dict[str, torch.Tensor]:
+        opt, d, T, w = self.opt, self.d, self.tdtype, self.w
+        feats = feats[:len(self.modality)]
+        B = feats[0].shape[0]
+        st = self._stream()
+        lib, ctx, dt = self.lib, self.ctx, self.dt
+        n_pred = len([c for c in self.modality if c in self.m_pred])
+        has_attr = "attribute" in self.nets
+        memory = torch.empty((B, self.Lm, d), dtype=T, device=self.device)
+        means = self._buf("means", (B, max(n_pred, 1) * d), T) if has_attr or "length" in self.nets else None
+        pred_slot = 0
+        pred_tokens = []
+        for s, x in zip(self.streams, feats):
+            ch, Tn, dim = s["ch"], x.shape[1], s["dim"]
+            if x.dtype != torch.float32 or not x.is_contiguous():
+                x = x.to(torch.float32).contiguous()
+            rows = B * Tn
+            if self.dt == BF16:
+                a = self._buf("feat_bf16", (rows, dim), torch.bfloat16)
+                check(lib.care_cast_f32_bf16(ctx, ptr(x), ptr(a), rows * dim, st), "care_cast_f32_bf16")
+            else:
+                a = x.view(rows, dim)
+            h32 = self._buf("enc_h32", (rows, d), torch.float32)
+            self.gemm(a, s["W"], s["b"], h32, rows, d, dim)
+            in_dec, in_pred = ch in self.m_dec, ch in self.m_pred and means is not None
+            out_ptr = ptr(memory) if in_dec else None
+            mean_ptr = ptr(means) if in_pred else None
+            if self.highway:
+                if self.dt == BF16:
+                    hT = self._buf("enc_hT", (rows, d), torch.bfloat16)
+                    check(lib.care_cast_f32_bf16(ctx, ptr(h32), ptr(hT), rows * d, st), "care_cast_f32_bf16")
+                else:
+                    hT = h32
+                y32 = self._buf("enc_y32", (rows, d), torch.float32)
+                g32 = self._buf("enc_g32", (rows, d), torch.float32)
+                self.gemm(hT, s["W1"], s["b1"], y32, rows, d, d)
+                self.gemm(hT, s["W2"], s["b2"], g32, rows, d, d)
+                check(lib.care_encoder_highway_bn_mean(
+                    ctx, dt, ptr(h32), ptr(y32), ptr(g32), ptr(s["bn_mean"]), ptr(s["bn_var"]), ptr(s["bn_w"]),
+                    ptr(s["bn_b"]), 1e-5, B, Tn, d, out_ptr, self.Lm, self.mem_off.get(ch, 0), mean_ptr,
+                    n_pred * d, pred_slot * d, st), "care_encoder_highway_bn_mean")
+            else:
+                check(lib.care_encoder_ln_mean(
+                    ctx, dt, ptr(h32), ptr(s["g"]), ptr(s["beta"]), self.eps, B, Tn, d, out_ptr, self.Lm,
+                    self.mem_off.get(ch, 0), mean_ptr, n_pred * d, pred_slot * d, st), "care_encoder_ln_mean")
+            if in_pred:
+                pred_slot += 1
+                pred_tokens.append(Tn)
+        out = {"encoder_hidden_states": memory}
+        if has_attr:
+            ld_sc = _round_up(self.n_attr, 8)
+            scores = self._buf("attr_scores", (B, ld_sc), torch.float32)
+            self.gemm(means, w["prj_W"], w["prj_b"], scores, B, self.n_attr, n_pred * d)
+            preds = torch.empty((B, self.n_attr), dtype=torch.float32, device=self.device)
+            out["preds_attr"] = preds
+            if "SemanticContainer" in self.nets:
+                kpad = w["s2h_W"].shape[1] if self.use_gsg else _round_up(self.n_attr, 64)
+                predsT = self._buf("preds_T", (B, kpad), T)
+                labels = torch.empty((B, self.n_concepts), dtype=torch.int64, device=self.device)
+                check(lib.care_concept_head(
+                    ctx, dt, ptr(scores), ld_sc, B, self.n_attr, self.n_concepts, ptr(w["attr_word"]),
+                    ptr(w["attr_pos"]), ptr(w["attr_g"]), ptr(w["attr_b"]), self.eps, d, ptr(preds), ptr(predsT),
+                    kpad, ptr(labels), ptr(memory) if self.concat_concepts else None, self.Lm, self.enc_len, st),
+                    "care_concept_head")
+                out["semantic_labels"] = labels
+                if self.use_gsg:
+                    gsg = torch.empty((B, d), dtype=torch.float32, device=self.device)
+                    self.gemm(predsT, w["s2h_W"], None, gsg, B, d, kpad)
+                    out["semantic_hidden_states"] = gsg
+            else:
+                check(lib.care_concept_head(
+                    ctx, dt, ptr(scores), ld_sc, B, self.n_attr, 1, None, None, None, None, self.eps, d, ptr(preds),
+                    None, 0, None, None, 0, 0, st), "care_concept_head")
+        if "length" in self.nets:
+            # Predictor_length (pred_length.py:14-22): mean over all predictor tokens, then a 2-layer MLP.
+            out["preds_length_logits"] = self._length_logits(B, means, pred_tokens, n_pred)
+        return out
+
+    def _length_logits(self, B, means, pred_tokens, n_pred):
+        raise NotImplementedError("the NACF length head lands with the mask-predict path")
+
+    def cross_kv(self, memory):
+        """K/V of the cross-attention memory, projected once per video (hoisted out of the step loop)."""
+        B = memory.shape[0]
+        kv = torch.empty((B, self.Lm, 2 * self.d), dtype=self.tdtype, device=self.device)
+        self.gemm(memory.view(B * self.Lm, self.d), self.w["Wxkv"], self.w["bxkv"], kv.view(B * self.Lm, 2 * self.d),
+                  B * self.Lm, 2 * self.d, self.d)
+        return kv
+
+    # ------------------------------------------------------------------------------------------
+    # auto-regressive beam decode  (reference: models/Translator.py:35-220 + misc/Decoding/Beam.py)
+    # ------------------------------------------------------------------------------------------
+    def _beam_buffers(self, B, K, need):
+        Tm = self.max_len - 1
+        dev = self.device
+        i32 = torch.int32
+        bufs = dict(
+            scores=self._buf("bs_scores", (B, K), torch.float32),
+            cur_tok=self._buf("bs_cur", (B * K,), i32),
+            tok_hist=self._buf("bs_hist", (B, Tm + 1, K), i32),
+            prev_ks=self._buf("bs_prev", (B, Tm, K), i32),
+            anc=self._buf("bs_anc", (B, K, Tm), torch.uint8),
+            fin_score=self._buf("bs_fs", (B, need), torch.float32),
+            fin_t=self._buf("bs_ft", (B, need), i32),
+            fin_k=self._buf("bs_fk", (B, need), i32),
+            fin_count=self._buf("bs_fc", (B,), i32),
+            done=self._buf("bs_done", (B,), i32),
+            n_done=self._buf("bs_nd", (1,), i32),
+        )
+        st = BeamState(B=B, K=K, T_max=Tm, V=self.V, need=need, **{k: ptr(v) for k, v in bufs.items()})
+        return bufs, st
+
+    def decode_step(self, t, B, K, enc, kv, bufs, bst, audit=None):
+        """One beam step (len_input_ids == t) for every video; 14 kernel launches."""
+        lib, ctx, dt, w, d, T = self.lib, self.ctx, self.dt, self.w, self.d, self.tdtype
+        st = self._stream()
+        R = B * K
+        Tm = self.max_len - 1
+        cache = self._buf("kv_cache", (Tm, R, 3 * d), T)
+        x0 = self._buf("x0", (R, d), T); x1 = self._buf("x1", (R, d), T)
+        x2 = self._buf("x2", (R, d), T); x3 = self._buf("x3", (R, d), T)
+        cx = self._buf("ctx", (R, d), T); qc = self._buf("qc", (R, d), T)
+        y32 = self._buf("y32", (R, d), torch.float32)
+        hb = self._buf("ffn_h", (R, self.F), T)
+        logits = self._buf("logits", (R, self.ldv), torch.float32)
+        gsg = enc.get("semantic_hidden_states")
+        done = ptr(bufs["done"])
+        check(lib.care_embed_ln(ctx, dt, ptr(bufs["cur_tok"]), None, t - 1, ptr(w["word"]), ptr(w["pos"]), None,
+                                ptr(gsg), K, ptr(w["emb_g"]), ptr(w["emb_b"]), self.eps, R, d, ptr(x0), st),
+              "care_embed_ln")
+        self.gemm(x0, w["Wqkv"], w["bqkv"], cache[t - 1], R, 3 * d, d)
+        check(lib.care_self_attn_step(ctx, dt, ptr(cache), t, B, K, self.H, d, ptr(bufs["anc"]), Tm,
+                                      ptr(bufs["tok_hist"]), done, ptr(cx), st), "care_self_attn_step")
+        self.gemm(cx, w["Wo"], w["bo"], y32, R, d, d)
+        check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x0), ptr(w["ln1_g"]), ptr(w["ln1_b"]), self.eps, R, d, ptr(x1),
+                              st), "care_add_ln")
+        self.gemm(x1, w["Wxq"], w["bxq"], qc, R, d, d)
+        check(lib.care_cross_attn_step(ctx, dt, ptr(qc), d, ptr(kv), self.Lm, B, K, self.H, d, ptr(w["hybrid_bias"]),
+                                       done, ptr(cx), st), "care_cross_attn_step")
+        self.gemm(cx, w["Wxo"], w["bxo"], y32, R, d, d)
+        check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x1), ptr(w["ln2_g"]), ptr(w["ln2_b"]), self.eps, R, d, ptr(x2),
+                              st), "care_add_ln")
+        self.gemm(x2, w["W1"], w["b1"], hb, R, self.F, d, act=ACT_RELU)
+        self.gemm(hb, w["W2"], w["b2"], y32, R, d, self.F)
+        check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x2), ptr(w["ln3_g"]), ptr(w["ln3_b"]), self.eps, R, d, ptr(x3),
+                              st), "care_add_ln")
+        self.gemm(x3, w["Wvocab"], None, logits, R, self.V, d)
+        cv = ci = None
+        if audit is not None:
+            cv, ci = audit
+        check(lib.care_beam_step(ctx, ctypes.byref(bst), ptr(logits), self.ldv, t, self.max_len, ptr(cv), ptr(ci),
+                                 st), "care_beam_step")
+        return logits
+
+    def ar_decode(self, enc, B, beam_size=5, topk=1, beam_alpha=1.0, early_exit_every=4, trace=None,
+                  trace_logits=False):
+        """Runs the whole beam search on device; returns padded int32 ids, lengths, raw scores, steps
+        (device tensors).  `trace` (a list, tests only) receives per-step snapshots of the beam state."""
+        K = beam_size
+        need = max(K, topk)
+        lib, ctx = self.lib, self.ctx
+        st = self._stream()
+        kv = self.cross_kv(enc["encoder_hidden_states"])
+        bufs, bst = self._beam_buffers(B, K, need)
+        check(lib.care_beam_init(ctx, ctypes.byref(bst), BOS, st), "care_beam_init")
+        for t in range(1, self.max_len):
+            audit = None
+            if trace is not None:
+                audit = (torch.empty((B, K + 1), dtype=torch.float32, device=self.device),
+                         torch.empty((B, K + 1), dtype=torch.int32, device=self.device))
+                pre = {k: bufs[k].cpu().clone() for k in ("anc", "tok_hist", "done", "scores", "cur_tok")}
+            logits = self.decode_step(t, B, K, enc, kv, bufs, bst, audit)
+            if trace is not None:
+                trace.append(dict(step=t, pre=pre, cand_val=audit[0].cpu(), cand_idx=audit[1].cpu(),
+                                  logits=logits[:, :self.V].cpu().clone() if trace_logits else None))
+            if early_exit_every and t % early_exit_every == 0 and t < self.max_len - 1:
+                if int(bufs["n_done"].item()) == B:
+                    break
+        Tm = self.max_len - 1
+        out_tok = torch.empty((B, topk, Tm), dtype=torch.int32, device=self.device)
+        out_len = torch.empty((B, topk), dtype=torch.int32, device=self.device)
+        out_score = torch.empty((B, topk), dtype=torch.float32, device=self.device)
+        out_t = torch.empty((B, topk), dtype=torch.int32, device=self.device)
+        check(lib.care_beam_finalize(ctx, ctypes.byref(bst), float(beam_alpha), topk, ptr(out_tok), ptr(out_len),
+                                     ptr(out_score), ptr(out_t), st), "care_beam_finalize")
+        return out_tok, out_len, out_score, out_t
+
+
+def hyps_from_device(out_tok, out_len, out_score, out_t, beam_alpha, topk):
+    """Host-side tail of Translator.collect_hypothesis_and_scores (models/Translator.py:211-220):
+    scores are `float(score) / t ** alpha` in Python double precision (Beam.py:91-101), and the
+    reference's n_best carry-over between videos (Translator.py:215) is reproduced."""
+    tok = out_tok.cpu().tolist()
+    ln = out_len.cpu().tolist()
+    sc = out_score.cpu().tolist()
+    tt = out_t.cpu().tolist()
+    hyps, scores = [], []
+    n_best = topk
+    for v in range(len(tok)):
+        avail = sum(1 for x in ln[v] if x > 0)
+        n_best = min(n_best, avail)
+        hyps.append([tok[v][r][:ln[v][r]] for r in range(n_best)])
+        scores.append([sc[v][r] / tt[v][r] ** beam_alpha for r in range(n_best)])
+    return hyps, scores

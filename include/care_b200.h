@@ -1,0 +1,171 @@
+/*
+ * care_b200 — C ABI of the B200-native CARE caption-decode hot path.
+ *
+ * The reference (yangbang18/CARE) is pure Python/PyTorch: it has no FFI of its own.  The
+ * boundary this library replaces is therefore the set of PyTorch calls the reference issues on
+ * its inference path; each entry point below names the reference lines it stands in for
+ * (paths relative to the reference tree).  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: raw device pointers + explicit sizes/strides, no torch types.
+ *   - the caller (PyTorch on the host side) allocates and owns every buffer; the library never
+ *     frees or keeps a pointer beyond the call, except TMA descriptors cached inside the ctx.
+ *   - every call only enqueues work on the caller's stream (`stream` is a cudaStream_t passed
+ *     as void*); there is no hidden device synchronisation.
+ *   - return value: 0 = ok, negative = argument/shape error, positive = cudaError_t / CUresult;
+ *     care_last_error() returns a thread-local message.
+ *   - dtype codes: CARE_F32 = 0, CARE_BF16 = 1.  "T" below means the activation type of the
+ *     precision mode (fp32 in the bit-exact parity mode, bf16 in the throughput mode).
+ *   - rows of decoder-side tensors are ordered (video, beam): row = video * K + beam.
+ *   - sm_100a only.  There is no CPU path: every entry point fails if no device is present.
+ */
+#ifndef CARE_B200_H_
+#define CARE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CARE_F32 0
+#define CARE_BF16 1
+
+#define CARE_ACT_NONE 0
+#define CARE_ACT_RELU 1
+
+#define CARE_PAD 0 /* config/Constants.py:1-6 */
+#define CARE_BOS 2
+#define CARE_EOS 3
+#define CARE_MASK 4
+#define CARE_VIS 5
+
+typedef struct care_ctx care_ctx;
+
+/* library plumbing ------------------------------------------------------------------------- */
+int care_version(void);
+const char* care_last_error(void);
+int care_ctx_create(care_ctx** out, int device);
+void care_ctx_destroy(care_ctx* ctx);
+int care_ctx_sm_count(const care_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches claim) */
+int64_t care_ctx_launch_count(const care_ctx* ctx);
+
+/* C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) — every nn.Linear on the path:
+ * Encoder.py:165-168 (Embedder Linear), Attention.py:53-67 (query/key/value),
+ * SubLayers.py:33-38 (dense), SubLayers.py:126-135 (dense1/dense2), Head.py:26-32
+ * (tgt_word_prj), pred_attribute.py:62-65,124 (prj), :257-260 (semantic2hidden).
+ * A, W are `dtype` (fp32: SIMT FFMA kernel, bit-comparable accumulation; bf16: tcgen05/TMEM
+ * kernel fed by TMA, fp32 accumulate).  bias fp32 or NULL.  C is `out_dtype`.
+ * Requirements: lda, ldw multiples of 8 elements (bf16) / 4 (fp32), 16-byte aligned bases;
+ * ldc a multiple of 8; columns [N, min(roundup8(N), ldc)) of C are written with zeros. */
+int care_gemm(care_ctx* ctx, int dtype, const void* A, int64_t lda, const void* W, int64_t ldw,
+              const float* bias, void* C, int64_t ldc, int out_dtype, int M, int N, int K, int act,
+              void* stream);
+
+/* fp32 -> bf16 cast of the incoming feature tensors (translate.py:36-38 hands fp32 features). */
+int care_cast_f32_bf16(care_ctx* ctx, const float* src, void* dst, int64_t n, void* stream);
+
+/* Encoder stream tail (Encoder.py:167: LayerNorm after Linear; Encoder.py:106: mean over time).
+ * x: fp32 [B*T, d] (the Linear output incl. bias).  Writes LN(x) as T into
+ * out[(v*out_rows + out_row0 + t)*d ...] when out != NULL, and the per-video temporal mean of
+ * LN(x) as T into mean_out[v*mean_ld + mean_col0 ...] when mean_out != NULL. */
+int care_encoder_ln_mean(care_ctx* ctx, int dtype, const float* x, const float* gamma,
+                         const float* beta, float eps, int B, int T, int d, void* out,
+                         int out_rows, int out_row0, void* mean_out, int64_t mean_ld, int mean_col0,
+                         void* stream);
+
+/* EncoderWithHighWayBN tail (Encoder.py:184-187,210-241): out = BN_eval(g*h + (1-g)*tanh(y)),
+ * g = sigmoid(gpre); h, ypre, gpre fp32 [B*T, d] (Linear outputs incl. bias).  Same outputs as
+ * care_encoder_ln_mean.  bn_scale/bn_shift are the folded eval-mode affine (fp32 [d]). */
+int care_encoder_highway_bn_mean(care_ctx* ctx, int dtype, const float* h, const float* ypre,
+                                 const float* gpre, const float* bn_mean, const float* bn_var,
+                                 const float* bn_w, const float* bn_b, float bn_eps, int B, int T,
+                                 int d, void* out, int out_rows, int out_row0, void* mean_out,
+                                 int64_t mean_ld, int mean_col0, void* stream);
+
+/* Concept head (pred_attribute.py:17-46 noisy-or, :262-289 SemanticContainer, Embeddings.py:53-87
+ * NaiveEmbeddings, Framework.py:184-185 concat).  scores fp32 [B, ld_scores] = prj output incl. bias.
+ * preds_f32 [B, n_attr]; preds_T [B, ld_preds_T] (A operand of semantic2hidden, zero padded);
+ * labels int64 [B, topk] sorted by (prob desc, index asc); LN(word[label]+pos[rank]) written as T
+ * into memory rows mem_row0 .. mem_row0+topk-1 of each video ([B, mem_rows, d]). */
+int care_concept_head(care_ctx* ctx, int dtype, const float* scores, int64_t ld_scores, int B,
+                      int n_attr, int topk, const float* attr_word, const float* attr_pos,
+                      const float* gamma, const float* beta, float eps, int d, float* preds_f32,
+                      void* preds_T, int64_t ld_preds_T, int64_t* labels, void* memory, int mem_rows,
+                      int mem_row0, void* stream);
+
+/* Decoder input embedding for ONE position per row (Embeddings.py:134-188):
+ * out[r] = LN(((word[tok[r]] + pos[position]) + add_feats[r / rows_per_video]) + gsg[r / rows_per_video]).
+ * tokens int32 [R]; add_feats / gsg fp32 [n_videos, d] or NULL; out T [R, d].
+ * With positions != NULL (int32 [R]) each row uses its own position (mask-predict passes). */
+int care_embed_ln(care_ctx* ctx, int dtype, const int32_t* tokens, const int32_t* positions,
+                  int position, const float* word_emb, const float* pos_emb, const float* add_feats,
+                  const float* gsg, int rows_per_video, const float* gamma, const float* beta,
+                  float eps, int R, int d, void* out, void* stream);
+
+/* Post-LN residual block tail (SubLayers.py:74-79, :148-150): out = LN(x + residual).
+ * x fp32 [R, d] (Linear output incl. bias), residual T [R, d], out T [R, d]. */
+int care_add_ln(care_ctx* ctx, int dtype, const float* x, const void* residual, const float* gamma,
+                const float* beta, float eps, int R, int d, void* out, void* stream);
+
+/* Fused decode-step self-attention over the KV cache (Attention.py:81-129 for the newest query
+ * position only; masks Transformer.py:15-47,169-174).  qkv_step: T [R, 3d] of THIS step (q|k|v);
+ * cache: T [T_max, R, 3d] holding every step's qkv (the step-t slice is qkv_step itself), so the
+ * cache is never reordered: anc uint8 [B, K, T_max] maps (beam, position) -> cache slot, and
+ * tok_hist int32 [B, T_max+1, K] holds the token fed at (position, slot) for the PAD-key mask.
+ * n_pos = number of positions to attend (= step t).  ctx_out T [R, d].  done int32 [B] or NULL. */
+int care_self_attn_step(care_ctx* ctx, int dtype, const void* cache, int n_pos, int B, int K, int H,
+                        int d, const uint8_t* anc, int anc_stride, const int32_t* tok_hist,
+                        const int32_t* done, void* ctx_out, void* stream);
+
+/* Fused decode-step cross-attention (Attention.py:81-129 with hybrid_bias :109-111).  q T [R, ldq];
+ * kv T [B, Lm, 2d] (k|v projected ONCE per video, never replicated per beam — replaces
+ * auto_enlarge, misc/utils.py:244-279, and the per-step re-projection Attention.py:63-67);
+ * hybrid_bias fp32 [H, Lm] or NULL.  ctx_out T [R, d]. */
+int care_cross_attn_step(care_ctx* ctx, int dtype, const void* q, int64_t ldq, const void* kv, int Lm,
+                         int B, int K, int H, int d, const float* hybrid_bias, const int32_t* done,
+                         void* ctx_out, void* stream);
+
+/* Beam state, all device resident (replaces misc/Decoding/Beam.py's per-video Python objects). */
+typedef struct care_beam_state {
+  int32_t B, K, T_max, V, need;   /* need = max(K, topk)  (Beam.py:10) */
+  float* scores;                  /* [B, K]              Beam.scores */
+  int32_t* cur_tok;               /* [B*K]               token fed at the next step */
+  int32_t* tok_hist;              /* [B, T_max+1, K]     Beam.next_ys (position 0 = BOS) */
+  int32_t* prev_ks;               /* [B, T_max, K]       Beam.prev_ks */
+  uint8_t* anc;                   /* [B, K, T_max]       ancestry slot table for the KV cache */
+  float* fin_score;               /* [B, need]           Beam.finished */
+  int32_t* fin_t;                 /* [B, need] */
+  int32_t* fin_k;                 /* [B, need] */
+  int32_t* fin_count;             /* [B] */
+  int32_t* done;                  /* [B] */
+  int32_t* n_done;                /* [1] number of finished videos */
+} care_beam_state;
+
+/* reset state for a new batch: scores 0, cur_tok/tok_hist[0] = bos, counters 0 */
+int care_beam_init(care_ctx* ctx, const care_beam_state* st, int bos, void* stream);
+
+/* One beam-search step for every unfinished video (Translator.py:111-143 + Beam.py:45-85):
+ * log_softmax over V, + running score, rows whose last token is <eos> := -1e20, top-K over the
+ * flattened K*V candidates ordered by (value desc, flat index asc), back-pointers / tokens /
+ * scores / ancestry update, finished list and the finish rule.  logits fp32 [R, ldv].
+ * step = len_input_ids (1-based); at step 1 only beam row 0 is scored (Beam.py:56).
+ * Optional audit outputs: cand_val fp32 [B, K+1], cand_idx int32 [B, K+1] (the K winners and the
+ * runner-up), may be NULL. */
+int care_beam_step(care_ctx* ctx, const care_beam_state* st, const float* logits, int64_t ldv,
+                   int step, int max_len, float* cand_val, int32_t* cand_idx, void* stream);
+
+/* Hypothesis extraction (Translator.py:211-220, Beam.py:91-105,119-132): rank finished items by
+ * score / t^alpha (double), stable, and back-walk the n_best first.  out_tokens int32
+ * [B, n_best, T_max] PAD filled; out_len int32 [B, n_best] (0 = no such hypothesis);
+ * out_score fp32 [B, n_best] raw cumulative log-prob; out_t int32 [B, n_best]. */
+int care_beam_finalize(care_ctx* ctx, const care_beam_state* st, double alpha, int n_best,
+                       int32_t* out_tokens, int32_t* out_len, float* out_score, int32_t* out_t,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CARE_B200_H_ */

