@@ -108,7 +108,8 @@ int gemm_f32(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t l
   CARE_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(C) & 15) == 0,
                  "care_gemm(f32): A, W, C must be 16-byte aligned");
-  const int n_pad = (N + 3) & ~3;
+  const int n_pad8 = (N + 7) & ~7;
+  const int n_pad = n_pad8 <= ldc ? n_pad8 : ((N + 3) & ~3);
   CARE_CHECK_ARG(n_pad <= ldc, "care_gemm(f32): ldc %lld too small for N=%d", (long long)ldc, N);
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   if (out_dtype == CARE_F32)

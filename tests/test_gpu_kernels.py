@@ -256,8 +256,9 @@ def test_self_attention(env, dt, T, K, H, n_pos):
     done = torch.zeros(B, dtype=torch.int32)
     done[B - 1] = 1
     out = torch.full((R, d), 123.0, device="cuda", dtype=T)
-    L.check(lib.care_self_attn_step(h, dt, cache.data_ptr(), n_pos, B, K, H, d, anc.cuda().data_ptr(), Tm,
-                                    tok.cuda().data_ptr(), done.cuda().data_ptr(), out.data_ptr(), _stream()),
+    d_anc, d_tok, d_done = anc.cuda(), tok.cuda(), done.cuda()   # keep alive: raw pointers are passed
+    L.check(lib.care_self_attn_step(h, dt, cache.data_ptr(), n_pos, B, K, H, d, d_anc.data_ptr(), Tm,
+                                    d_tok.data_ptr(), d_done.data_ptr(), out.data_ptr(), _stream()),
             "self_attn")
     torch.cuda.synchronize()
     cf = cache.float().cpu()
