@@ -20,7 +20,7 @@ class BeamState(Structure):
         ("B", c_int32), ("K", c_int32), ("T_max", c_int32), ("V", c_int32), ("need", c_int32),
         ("scores", c_void_p), ("cur_tok", c_void_p), ("tok_hist", c_void_p), ("prev_ks", c_void_p),
         ("anc", c_void_p), ("fin_score", c_void_p), ("fin_t", c_void_p), ("fin_k", c_void_p),
-        ("fin_count", c_void_p), ("done", c_void_p), ("n_done", c_void_p),
+        ("fin_count", c_void_p), ("done", c_void_p), ("n_done", c_void_p), ("scratch", c_void_p),
     ]
 
 

@@ -1,11 +1,11 @@
 // Device-resident beam search (replaces misc/Decoding/Beam.py's per-video Python objects and their
 // per-element device syncs).  One CTA per video and step:
-//   for each live beam row: max and sum-exp over V (log_softmax statistics, Translator.py:127),
-//   candidate value = ((x - max) - log(sum)) + score  (Beam.py:51),  rows ending in <eos> := -1e20 (:52-54),
-//   per-thread register top-(K+1) -> warp shuffle merge -> block merge, ordered by (value desc, flat index asc),
-//   then one thread applies Beam.advance's bookkeeping (:61-85) and maintains the KV-cache ancestry table.
-// The logits row of a beam (<= 59 KB) is read three times (max, sum-exp, select); passes two and three
-// hit L1/L2, so HBM sees each logit once.
+//   kernel 1 (one CTA per logits row): single pass, online max / sum-exp (log_softmax statistics,
+//     Translator.py:127) and a register top-(K+1) of the raw logits -> warp shuffle merge -> block merge;
+//   kernel 2 (one warp per video): candidate value = ((x - max) - log(sum)) + score (Beam.py:51), rows ending
+//     in <eos> := -1e20 (:52-54), merge by (value desc, flat index asc), Beam.advance's bookkeeping (:61-85)
+//     and the KV-cache ancestry table.
+// HBM sees each logit exactly once.
 #include <cfloat>
 #include <climits>
 
@@ -78,121 +78,171 @@ __device__ __forceinline__ void warp_merge(TopList<KB>& l, float (&out_v)[KB], i
   }
 }
 
-__device__ __forceinline__ float block_reduce(float x, bool is_max, float* red) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  x = is_max ? warp_max(x) : warp_sum(x);
-  __syncthreads();  // protects `red` against the previous use
-  if (lane == 0) red[warp] = x;
-  __syncthreads();
-  float r = red[0];
-#pragma unroll
-  for (int w = 1; w < WARPS; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
-  return r;
-}
+// ---------------------------------------------------------------------------------------------
+// Kernel 1: one CTA per logits row.  Single pass over the row (each logit is read from HBM exactly
+// once): online (max, sum-exp) and a register top-KB of the RAW logits.  Within a row the map
+// x -> ((x - max) - log(sum)) + score is monotone, so the row's best final candidates are its best raw
+// logits.  Writes one small partial record per row.
+// ---------------------------------------------------------------------------------------------
+constexpr int ROW_THREADS = 256;
+constexpr int ROW_WARPS = ROW_THREADS / 32;
 
 template <int KB>
-__global__ void __launch_bounds__(THREADS)
-beam_step_kernel(const care_beam_state st, const float* __restrict__ logits, int64_t ldv, int step, int max_len,
-                 float* __restrict__ cand_val, int32_t* __restrict__ cand_idx) {
-  __shared__ float red[WARPS];
-  __shared__ float wl_v[WARPS][KB];
-  __shared__ int wl_i[WARPS][KB];
-  __shared__ float fin_v[KB];
-  __shared__ int fin_i[KB];
-  __shared__ uint8_t old_anc[8 * 64];
-
-  const int v = blockIdx.x;
+__global__ void __launch_bounds__(ROW_THREADS)
+beam_row_kernel(const care_beam_state st, const float* __restrict__ logits, int64_t ldv, int step) {
+  __shared__ float sm_m[ROW_WARPS], sm_s[ROW_WARPS];
+  __shared__ float wl_v[ROW_WARPS][KB];
+  __shared__ int wl_i[ROW_WARPS][KB];
+  const int r = blockIdx.x;
+  const int K = st.K, V = st.V;
+  const int v = r / K, b = r - v * K;
   if (st.done[v]) return;
-  const int K = st.K, V = st.V, T = st.T_max;
-  const int nsel = K + 1;  // K winners + runner-up (audit)
+  if (step == 1 && b > 0) return;                            // Beam.py:56
+  if (step > 1 && st.cur_tok[r] == CARE_EOS) return;         // Beam.py:52-54 (handled in kernel 2)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* row = logits + (int64_t)r * ldv;
+  const float4* row4 = reinterpret_cast<const float4*>(row);
+  const int V4 = V >> 2;
 
   TopList<KB> mine;
   mine.init();
-  const int n_rows = (step == 1) ? 1 : K;  // Beam.py:56: the first step only looks at beam 0
-  for (int b = 0; b < n_rows; ++b) {
-    const bool killed = (step > 1) && (st.cur_tok[v * K + b] == CARE_EOS);
-    if (killed) {
-      // Beam.py:52-54 sets the whole row to -1e20; under (value desc, index asc) only its first
-      // entries can ever be selected
-      if (tid < KB && tid < V) mine.insert(-1e20f, b * V + tid);
-      continue;
-    }
-    const float* row = logits + ((int64_t)v * K + b) * ldv;
-    const int V4 = V >> 2;
-    const float4* row4 = reinterpret_cast<const float4*>(row);
-    float m = -INFINITY;
-    for (int c = tid; c < V4; c += THREADS) {
-      const float4 x = row4[c];
-      m = fmaxf(fmaxf(m, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
-    }
-    for (int c = V4 * 4 + tid; c < V; c += THREADS) m = fmaxf(m, row[c]);
-    m = block_reduce(m, true, red);
-    float s = 0.f;
-    for (int c = tid; c < V4; c += THREADS) {
-      const float4 x = row4[c];
-      s += expf(x.x - m) + expf(x.y - m) + expf(x.z - m) + expf(x.w - m);
-    }
-    for (int c = V4 * 4 + tid; c < V; c += THREADS) s += expf(row[c] - m);
-    s = block_reduce(s, false, red);
-    const float logsum = logf(s);
-    const float score = (step == 1) ? 0.f : st.scores[v * K + b];
-    const int base = b * V;
-    for (int c = tid; c < V4; c += THREADS) {
-      const float4 x = row4[c];
-      const float xs[4] = {x.x, x.y, x.z, x.w};
+  float m = -INFINITY, s = 0.f;
+  constexpr int U = 4;
+  for (int c0 = tid; c0 < V4; c0 += ROW_THREADS * U) {
+    float4 x[U];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float val = (xs[e] - m) - logsum;
-        if (step > 1) val += score;
-        mine.insert(val, base + c * 4 + e);
+    for (int u = 0; u < U; ++u) {
+      const int c = c0 + u * ROW_THREADS;
+      x[u] = (c < V4) ? __ldcs(row4 + c) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+    float cm = m;
+#pragma unroll
+    for (int u = 0; u < U; ++u) cm = fmaxf(cm, fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w)));
+    if (cm > m) {
+      s *= __expf(m - cm);
+      m = cm;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int c = c0 + u * ROW_THREADS;
+      if (c < V4) {
+        s += __expf(x[u].x - m) + __expf(x[u].y - m) + __expf(x[u].z - m) + __expf(x[u].w - m);
+        mine.insert(x[u].x, c * 4 + 0);
+        mine.insert(x[u].y, c * 4 + 1);
+        mine.insert(x[u].z, c * 4 + 2);
+        mine.insert(x[u].w, c * 4 + 3);
       }
     }
-    for (int c = V4 * 4 + tid; c < V; c += THREADS) {
-      float val = (row[c] - m) - logsum;
-      if (step > 1) val += score;
-      mine.insert(val, base + c);
+  }
+  for (int c = V4 * 4 + tid; c < V; c += ROW_THREADS) {
+    const float x = row[c];
+    if (x > m) {
+      s *= __expf(m - x);
+      m = x;
+    }
+    s += __expf(x - m);
+    mine.insert(x, c);
+  }
+  // (max, sum) across the warp, then the block
+  const float wm = warp_max(m);
+  const float ws = warp_sum(m == -INFINITY ? 0.f : s * __expf(m - wm));  // -inf: the thread saw no element
+  float ov[KB];
+  int oi[KB];
+  warp_merge<KB>(mine, ov, oi);
+  if (lane == 0) {
+    sm_m[warp] = wm;
+    sm_s[warp] = ws;
+#pragma unroll
+    for (int q = 0; q < KB; ++q) {
+      wl_v[warp][q] = ov[q];
+      wl_i[warp][q] = oi[q];
     }
   }
+  __syncthreads();
+  if (warp == 0) {
+    float bm = lane < ROW_WARPS ? sm_m[lane] : -INFINITY;
+    float bs = lane < ROW_WARPS ? sm_s[lane] : 0.f;
+    const float M = warp_max(bm);
+    const float S = warp_sum(bm == -INFINITY ? 0.f : bs * __expf(bm - M));
+    TopList<KB> l;
+    l.init();
+    if (lane < ROW_WARPS) {
+#pragma unroll
+      for (int q = 0; q < KB; ++q) {
+        l.v[q] = wl_v[lane][q];
+        l.i[q] = wl_i[lane][q];
+      }
+    }
+    warp_merge<KB>(l, ov, oi);
+    if (lane == 0) {
+      float* rec = st.scratch + (int64_t)r * (2 + 2 * KB);
+      rec[0] = M;
+      rec[1] = S;
+#pragma unroll
+      for (int q = 0; q < KB; ++q) {
+        rec[2 + q] = ov[q];
+        reinterpret_cast<int*>(rec)[2 + KB + q] = oi[q];
+      }
+    }
+  }
+}
 
-  // ---- merge: warp, then block ---------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// Kernel 2: one warp per video.  Turns the K row records into final candidates
+// ((x - max) - log(sum)) + score, merges them by (value desc, flat index asc), then applies
+// Beam.advance's bookkeeping (Beam.py:61-85) and maintains the KV-cache ancestry table.
+// ---------------------------------------------------------------------------------------------
+constexpr int UPD_WARPS = 4;
+
+template <int KB>
+__global__ void __launch_bounds__(UPD_WARPS * 32)
+beam_update_kernel(const care_beam_state st, int step, int max_len, float* __restrict__ cand_val,
+                   int32_t* __restrict__ cand_idx) {
+  __shared__ uint8_t old_anc_all[UPD_WARPS][8 * 64];
+  __shared__ float fin_v_all[UPD_WARPS][KB];
+  __shared__ int fin_i_all[UPD_WARPS][KB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int v = blockIdx.x * UPD_WARPS + warp;
+  if (v >= st.B) return;
+  if (st.done[v]) return;
+  uint8_t* old_anc = old_anc_all[warp];
+  float* fin_v = fin_v_all[warp];
+  int* fin_i = fin_i_all[warp];
+  const int K = st.K, V = st.V, T = st.T_max;
+  const int nsel = K + 1;
+
+  TopList<KB> mine;
+  mine.init();
+  for (int c = lane; c < K * KB; c += 32) {
+    const int b = c / KB, q = c - b * KB;
+    if (step == 1 && b > 0) continue;
+    const int r = v * K + b;
+    if (step > 1 && st.cur_tok[r] == CARE_EOS) {
+      if (q < V) mine.insert(-1e20f, b * V + q);   // the whole row is -1e20 (Beam.py:52-54)
+      continue;
+    }
+    const float* rec = st.scratch + (int64_t)r * (2 + 2 * KB);
+    const int tok = reinterpret_cast<const int*>(rec)[2 + KB + q];
+    if (tok == INT_MAX) continue;
+    float val = (rec[2 + q] - rec[0]) - logf(rec[1]);
+    if (step > 1) val += st.scores[r];
+    mine.insert(val, b * V + tok);
+  }
   float ov[KB];
   int oi[KB];
   warp_merge<KB>(mine, ov, oi);
   if (lane == 0) {
 #pragma unroll
-    for (int r = 0; r < KB; ++r) {
-      wl_v[warp][r] = ov[r];
-      wl_i[warp][r] = oi[r];
+    for (int q = 0; q < KB; ++q) {
+      fin_v[q] = ov[q];
+      fin_i[q] = oi[q];
     }
   }
-  // snapshot of the ancestry table (read before anyone overwrites it)
-  for (int idx = tid; idx < K * T; idx += THREADS) old_anc[idx] = st.anc[(int64_t)v * K * T + idx];
-  __syncthreads();
-  if (warp == 0) {
-    TopList<KB> l;
-    l.init();
-    if (lane < WARPS) {
-#pragma unroll
-      for (int r = 0; r < KB; ++r) {
-        l.v[r] = wl_v[lane][r];
-        l.i[r] = wl_i[lane][r];
-      }
-    }
-    warp_merge<KB>(l, ov, oi);
-    if (lane == 0) {
-#pragma unroll
-      for (int r = 0; r < KB; ++r) {
-        fin_v[r] = ov[r];
-        fin_i[r] = oi[r];
-      }
-    }
-  }
-  __syncthreads();
+  for (int idx = lane; idx < K * T; idx += 32) old_anc[idx] = st.anc[(int64_t)v * K * T + idx];
+  __syncwarp();
 
-  // ---- Beam.advance bookkeeping -----------------------------------------------------------------------
   // ancestry: new_anc[b'][p] = old_anc[parent(b')][p] for p < step-1, new_anc[b'][step-1] = parent(b')
-  for (int idx = tid; idx < K * T; idx += THREADS) {
+  for (int idx = lane; idx < K * T; idx += 32) {
     const int b = idx / T, pp = idx - b * T;
     const int parent = fin_i[b] / V;
     uint8_t a = 0;
@@ -200,20 +250,20 @@ beam_step_kernel(const care_beam_state st, const float* __restrict__ logits, int
     else if (pp == step - 1) a = (uint8_t)parent;
     st.anc[(int64_t)v * K * T + idx] = a;
   }
-  if (tid < K) {
-    const int fi = fin_i[tid];
+  if (lane < K) {
+    const int fi = fin_i[lane];
     const int parent = fi / V;
     const int tok = fi - parent * V;
-    st.scores[v * K + tid] = fin_v[tid];
-    st.prev_ks[((int64_t)v * T + (step - 1)) * K + tid] = parent;
-    st.tok_hist[((int64_t)v * (T + 1) + step) * K + tid] = tok;
-    st.cur_tok[v * K + tid] = tok;
+    st.scores[v * K + lane] = fin_v[lane];
+    st.prev_ks[((int64_t)v * T + (step - 1)) * K + lane] = parent;
+    st.tok_hist[((int64_t)v * (T + 1) + step) * K + lane] = tok;
+    st.cur_tok[v * K + lane] = tok;
   }
-  if (cand_val != nullptr && tid < nsel) {
-    cand_val[(int64_t)v * nsel + tid] = fin_v[tid];
-    cand_idx[(int64_t)v * nsel + tid] = fin_i[tid];
+  if (cand_val != nullptr && lane < nsel) {
+    cand_val[(int64_t)v * nsel + lane] = fin_v[lane];
+    cand_idx[(int64_t)v * nsel + lane] = fin_i[lane];
   }
-  if (tid == 0) {
+  if (lane == 0) {
     int count = st.fin_count[v];
     bool done = false;
     for (int i = 0; i < K && !done; ++i) {  // Beam.py:72-76
@@ -354,16 +404,21 @@ int care_beam_step(care_ctx* ctx, const care_beam_state* st, const float* logits
                  (long long)ldv);
   CARE_CHECK_ARG((reinterpret_cast<uintptr_t>(logits) & 15) == 0, "care_beam_step: logits must be 16-byte aligned");
   CARE_CHECK_ARG((cand_val == nullptr) == (cand_idx == nullptr), "care_beam_step: cand_val/cand_idx must go together");
+  CARE_CHECK_ARG(st->scratch != nullptr, "care_beam_step: state.scratch is NULL");
   cudaStream_t s = (cudaStream_t)stream;
-  const int K = st->K;
-  if (K <= 1)
-    beam::beam_step_kernel<2><<<st->B, beam::THREADS, 0, s>>>(*st, logits, ldv, step, max_len, cand_val, cand_idx);
-  else if (K <= 3)
-    beam::beam_step_kernel<4><<<st->B, beam::THREADS, 0, s>>>(*st, logits, ldv, step, max_len, cand_val, cand_idx);
-  else if (K <= 5)
-    beam::beam_step_kernel<6><<<st->B, beam::THREADS, 0, s>>>(*st, logits, ldv, step, max_len, cand_val, cand_idx);
-  else
-    beam::beam_step_kernel<9><<<st->B, beam::THREADS, 0, s>>>(*st, logits, ldv, step, max_len, cand_val, cand_idx);
+  const int K = st->K, R = st->B * st->K;
+  const int ugrid = (st->B + beam::UPD_WARPS - 1) / beam::UPD_WARPS, uthreads = beam::UPD_WARPS * 32;
+#define CARE_BEAM_GO(KB_)                                                                                  \
+  do {                                                                                                     \
+    beam::beam_row_kernel<KB_><<<R, beam::ROW_THREADS, 0, s>>>(*st, logits, ldv, step);                    \
+    CARE_LAUNCH_CHECK(ctx);                                                                                \
+    beam::beam_update_kernel<KB_><<<ugrid, uthreads, 0, s>>>(*st, step, max_len, cand_val, cand_idx);      \
+  } while (0)
+  if (K <= 1) CARE_BEAM_GO(2);
+  else if (K <= 3) CARE_BEAM_GO(4);
+  else if (K <= 5) CARE_BEAM_GO(6);
+  else CARE_BEAM_GO(9);
+#undef CARE_BEAM_GO
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

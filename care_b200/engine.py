@@ -301,6 +301,7 @@ class CareEngine:
             fin_count=self._buf("bs_fc", (B,), i32),
             done=self._buf("bs_done", (B,), i32),
             n_done=self._buf("bs_nd", (1,), i32),
+            scratch=self._buf("bs_scratch", (B * K * 20,), torch.float32),
         )
         st = BeamState(B=B, K=K, T_max=Tm, V=self.V, need=need, **{k: ptr(v) for k, v in bufs.items()})
         return bufs, st

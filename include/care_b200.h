@@ -142,6 +142,7 @@ typedef struct care_beam_state {
   int32_t* fin_count;             /* [B] */
   int32_t* done;                  /* [B] */
   int32_t* n_done;                /* [1] number of finished videos */
+  float* scratch;                 /* [B*K*20] 32-bit words: per-row (max, sum-exp, top candidates) */
 } care_beam_state;
 
 /* reset state for a new batch: scores 0, cur_tok/tok_hist[0] = bos, counters 0 */

@@ -292,7 +292,7 @@ def _beam_buffers(B, K, Tm, V, need):
         anc=torch.zeros(B, K, Tm, dtype=torch.uint8), fin_score=torch.zeros(B, need),
         fin_t=torch.zeros(B, need, dtype=torch.int32), fin_k=torch.zeros(B, need, dtype=torch.int32),
         fin_count=torch.zeros(B, dtype=torch.int32), done=torch.zeros(B, dtype=torch.int32),
-        n_done=torch.zeros(1, dtype=torch.int32))
+        n_done=torch.zeros(1, dtype=torch.int32), scratch=torch.zeros(B * K * 20))
     t = {k: v.cuda() for k, v in t.items()}
     st = BeamState(B=B, K=K, T_max=Tm, V=V, need=need, **{k: v.data_ptr() for k, v in t.items()})
     return t, st
