@@ -86,13 +86,22 @@ __device__ __forceinline__ void warp_merge(TopList<KB>& l, float (&out_v)[KB], i
 // ---------------------------------------------------------------------------------------------
 constexpr int ROW_THREADS = 256;
 constexpr int ROW_WARPS = ROW_THREADS / 32;
+constexpr int ROW_NV4 = 16;                             // float4 per thread held in registers
+constexpr int ROW_SPAN = ROW_THREADS * ROW_NV4 * 4;     // 16384 logits per register-resident pass
+constexpr int ROW_CAP = 64;                             // candidate list capacity
 
 template <int KB>
 __global__ void __launch_bounds__(ROW_THREADS)
 beam_row_kernel(const care_beam_state st, const float* __restrict__ logits, int64_t ldv, int step) {
-  __shared__ float sm_m[ROW_WARPS], sm_s[ROW_WARPS];
   __shared__ float wl_v[ROW_WARPS][KB];
   __shared__ int wl_i[ROW_WARPS][KB];
+  __shared__ float sm_red[ROW_WARPS];
+  __shared__ float sm_M, sm_T, sm_S;
+  __shared__ int sm_cnt;
+  __shared__ float cl_v[ROW_CAP];
+  __shared__ int cl_i[ROW_CAP];
+  __shared__ float keep_v[KB];   // running best across spans (V > ROW_SPAN only)
+  __shared__ int keep_i[KB];
   const int r = blockIdx.x;
   const int K = st.K, V = st.V;
   const int v = r / K, b = r - v * K;
@@ -101,88 +110,163 @@ beam_row_kernel(const care_beam_state st, const float* __restrict__ logits, int6
   if (step > 1 && st.cur_tok[r] == CARE_EOS) return;         // Beam.py:52-54 (handled in kernel 2)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* row = logits + (int64_t)r * ldv;
-  const float4* row4 = reinterpret_cast<const float4*>(row);
-  const int V4 = V >> 2;
+  float run_M = -INFINITY, run_S = 0.f;
+  if (tid < KB) {
+    keep_v[tid] = -INFINITY;
+    keep_i[tid] = INT_MAX;
+  }
 
-  TopList<KB> mine;
-  mine.init();
-  float m = -INFINITY, s = 0.f;
-  constexpr int U = 4;
-  for (int c0 = tid; c0 < V4; c0 += ROW_THREADS * U) {
-    float4 x[U];
+  for (int base = 0; base < V; base += ROW_SPAN) {
+    // ---- the whole span goes into registers: every logit is read from HBM exactly once ----
+    const int n_here = min(ROW_SPAN, V - base);
+    const int n4 = n_here >> 2;
+    const float4* row4 = reinterpret_cast<const float4*>(row + base);
+    float4 x[ROW_NV4];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int c = c0 + u * ROW_THREADS;
-      x[u] = (c < V4) ? __ldcs(row4 + c) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int u = 0; u < ROW_NV4; ++u) {
+      const int c = tid + u * ROW_THREADS;
+      x[u] = (c < n4) ? __ldcs(row4 + c) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     }
-    float cm = m;
+    const int tail_idx = base + n4 * 4 + tid;                // n_here % 4 leftover scalars
+    const float xt = (tid < (n_here & 3)) ? row[tail_idx] : -INFINITY;
+    float m = xt;
 #pragma unroll
-    for (int u = 0; u < U; ++u) cm = fmaxf(cm, fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w)));
-    if (cm > m) {
-      s *= __expf(m - cm);
-      m = cm;
-    }
+    for (int u = 0; u < ROW_NV4; ++u) m = fmaxf(m, fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w)));
+
+    // ---- block max M and threshold T = KB-th largest of the per-thread maxima (a lower bound of the
+    //      KB-th largest logit of the span, so only a handful of elements pass `x >= T`) ----
+    TopList<KB> tl;
+    tl.init();
+    if (m > -INFINITY) tl.insert(m, tid);
+    float ov[KB];
+    int oi[KB];
+    warp_merge<KB>(tl, ov, oi);
+    __syncthreads();   // previous span's readers of wl_*/sm_* are done
+    if (lane == 0) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int c = c0 + u * ROW_THREADS;
-      if (c < V4) {
-        s += __expf(x[u].x - m) + __expf(x[u].y - m) + __expf(x[u].z - m) + __expf(x[u].w - m);
-        mine.insert(x[u].x, c * 4 + 0);
-        mine.insert(x[u].y, c * 4 + 1);
-        mine.insert(x[u].z, c * 4 + 2);
-        mine.insert(x[u].w, c * 4 + 3);
+      for (int q = 0; q < KB; ++q) {
+        wl_v[warp][q] = ov[q];
+        wl_i[warp][q] = oi[q];
       }
     }
-  }
-  for (int c = V4 * 4 + tid; c < V; c += ROW_THREADS) {
-    const float x = row[c];
-    if (x > m) {
-      s *= __expf(m - x);
-      m = x;
+    if (tid == 0) sm_cnt = 0;
+    __syncthreads();
+    if (warp == 0) {
+      TopList<KB> l;
+      l.init();
+      if (lane < ROW_WARPS) {
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+          l.v[q] = wl_v[lane][q];
+          l.i[q] = wl_i[lane][q];
+        }
+      }
+      warp_merge<KB>(l, ov, oi);
+      if (lane == 0) {
+        sm_M = ov[0];
+        sm_T = fmaxf(ov[KB - 1], keep_v[KB - 1]);   // nothing below the running KB-th best can matter
+      }
     }
-    s += __expf(x - m);
-    mine.insert(x, c);
+    __syncthreads();
+    const float M = fmaxf(sm_M, run_M), T = sm_T;
+
+    // ---- sum of exp(x - M) (two-pass statistics, as torch.log_softmax computes them) ----
+    float s = (xt > -INFINITY) ? __expf(xt - M) : 0.f;
+#pragma unroll
+    for (int u = 0; u < ROW_NV4; ++u) {
+      if (tid + u * ROW_THREADS < n4)
+        s += __expf(x[u].x - M) + __expf(x[u].y - M) + __expf(x[u].z - M) + __expf(x[u].w - M);
+    }
+    s = warp_sum(s);
+    if (lane == 0) sm_red[warp] = s;
+
+    // ---- candidates: elements >= T are appended to a small shared list ----
+#pragma unroll
+    for (int u = 0; u < ROW_NV4; ++u) {
+      const int c = tid + u * ROW_THREADS;
+      const float xs[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+      if (c < n4 && fmaxf(fmaxf(xs[0], xs[1]), fmaxf(xs[2], xs[3])) >= T) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (xs[e] >= T) {
+            const int pos = atomicAdd(&sm_cnt, 1);
+            if (pos < ROW_CAP) {
+              cl_v[pos] = xs[e];
+              cl_i[pos] = base + c * 4 + e;
+            }
+          }
+      }
+    }
+    if (xt >= T && xt > -INFINITY) {
+      const int pos = atomicAdd(&sm_cnt, 1);
+      if (pos < ROW_CAP) {
+        cl_v[pos] = xt;
+        cl_i[pos] = tail_idx;
+      }
+    }
+    __syncthreads();
+    const int cnt = sm_cnt;
+    if (cnt > ROW_CAP) {
+      // degenerate span (masses of equal logits): exact but slow per-thread selection
+      TopList<KB> mine;
+      mine.init();
+#pragma unroll
+      for (int u = 0; u < ROW_NV4; ++u) {
+        const int c = tid + u * ROW_THREADS;
+        if (c < n4) {
+          mine.insert(x[u].x, base + c * 4 + 0);
+          mine.insert(x[u].y, base + c * 4 + 1);
+          mine.insert(x[u].z, base + c * 4 + 2);
+          mine.insert(x[u].w, base + c * 4 + 3);
+        }
+      }
+      if (xt > -INFINITY) mine.insert(xt, tail_idx);
+      warp_merge<KB>(mine, ov, oi);
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+          wl_v[warp][q] = ov[q];
+          wl_i[warp][q] = oi[q];
+        }
+      }
+      __syncthreads();
+    }
+    if (warp == 0) {
+      TopList<KB> l;
+      l.init();
+      if (cnt > ROW_CAP) {
+        if (lane < ROW_WARPS) {
+#pragma unroll
+          for (int q = 0; q < KB; ++q) l.insert(wl_v[lane][q], wl_i[lane][q]);
+        }
+      } else {
+        for (int q = lane; q < cnt; q += 32) l.insert(cl_v[q], cl_i[q]);
+      }
+      if (lane < KB) l.insert(keep_v[lane], keep_i[lane]);   // carry the previous spans' best
+      warp_merge<KB>(l, ov, oi);
+      float ssum = lane < ROW_WARPS ? sm_red[lane] : 0.f;
+      ssum = warp_sum(ssum);
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+          keep_v[q] = ov[q];
+          keep_i[q] = oi[q];
+        }
+        sm_S = (run_M > -INFINITY ? run_S * __expf(run_M - M) : 0.f) + ssum;
+      }
+    }
+    __syncthreads();
+    run_M = M;
+    run_S = sm_S;
   }
-  // (max, sum) across the warp, then the block
-  const float wm = warp_max(m);
-  const float ws = warp_sum(m == -INFINITY ? 0.f : s * __expf(m - wm));  // -inf: the thread saw no element
-  float ov[KB];
-  int oi[KB];
-  warp_merge<KB>(mine, ov, oi);
-  if (lane == 0) {
-    sm_m[warp] = wm;
-    sm_s[warp] = ws;
+  if (tid == 0) {
+    float* rec = st.scratch + (int64_t)r * (2 + 2 * KB);
+    rec[0] = run_M;
+    rec[1] = run_S;
 #pragma unroll
     for (int q = 0; q < KB; ++q) {
-      wl_v[warp][q] = ov[q];
-      wl_i[warp][q] = oi[q];
-    }
-  }
-  __syncthreads();
-  if (warp == 0) {
-    float bm = lane < ROW_WARPS ? sm_m[lane] : -INFINITY;
-    float bs = lane < ROW_WARPS ? sm_s[lane] : 0.f;
-    const float M = warp_max(bm);
-    const float S = warp_sum(bm == -INFINITY ? 0.f : bs * __expf(bm - M));
-    TopList<KB> l;
-    l.init();
-    if (lane < ROW_WARPS) {
-#pragma unroll
-      for (int q = 0; q < KB; ++q) {
-        l.v[q] = wl_v[lane][q];
-        l.i[q] = wl_i[lane][q];
-      }
-    }
-    warp_merge<KB>(l, ov, oi);
-    if (lane == 0) {
-      float* rec = st.scratch + (int64_t)r * (2 + 2 * KB);
-      rec[0] = M;
-      rec[1] = S;
-#pragma unroll
-      for (int q = 0; q < KB; ++q) {
-        rec[2 + q] = ov[q];
-        reinterpret_cast<int*>(rec)[2 + KB + q] = oi[q];
-      }
+      rec[2 + q] = keep_v[q];
+      reinterpret_cast<int*>(rec)[2 + KB + q] = keep_i[q];
     }
   }
 }
