@@ -15,6 +15,49 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int get_tmap_bf16(care_ctx* ctx, const void* ptr, int rank, const uint64_t* gdim, const uint64_t* gstride_bytes,
+                  const uint32_t* box, CUtensorMap* out) {
+  TmapKey key{};
+  key.ptr = ptr;
+  key.rank = (uint32_t)rank;
+  for (int i = 0; i < rank; ++i) {
+    key.gdim[i] = gdim[i];
+    key.box[i] = box[i];
+    if (i > 0) key.gstride[i - 1] = gstride_bytes[i - 1];
+  }
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    auto it = ctx->tmaps.find(key);
+    if (it != ctx->tmaps.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  CUtensorMap m;
+  cuuint64_t gd[3] = {1, 1, 1}, gs[2] = {0, 0};
+  cuuint32_t bx[3] = {1, 1, 1}, es[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = gdim[i];
+    bx[i] = box[i];
+    if (i > 0) gs[i - 1] = gstride_bytes[i - 1];
+  }
+  CUresult r = ctx->encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p rank=%d dims=%llu,%llu,%llu box=%u,%u,%u", (int)r, ptr, rank,
+              (unsigned long long)gd[0], (unsigned long long)gd[1], (unsigned long long)gd[2], bx[0], bx[1], bx[2]);
+    return (int)r;
+  }
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (ctx->tmaps.size() > 8192) ctx->tmaps.clear();
+    ctx->tmaps[key] = m;
+  }
+  *out = m;
+  return 0;
+}
+
 }  // namespace care
 
 extern "C" {
@@ -62,5 +105,15 @@ void care_ctx_destroy(care_ctx* ctx) { delete ctx; }
 int care_ctx_sm_count(const care_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
 int64_t care_ctx_launch_count(const care_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int care_ctx_set_option(care_ctx* ctx, const char* name, int value) {
+  CARE_CHECK_ARG(ctx && name, "care_ctx_set_option: bad args");
+  if (strcmp(name, "attn_impl") == 0) {
+    ctx->attn_impl = value;
+    return 0;
+  }
+  care::set_error("care_ctx_set_option: unknown option '%s'", name);
+  return -1;
+}
 
 }  // extern "C"

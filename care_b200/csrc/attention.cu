@@ -205,6 +205,13 @@ static int common_checks(const char* who, int B, int K, int H, int d) {
 }
 
 }  // namespace attn
+
+namespace attn_mma {  // attention_mma.cu: return 1 when the shape is not covered
+int cross_step(care_ctx* ctx, const void* q, int64_t ldq, const void* kv, int Lm, int B, int K, int H, int d,
+               const float* hybrid_bias, const int32_t* done, void* ctx_out, cudaStream_t stream);
+int self_step(care_ctx* ctx, const void* cache, int n_pos, int B, int K, int H, int d, const uint8_t* anc,
+              int anc_stride, const int32_t* tok_hist, const int32_t* done, void* ctx_out, cudaStream_t stream);
+}  // namespace attn_mma
 }  // namespace care
 
 using namespace care;
@@ -216,6 +223,11 @@ int care_self_attn_step(care_ctx* ctx, int dtype, const void* cache, int n_pos, 
                         void* ctx_out, void* stream) {
   CARE_CHECK_ARG(ctx && cache && anc && tok_hist && ctx_out && n_pos >= 1, "care_self_attn_step: bad args");
   if (attn::common_checks("care_self_attn_step", B, K, H, d)) return -1;
+  if (dtype == CARE_BF16 && ctx->attn_impl == 1) {
+    const int rc = attn_mma::self_step(ctx, cache, n_pos, B, K, H, d, anc, anc_stride, tok_hist, done, ctx_out,
+                                       (cudaStream_t)stream);
+    if (rc != 1) return rc;
+  }
   attn::Params p{};
   const int64_t ld = 3LL * d;
   const size_t esz = dtype == CARE_F32 ? 4 : 2;
@@ -249,6 +261,11 @@ int care_cross_attn_step(care_ctx* ctx, int dtype, const void* q, int64_t ldq, c
   CARE_CHECK_ARG(ctx && q && kv && ctx_out && Lm >= 1, "care_cross_attn_step: bad args");
   if (attn::common_checks("care_cross_attn_step", B, K, H, d)) return -1;
   CARE_CHECK_ARG(ldq % 8 == 0, "care_cross_attn_step: ldq must be a multiple of 8");
+  if (dtype == CARE_BF16 && ctx->attn_impl == 1) {
+    const int rc = attn_mma::cross_step(ctx, q, ldq, kv, Lm, B, K, H, d, hybrid_bias, done, ctx_out,
+                                        (cudaStream_t)stream);
+    if (rc != 1) return rc;
+  }
   attn::Params p{};
   p.q = q;
   p.q_ld = ldq;

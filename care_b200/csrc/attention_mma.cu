@@ -1,0 +1,351 @@
+// Decode-step attention for the bf16 mode: HBM-bound, one warp per (video, head).
+//
+// The v0 SIMT kernel (attention.cu) spent ~10k issue slots per (video, head) on per-key FFMA/shuffle
+// chains and reached only ~22 % of HBM bandwidth (profiles/r01_ncu_full_v0_step15.txt).  Here:
+//   * the K and V tiles of one (video, head) - 114 x 64 (cross) or t*K x 64 (self) bf16 - are staged in
+//     shared memory by ONE TMA tensor copy each (SWIZZLE_128B), so the bytes in flight per SM are set
+//     by resident warps x 2 tiles, not by registers;
+//   * S = Q K^T and O = P V run as warp-level mma.sync.m16n8k16 (M = the K beams padded to 16) on
+//     ldmatrix fragments; this is only to cut issue slots - 0.15 MFLOP per 29 KB tile is far below
+//     what would justify a tcgen05/TMEM round trip - and leaves HBM as the bound;
+//   * scale, PAD/ancestry mask (self) or per-head hybrid bias (cross), softmax: fp32 in registers,
+//     statistics through quad shuffles; P is fed to the second MMA as a bf16 hi+lo pair (~16 bit).
+// Semantics are those of attention.cu (Attention.py:81-129, Transformer.py:15-47,169-174).
+#include "common.cuh"
+
+namespace care {
+namespace attn_mma {
+
+constexpr int DH = 64;
+
+struct Params {
+  const __nv_bfloat16* q;   // q of (row 0, head 0)
+  int64_t q_ld;
+  int k_col, v_col;         // element column of K / V (head 0) in the tensor map's row
+  int n_keys;               // Lm (cross) or n_pos * K (self)
+  int rows_pad;             // n_keys rounded up to 16
+  int K, H, d;
+  int Lm;                   // cross
+  int n_pos;                // self
+  const float* bias;        // cross: [H, Lm] or NULL
+  const uint8_t* anc;       // self: [B, K, anc_stride]
+  int anc_stride;
+  const int32_t* tok_hist;  // self: [B, T_max+1, K]
+  int tok_stride;
+  const int32_t* done;
+  __nv_bfloat16* out;       // [R, d]
+  int n_items;              // B * H
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+// D += A * B with A rows 8..15 all zero (only beams 0..7 exist): a1 = a3 = 0.
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(z), "r"(a2), "r"(z), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// physical byte offset of 16-byte chunk `c16` of row `r` inside a SWIZZLE_128B tile (1024-B aligned)
+__device__ __forceinline__ uint32_t sw128(int r, int c16) { return (uint32_t)(r * 128 + ((c16 ^ (r & 7)) << 4)); }
+
+// NT = key tiles of 8 the registers are sized for (n_keys <= 8 * NT)
+template <int NT, bool SELF, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * WARPS + warp;
+  if (item >= p.n_items) return;
+  const int v = item / p.H, h = item - v * p.H;
+  if (p.done != nullptr && p.done[v]) return;
+  const int K = p.K, n_keys = p.n_keys;
+
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t tile_bytes = (uint32_t)p.rows_pad * 128u;
+  const uint32_t k_s = base + (uint32_t)warp * 2u * tile_bytes;
+  const uint32_t v_s = k_s + tile_bytes;
+  const uint32_t aux = base + (uint32_t)WARPS * 2u * tile_bytes;
+  const uint32_t bar_k = aux + (uint32_t)warp * 16u, bar_v = bar_k + 8u;
+
+  // V rows [n_keys, rows_pad) are multiplied by P == 0: they must hold finite values
+  {
+    uint8_t* v_gen = smem_raw + (v_s - raw);
+    const int n16 = (p.rows_pad - n_keys) * 8;
+    for (int i = lane; i < n16; i += 32)
+      *reinterpret_cast<uint4*>(v_gen + (size_t)n_keys * 128 + (size_t)i * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (lane == 0) {
+    mbar_init(bar_k, 1);
+    mbar_init(bar_v, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes = (uint32_t)n_keys * 128u;
+    mbar_expect_tx(bar_k, bytes);
+    if (SELF) tma_load_3d(k_s, &tmap, bar_k, p.k_col + h * DH, v * K, 0);
+    else tma_load_2d(k_s, &tmap, bar_k, p.k_col + h * DH, v * p.Lm);
+    mbar_expect_tx(bar_v, bytes);
+    if (SELF) tma_load_3d(v_s, &tmap, bar_v, p.v_col + h * DH, v * K, 0);
+    else tma_load_2d(v_s, &tmap, bar_v, p.v_col + h * DH, v * p.Lm);
+  }
+
+  const int g = lane >> 2, tig = lane & 3;   // g = beam (MMA row), tig = column pair
+  // Q fragments: A[beam g][dims 16ks + 2tig, +1] and [.. + 8, + 9]
+  uint32_t qa[4][2];
+  {
+    const __nv_bfloat16* qrow = p.q + (int64_t)(v * K + (g < K ? g : 0)) * p.q_ld + h * DH;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t lo = *reinterpret_cast<const uint32_t*>(qrow + 16 * ks + 2 * tig);
+      const uint32_t hi = *reinterpret_cast<const uint32_t*>(qrow + 16 * ks + 2 * tig + 8);
+      qa[ks][0] = g < K ? lo : 0u;
+      qa[ks][1] = g < K ? hi : 0u;
+    }
+  }
+  // self: bit j of beam b's mask = key j (position j / K, slot j % K) is on b's prefix and not <pad>
+  uint32_t wmask[(NT + 3) / 4];
+  if (SELF) {
+    uint32_t* mw = reinterpret_cast<uint32_t*>(smem_raw + (aux - raw) + WARPS * 16) + warp * 8 * ((NT + 3) / 4);
+    constexpr int WPB = (NT + 3) / 4;
+    for (int i = lane; i < 8 * WPB; i += 32) mw[i] = 0u;
+    __syncwarp();
+    for (int i = lane; i < K * p.n_pos; i += 32) {
+      const int b = i / p.n_pos, pp = i - b * p.n_pos;
+      const int slot = (pp == p.n_pos - 1) ? b : (int)p.anc[((int64_t)v * K + b) * p.anc_stride + pp];
+      const int tok = p.tok_hist[(int64_t)v * p.tok_stride + pp * K + slot];
+      if (tok != CARE_PAD) {
+        const int j = pp * K + slot;
+        atomicOr(&mw[b * WPB + (j >> 5)], 1u << (j & 31));
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int w = 0; w < WPB; ++w) wmask[w] = mw[g * WPB + w];
+  }
+  __syncwarp();
+
+  // ---- S = Q K^T ---------------------------------------------------------------------------------
+  float s[NT][2];
+  mbar_wait(bar_k, 0);
+  {
+    const int m = lane >> 3, rr = lane & 7;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      if (nt * 8 < n_keys) {
+        const int r = nt * 8 + rr;
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+          uint32_t b[4];
+          ldsm_x4(b, k_s + sw128(r, 4 * kp + m));
+          mma_bf16(c, qa[2 * kp][0], qa[2 * kp][1], b[0], b[1]);
+          mma_bf16(c, qa[2 * kp + 1][0], qa[2 * kp + 1][1], b[2], b[3]);
+        }
+      }
+      s[nt][0] = c[0];
+      s[nt][1] = c[1];
+    }
+  }
+  // ---- scale, mask / bias, softmax (fp32) ----------------------------------------------------------
+  float mx = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = nt * 8 + 2 * tig + e;
+      float x = s[nt][e] * 0.125f;   // / sqrt(64), Attention.py:84
+      if (SELF) {
+        if (!((wmask[nt >> 2] >> (j & 31)) & 1u)) x = -1e9f;
+      } else if (p.bias != nullptr && j < n_keys) {
+        x += __ldg(p.bias + (int64_t)h * p.Lm + j);
+      }
+      if (j >= n_keys) x = -INFINITY;
+      s[nt][e] = x;
+      mx = fmaxf(mx, x);
+    }
+  }
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  float sum = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float pe = __expf(s[nt][e] - mx);
+      s[nt][e] = pe;
+      sum += pe;
+    }
+  }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+
+  // ---- O = P V ---------------------------------------------------------------------------------------
+  float o[8][4];
+#pragma unroll
+  for (int dn = 0; dn < 8; ++dn)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[dn][e] = 0.f;
+  mbar_wait(bar_v, 0);
+  {
+    const int m = lane >> 3, rr = lane & 7;
+#pragma unroll
+    for (int kk = 0; kk < NT / 2; ++kk) {
+      if (kk * 16 < n_keys) {
+        const float p0 = s[2 * kk][0], p1 = s[2 * kk][1], p2 = s[2 * kk + 1][0], p3 = s[2 * kk + 1][1];
+        const uint32_t a0h = pack_bf16(p0, p1), a2h = pack_bf16(p2, p3);
+        const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&a0h);
+        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&a2h);
+        const uint32_t a0l = pack_bf16(p0 - __low2float(h0), p1 - __high2float(h0));
+        const uint32_t a2l = pack_bf16(p2 - __low2float(h2), p3 - __high2float(h2));
+        const int r = kk * 16 + 8 * (m & 1) + rr;
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t b[4];
+          ldsm_x4_trans(b, v_s + sw128(r, 2 * dp + (m >> 1)));
+          mma_bf16(o[2 * dp], a0h, a2h, b[0], b[1]);
+          mma_bf16(o[2 * dp], a0l, a2l, b[0], b[1]);
+          mma_bf16(o[2 * dp + 1], a0h, a2h, b[2], b[3]);
+          mma_bf16(o[2 * dp + 1], a0l, a2l, b[2], b[3]);
+        }
+      }
+    }
+  }
+  if (g < K) {
+    const float inv = 1.0f / sum;
+    __nv_bfloat16* orow = p.out + (int64_t)(v * K + g) * p.d + h * DH + 2 * tig;
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn)
+      *reinterpret_cast<__nv_bfloat162*>(orow + 8 * dn) = __floats2bfloat162_rn(o[dn][0] * inv, o[dn][1] * inv);
+  }
+}
+
+template <int NT, bool SELF>
+static int launch(care_ctx* ctx, const CUtensorMap& tmap, const Params& p, cudaStream_t stream) {
+  constexpr int WARPS = 1;
+  auto kern = attn_mma_kernel<NT, SELF, WARPS>;
+  const size_t smem = (size_t)WARPS * 2 * p.rows_pad * 128 + 1024 + WARPS * 16 + (SELF ? WARPS * 8 * ((NT + 3) / 4) * 4 : 0);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int grid = (p.n_items + WARPS - 1) / WARPS;
+  kern<<<grid, WARPS * 32, smem, stream>>>(tmap, p);
+  CARE_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+// returns 1 if the shape is not covered (caller falls back to the SIMT kernel), 0 on launch, else error
+int cross_step(care_ctx* ctx, const void* q, int64_t ldq, const void* kv, int Lm, int B, int K, int H, int d,
+               const float* hybrid_bias, const int32_t* done, void* ctx_out, cudaStream_t stream) {
+  if (K > 8 || Lm > 128 || (ldq % 2) != 0 || (reinterpret_cast<uintptr_t>(q) & 3) != 0 ||
+      (reinterpret_cast<uintptr_t>(kv) & 15) != 0 || (reinterpret_cast<uintptr_t>(ctx_out) & 3) != 0)
+    return 1;
+  CUtensorMap tmap;
+  const uint64_t gdim[2] = {(uint64_t)2 * d, (uint64_t)B * Lm};
+  const uint64_t gstr[1] = {(uint64_t)2 * d * 2};
+  const uint32_t box[2] = {(uint32_t)DH, (uint32_t)Lm};
+  int rc = get_tmap_bf16(ctx, kv, 2, gdim, gstr, box, &tmap);
+  if (rc) return rc;
+  Params p{};
+  p.q = static_cast<const __nv_bfloat16*>(q);
+  p.q_ld = ldq;
+  p.k_col = 0;
+  p.v_col = d;
+  p.n_keys = Lm;
+  p.rows_pad = (Lm + 15) & ~15;
+  p.K = K; p.H = H; p.d = d; p.Lm = Lm;
+  p.bias = hybrid_bias;
+  p.done = done;
+  p.out = static_cast<__nv_bfloat16*>(ctx_out);
+  p.n_items = B * H;
+  return launch<16, false>(ctx, tmap, p, stream);
+}
+
+int self_step(care_ctx* ctx, const void* cache, int n_pos, int B, int K, int H, int d, const uint8_t* anc,
+              int anc_stride, const int32_t* tok_hist, const int32_t* done, void* ctx_out, cudaStream_t stream) {
+  const int n_keys = n_pos * K;
+  if (K > 8 || n_keys > 160 || (reinterpret_cast<uintptr_t>(cache) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(ctx_out) & 3) != 0)
+    return 1;
+  const int64_t R = (int64_t)B * K;
+  CUtensorMap tmap;
+  const uint64_t gdim[3] = {(uint64_t)3 * d, (uint64_t)R, (uint64_t)n_pos};
+  const uint64_t gstr[2] = {(uint64_t)3 * d * 2, (uint64_t)R * 3 * d * 2};
+  const uint32_t box[3] = {(uint32_t)DH, (uint32_t)K, (uint32_t)n_pos};
+  int rc = get_tmap_bf16(ctx, cache, 3, gdim, gstr, box, &tmap);
+  if (rc) return rc;
+  Params p{};
+  p.q = static_cast<const __nv_bfloat16*>(cache) + (int64_t)(n_pos - 1) * R * 3 * d;
+  p.q_ld = 3LL * d;
+  p.k_col = d;
+  p.v_col = 2 * d;
+  p.n_keys = n_keys;
+  p.rows_pad = (n_keys + 15) & ~15;
+  p.K = K; p.H = H; p.d = d;
+  p.n_pos = n_pos;
+  p.anc = anc;
+  p.anc_stride = anc_stride;
+  p.tok_hist = tok_hist;
+  p.tok_stride = (anc_stride + 1) * K;
+  p.done = done;
+  p.out = static_cast<__nv_bfloat16*>(ctx_out);
+  p.n_items = B * H;
+  if (n_keys <= 48) return launch<6, true>(ctx, tmap, p, stream);
+  if (n_keys <= 96) return launch<12, true>(ctx, tmap, p, stream);
+  return launch<20, true>(ctx, tmap, p, stream);
+}
+
+}  // namespace attn_mma
+}  // namespace care

@@ -40,20 +40,27 @@ void set_error(const char* fmt, ...);
     CARE_CUDA(cudaGetLastError());        \
   } while (0)
 
+// Cache key of an encoded TMA descriptor (any rank <= 3, bf16 elements, SWIZZLE_128B).
 struct TmapKey {
   const void* ptr;
-  uint64_t rows, cols, ld;
-  uint32_t box_rows, box_cols;
+  uint32_t rank;
+  uint64_t gdim[3];
+  uint64_t gstride[2];  // bytes, dims 1..rank-1
+  uint32_t box[3];
   bool operator==(const TmapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
-           box_cols == o.box_cols;
+    if (ptr != o.ptr || rank != o.rank) return false;
+    for (int i = 0; i < 3; ++i)
+      if (gdim[i] != o.gdim[i] || box[i] != o.box[i]) return false;
+    return gstride[0] == o.gstride[0] && gstride[1] == o.gstride[1];
   }
 };
 struct TmapKeyHash {
   size_t operator()(const TmapKey& k) const {
     size_t h = (size_t)k.ptr;
     auto mix = [&](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
-    mix(k.rows); mix(k.cols); mix(k.ld); mix(k.box_rows); mix(k.box_cols);
+    mix(k.rank);
+    for (int i = 0; i < 3; ++i) { mix(k.gdim[i]); mix(k.box[i]); }
+    mix(k.gstride[0]); mix(k.gstride[1]);
     return h;
   }
 };
@@ -69,12 +76,18 @@ struct care_ctx {
   int device = 0;
   int sm_count = 0;
   int64_t launches = 0;
+  int attn_impl = 1;   // 1: TMA + mma.sync attention for bf16 (default), 0: SIMT kernel everywhere
   care_tmap_encode_fn encode = nullptr;
   std::mutex mu;
   std::unordered_map<care::TmapKey, CUtensorMap, care::TmapKeyHash> tmaps;
 };
 
 namespace care {
+
+// Encodes (or fetches from the ctx cache) a bf16 SWIZZLE_128B tiled TMA descriptor.  gdim/box are
+// fastest-dimension first; gstride_bytes has rank-1 entries (dimension 0 is dense).  api.cu.
+int get_tmap_bf16(care_ctx* ctx, const void* ptr, int rank, const uint64_t* gdim, const uint64_t* gstride_bytes,
+                  const uint32_t* box, CUtensorMap* out);
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

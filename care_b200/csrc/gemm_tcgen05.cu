@@ -292,35 +292,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
 
 static int get_tmap(care_ctx* ctx, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                     CUtensorMap* out) {
-  TmapKey key{ptr, rows, cols, ld, box_rows, (uint32_t)BLOCK_K};
-  {
-    std::lock_guard<std::mutex> g(ctx->mu);
-    auto it = ctx->tmaps.find(key);
-    if (it != ctx->tmaps.end()) {
-      *out = it->second;
-      return 0;
-    }
-  }
-  CUtensorMap m;
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = ctx->encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%llu cols=%llu ld=%llu box_rows=%u", (int)r, ptr,
-              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
-    return (int)r;
-  }
-  {
-    std::lock_guard<std::mutex> g(ctx->mu);
-    if (ctx->tmaps.size() > 4096) ctx->tmaps.clear();
-    ctx->tmaps[key] = m;
-  }
-  *out = m;
-  return 0;
+  const uint64_t gdim[2] = {cols, rows};
+  const uint64_t gstride[1] = {ld * 2};
+  const uint32_t box[2] = {(uint32_t)BLOCK_K, box_rows};
+  return get_tmap_bf16(ctx, ptr, 2, gdim, gstride, box, out);
 }
 
 template <int BN, typename OutT>

@@ -51,6 +51,9 @@ void care_ctx_destroy(care_ctx* ctx);
 int care_ctx_sm_count(const care_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches claim) */
 int64_t care_ctx_launch_count(const care_ctx* ctx);
+/* implementation switches for A/B tests.  "attn_impl": 1 = TMA + tensor-core attention for bf16
+ * (default), 0 = the SIMT attention kernel for every dtype. */
+int care_ctx_set_option(care_ctx* ctx, const char* name, int value);
 
 /* C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) — every nn.Linear on the path:
  * Encoder.py:165-168 (Embedder Linear), Attention.py:53-67 (query/key/value),
