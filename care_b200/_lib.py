@@ -54,6 +54,11 @@ _SIGNATURES = {
     "care_beam_init": (c_int, [c_void_p, POINTER(BeamState), c_int, c_void_p]),
     "care_beam_step": (c_int, [c_void_p, POINTER(BeamState), c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p,
                                c_void_p]),
+    "care_vocab_beam_nseg": (c_int, [c_void_p, c_int, c_int]),
+    "care_vocab_beam_partials": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int,
+                                         c_void_p, c_int, c_void_p]),
+    "care_beam_step_partials": (c_int, [c_void_p, POINTER(BeamState), c_void_p, c_int, c_int, c_int, c_void_p,
+                                        c_void_p, c_void_p]),
     "care_beam_finalize": (c_int, [c_void_p, POINTER(BeamState), c_double, c_int, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
 }

@@ -278,9 +278,17 @@ beam_row_kernel(const care_beam_state st, const float* __restrict__ logits, int6
 // ---------------------------------------------------------------------------------------------
 constexpr int UPD_WARPS = 4;
 
+// Where the fused vocabulary kernel (vocab_beam.cu) left the per-row records: partials[row][seg],
+// seg < (runs touching the row's m-block); T tiles cut into G contiguous runs, n_tiles per m-block.
+struct SegLayout {
+  const float* partials;   // NULL: st.scratch already holds one record per row (beam_row_kernel)
+  int nseg, n_tiles;
+  int64_t T, G;
+};
+
 template <int KB>
 __global__ void __launch_bounds__(UPD_WARPS * 32)
-beam_update_kernel(const care_beam_state st, int step, int max_len, float* __restrict__ cand_val,
+beam_update_kernel(const care_beam_state st, const SegLayout sl, int step, int max_len, float* __restrict__ cand_val,
                    int32_t* __restrict__ cand_idx) {
   __shared__ uint8_t old_anc_all[UPD_WARPS][8 * 64];
   __shared__ float fin_v_all[UPD_WARPS][KB];
@@ -294,6 +302,51 @@ beam_update_kernel(const care_beam_state st, int step, int max_len, float* __res
   int* fin_i = fin_i_all[warp];
   const int K = st.K, V = st.V, T = st.T_max;
   const int nsel = K + 1;
+
+  if (sl.partials != nullptr) {
+    // merge the row's segment records into one (max, sum-exp, top-KB) record
+    if (lane < K) {
+      const int r = v * K + lane;
+      const int m_blk = r >> 7;
+      const int c0 = (int)((((int64_t)m_blk * sl.n_tiles + 1) * sl.G - 1) / sl.T);
+      const int c1 = (int)((((int64_t)m_blk * sl.n_tiles + sl.n_tiles) * sl.G - 1) / sl.T);
+      const float* base = sl.partials + (int64_t)r * sl.nseg * (2 + 2 * KB);
+      // segment 2*(c - c0) + g exists iff epilogue group g of run c saw a tile of this m-block
+      const int64_t mlo = (int64_t)m_blk * sl.n_tiles, mhi = mlo + sl.n_tiles;
+      auto exists = [&](int c, int g) -> bool {
+        const int64_t start = (int64_t)c * sl.T / sl.G, end = (int64_t)(c + 1) * sl.T / sl.G;
+        const int64_t lo = start > mlo ? start : mlo, hi = end < mhi ? end : mhi;
+        return lo + ((g - (lo - start)) & 1) < hi;
+      };
+      float M = -INFINITY;
+      for (int c = c0; c <= c1; ++c)
+        for (int g = 0; g < 2; ++g)
+          if (exists(c, g)) M = fmaxf(M, base[(2 * (c - c0) + g) * (2 + 2 * KB)]);
+      float S = 0.f;
+      TopList<KB> l;
+      l.init();
+      for (int c = c0; c <= c1; ++c)
+        for (int g = 0; g < 2; ++g) {
+          if (!exists(c, g)) continue;
+          const float* rec = base + (2 * (c - c0) + g) * (2 + 2 * KB);
+          S += rec[1] * __expf(rec[0] - M);
+#pragma unroll
+          for (int q = 0; q < KB; ++q) {
+            const int idx = reinterpret_cast<const int*>(rec)[2 + KB + q];
+            if (idx != INT_MAX) l.insert(rec[2 + q], idx);
+          }
+        }
+      float* out = st.scratch + (int64_t)r * (2 + 2 * KB);
+      out[0] = M;
+      out[1] = S;
+#pragma unroll
+      for (int q = 0; q < KB; ++q) {
+        out[2 + q] = l.v[q];
+        reinterpret_cast<int*>(out)[2 + KB + q] = l.i[q];
+      }
+    }
+    __syncwarp();
+  }
 
   TopList<KB> mine;
   mine.init();
@@ -463,6 +516,10 @@ static int check_state(const care_beam_state* st, const char* who) {
 }
 
 }  // namespace beam
+
+namespace vb {  // vocab_beam.cu
+void seg_layout(const care_ctx* ctx, int R, int V, int* n_tiles, int64_t* T, int64_t* G);
+}
 }  // namespace care
 
 using namespace care;
@@ -496,13 +553,37 @@ int care_beam_step(care_ctx* ctx, const care_beam_state* st, const float* logits
   do {                                                                                                     \
     beam::beam_row_kernel<KB_><<<R, beam::ROW_THREADS, 0, s>>>(*st, logits, ldv, step);                    \
     CARE_LAUNCH_CHECK(ctx);                                                                                \
-    beam::beam_update_kernel<KB_><<<ugrid, uthreads, 0, s>>>(*st, step, max_len, cand_val, cand_idx);      \
+    beam::beam_update_kernel<KB_><<<ugrid, uthreads, 0, s>>>(*st, beam::SegLayout{}, step, max_len, cand_val, \
+                                                              cand_idx);                                   \
   } while (0)
   if (K <= 1) CARE_BEAM_GO(2);
   else if (K <= 3) CARE_BEAM_GO(4);
   else if (K <= 5) CARE_BEAM_GO(6);
   else CARE_BEAM_GO(9);
 #undef CARE_BEAM_GO
+  CARE_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int care_beam_step_partials(care_ctx* ctx, const care_beam_state* st, const float* partials, int nseg, int step,
+                            int max_len, float* cand_val, int32_t* cand_idx, void* stream) {
+  CARE_CHECK_ARG(ctx && partials, "care_beam_step_partials: bad args");
+  if (beam::check_state(st, "care_beam_step_partials")) return -1;
+  CARE_CHECK_ARG(step >= 1 && step <= st->T_max, "care_beam_step_partials: step=%d outside [1,%d]", step, st->T_max);
+  CARE_CHECK_ARG((cand_val == nullptr) == (cand_idx == nullptr),
+                 "care_beam_step_partials: cand_val/cand_idx must go together");
+  CARE_CHECK_ARG(st->scratch != nullptr, "care_beam_step_partials: state.scratch is NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int K = st->K;
+  beam::SegLayout sl{};
+  sl.partials = partials;
+  sl.nseg = nseg;
+  vb::seg_layout(ctx, st->B * K, st->V, &sl.n_tiles, &sl.T, &sl.G);
+  const int ugrid = (st->B + beam::UPD_WARPS - 1) / beam::UPD_WARPS, uthreads = beam::UPD_WARPS * 32;
+  if (K <= 1) beam::beam_update_kernel<2><<<ugrid, uthreads, 0, s>>>(*st, sl, step, max_len, cand_val, cand_idx);
+  else if (K <= 3) beam::beam_update_kernel<4><<<ugrid, uthreads, 0, s>>>(*st, sl, step, max_len, cand_val, cand_idx);
+  else if (K <= 5) beam::beam_update_kernel<6><<<ugrid, uthreads, 0, s>>>(*st, sl, step, max_len, cand_val, cand_idx);
+  else beam::beam_update_kernel<9><<<ugrid, uthreads, 0, s>>>(*st, sl, step, max_len, cand_val, cand_idx);
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

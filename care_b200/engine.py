@@ -52,7 +52,10 @@ class CareEngine:
         self.m_pred = opt.get("modality_for_predictor") or self.modality
         self.max_len = opt.get("max_len", 30)
         self.ldv = _round_up(self.V, 8)
+        # bf16: the vocabulary GEMM's epilogue feeds the beam kernel directly (no logits in HBM)
+        self.fused_vocab = precision == "bf16" and bool(opt.get("care_fused_vocab", True))
         self._ws = {}
+        self._nseg = {}
         self._prepare_weights(state_dict)
 
     def __del__(self):
@@ -306,8 +309,8 @@ class CareEngine:
         st = BeamState(B=B, K=K, T_max=Tm, V=self.V, need=need, **{k: ptr(v) for k, v in bufs.items()})
         return bufs, st
 
-    def decode_step(self, t, B, K, enc, kv, bufs, bst, audit=None):
-        """One beam step (len_input_ids == t) for every video; 14 kernel launches."""
+    def decode_step(self, t, B, K, enc, kv, bufs, bst, audit=None, want_logits=False):
+        """One beam step (len_input_ids == t) for every video; 14 kernel launches (15 unfused)."""
         lib, ctx, dt, w, d, T = self.lib, self.ctx, self.dt, self.w, self.d, self.tdtype
         st = self._stream()
         R = B * K
@@ -318,7 +321,8 @@ class CareEngine:
         cx = self._buf("ctx", (R, d), T); qc = self._buf("qc", (R, d), T)
         y32 = self._buf("y32", (R, d), torch.float32)
         hb = self._buf("ffn_h", (R, self.F), T)
-        logits = self._buf("logits", (R, self.ldv), torch.float32)
+        fused = self.fused_vocab and not want_logits
+        logits = None if fused else self._buf("logits", (R, self.ldv), torch.float32)
         gsg = enc.get("semantic_hidden_states")
         done = ptr(bufs["done"])
         check(lib.care_embed_ln(ctx, dt, ptr(bufs["cur_tok"]), None, t - 1, ptr(w["word"]), ptr(w["pos"]), None,
@@ -340,10 +344,21 @@ class CareEngine:
         self.gemm(hb, w["W2"], w["b2"], y32, R, d, self.F)
         check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x2), ptr(w["ln3_g"]), ptr(w["ln3_b"]), self.eps, R, d, ptr(x3),
                               st), "care_add_ln")
-        self.gemm(x3, w["Wvocab"], None, logits, R, self.V, d)
         cv = ci = None
         if audit is not None:
             cv, ci = audit
+        if fused:
+            nseg = self._nseg.get(R)
+            if nseg is None:
+                nseg = self._nseg[R] = int(lib.care_vocab_beam_nseg(ctx, R, self.V))
+            kb = 2 if K <= 1 else 4 if K <= 3 else 6 if K <= 5 else 9
+            part = self._buf("vocab_partials", (R, nseg, 2 + 2 * kb), torch.float32)
+            check(lib.care_vocab_beam_partials(ctx, ptr(x3), d, ptr(w["Wvocab"]), w["Wvocab"].stride(0), R, self.V, d,
+                                               K, ptr(part), nseg, st), "care_vocab_beam_partials")
+            check(lib.care_beam_step_partials(ctx, ctypes.byref(bst), ptr(part), nseg, t, self.max_len, ptr(cv),
+                                              ptr(ci), st), "care_beam_step_partials")
+            return None
+        self.gemm(x3, w["Wvocab"], None, logits, R, self.V, d)
         check(lib.care_beam_step(ctx, ctypes.byref(bst), ptr(logits), self.ldv, t, self.max_len, ptr(cv), ptr(ci),
                                  st), "care_beam_step")
         return logits
@@ -365,7 +380,7 @@ class CareEngine:
                 audit = (torch.empty((B, K + 1), dtype=torch.float32, device=self.device),
                          torch.empty((B, K + 1), dtype=torch.int32, device=self.device))
                 pre = {k: bufs[k].cpu().clone() for k in ("anc", "tok_hist", "done", "scores", "cur_tok")}
-            logits = self.decode_step(t, B, K, enc, kv, bufs, bst, audit)
+            logits = self.decode_step(t, B, K, enc, kv, bufs, bst, audit, want_logits=trace_logits)
             if trace is not None:
                 trace.append(dict(step=t, pre=pre, cand_val=audit[0].cpu(), cand_idx=audit[1].cpu(),
                                   logits=logits[:, :self.V].cpu().clone() if trace_logits else None))

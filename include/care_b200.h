@@ -161,6 +161,19 @@ int care_beam_init(care_ctx* ctx, const care_beam_state* st, int bos, void* stre
 int care_beam_step(care_ctx* ctx, const care_beam_state* st, const float* logits, int64_t ldv,
                    int step, int max_len, float* cand_val, int32_t* cand_idx, void* stream);
 
+/* Fused vocabulary projection + beam partials, bf16 only (Head.py:26-32 + Translator.py:127 + the
+ * top-k half of Beam.py:45-60): the fp32 logits never reach HBM.  x bf16 [R, ldx] (decoder output of
+ * the newest position), W bf16 [V, ldw] (cls_head.tgt_word_prj.weight).  Each row's vocabulary is
+ * reduced on the tensor-core kernel's epilogue to per-segment records (max, sum-exp, top-(K+1) raw
+ * logits + column ids); partials is fp32 words [R, nseg, 2 + 2*KB] with nseg =
+ * care_vocab_beam_nseg(ctx, R, V) and KB = 2/4/6/9 for K <= 1/3/5/8.  care_beam_step_partials then
+ * does what care_beam_step does after its own row pass. */
+int care_vocab_beam_nseg(care_ctx* ctx, int R, int V);
+int care_vocab_beam_partials(care_ctx* ctx, const void* x, int64_t ldx, const void* W, int64_t ldw, int R,
+                             int V, int d, int K, float* partials, int nseg, void* stream);
+int care_beam_step_partials(care_ctx* ctx, const care_beam_state* st, const float* partials, int nseg,
+                            int step, int max_len, float* cand_val, int32_t* cand_idx, void* stream);
+
 /* Hypothesis extraction (Translator.py:211-220, Beam.py:91-105,119-132): rank finished items by
  * score / t^alpha (double), stable, and back-walk the n_best first.  out_tokens int32
  * [B, n_best, T_max] PAD filled; out_len int32 [B, n_best] (0 = no such hypothesis);

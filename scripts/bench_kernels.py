@@ -98,6 +98,16 @@ def main():
         lib.care_beam_init(h, ctypes.byref(bst), 2, st)
         ms = timed(lambda: _lib.check(lib.care_beam_step(h, ctypes.byref(bst), logits.data_ptr(), ldv, 5, 30, None,
                                                          None, st), "b"))
+        x = torch.randn(R, d, device="cuda").bfloat16()
+        W = (torch.randn(V, d, device="cuda") * 0.05).bfloat16()
+        nseg = lib.care_vocab_beam_nseg(h, R, V)
+        part = torch.empty(R, nseg, 14, device="cuda")
+        msf = timed(lambda: _lib.check(lib.care_vocab_beam_partials(h, x.data_ptr(), d, W.data_ptr(), d, R, V, d, K,
+                                                                    part.data_ptr(), nseg, st), "f"))
+        print("fused vocab+partials (nseg=%d): %.3f ms  %.0f TFLOP/s" % (nseg, msf, 2.0 * R * V * d / msf / 1e9))
+        msu = timed(lambda: _lib.check(lib.care_beam_step_partials(h, ctypes.byref(bst), part.data_ptr(), nseg, 5, 30,
+                                                                   None, None, st), "u"))
+        print("beam update from partials: %.3f ms" % msu)
         nbytes = R * V * 4
         print("beam step: %.3f ms  %.0f GB/s (%.1f%%)" % (ms, nbytes / ms / 1e6, 100 * nbytes / ms / 1e6 / PEAK))
 

@@ -402,3 +402,51 @@ def test_beam_step_and_finalize(env, K, V, topk):
             assert out_tok[v, j, :t].tolist() == hyp
             assert abs(float(out_sc[v, j]) - sc) < 2e-5
             assert (out_tok[v, j, t:] == 0).all()
+
+
+@pytest.mark.parametrize("B,K,V,d", [(6, 5, 10547, 512), (300, 5, 14745, 1024), (7, 1, 9468, 512), (40, 3, 700, 768)])
+def test_fused_vocab_beam_matches_unfused(env, B, K, V, d):
+    """care_vocab_beam_partials + care_beam_step_partials (logits never written) against care_gemm +
+    care_beam_step on the same inputs: same winners, same scores, same beam bookkeeping."""
+    lib, h, L = env
+    R, max_len = B * K, 8
+    Tm, need = max_len - 1, K
+    ldv = (V + 7) // 8 * 8
+    g = torch.Generator(device="cuda").manual_seed(B * 31 + V)
+    W = (torch.randn(V, d, device="cuda", generator=g) * 0.2).bfloat16()
+    nseg = lib.care_vocab_beam_nseg(h, R, V)
+    assert nseg >= 1
+    kb = 2 if K <= 1 else 4 if K <= 3 else 6 if K <= 5 else 9
+    part = torch.full((R, nseg, 2 + 2 * kb), float("nan"), device="cuda")
+    bufs_a, st_a = _beam_buffers(B, K, Tm, V, need)
+    bufs_b, st_b = _beam_buffers(B, K, Tm, V, need)
+    L.check(lib.care_beam_init(h, ctypes.byref(st_a), 2, _stream()), "init")
+    L.check(lib.care_beam_init(h, ctypes.byref(st_b), 2, _stream()), "init")
+    cva, cia = torch.empty(B, K + 1, device="cuda"), torch.empty(B, K + 1, device="cuda", dtype=torch.int32)
+    cvb, cib = torch.empty(B, K + 1, device="cuda"), torch.empty(B, K + 1, device="cuda", dtype=torch.int32)
+    for step in range(1, max_len):
+        x = torch.randn(R, d, device="cuda", generator=g).bfloat16()
+        W[3] = (x[0].float() * (0.02 * step)).bfloat16()     # <eos> gets likelier: finish rule exercised
+        logits = torch.zeros(R, ldv, device="cuda")
+        L.check(lib.care_gemm(h, BF16, x.data_ptr(), d, W.data_ptr(), d, None, logits.data_ptr(), ldv, F32, R, V, d, 0,
+                              _stream()), "gemm")
+        L.check(lib.care_beam_step(h, ctypes.byref(st_a), logits.data_ptr(), ldv, step, max_len, cva.data_ptr(),
+                                   cia.data_ptr(), _stream()), "step")
+        L.check(lib.care_vocab_beam_partials(h, x.data_ptr(), d, W.data_ptr(), d, R, V, d, K, part.data_ptr(), nseg,
+                                             _stream()), "fused")
+        L.check(lib.care_beam_step_partials(h, ctypes.byref(st_b), part.data_ptr(), nseg, step, max_len, cvb.data_ptr(),
+                                            cib.data_ptr(), _stream()), "step_partials")
+        torch.cuda.synchronize()
+        live = bufs_a["done"].cpu() == 0
+        # the row statistics agree with torch on the unfused logits
+        lse = torch.logsumexp(logits[:, :V], dim=1)
+        va, vb_ = cva.cpu()[:, :K], cvb.cpu()[:, :K]
+        assert torch.allclose(va, vb_, rtol=0, atol=2e-5), (step, (va - vb_).abs().max())
+        gaps = (cva.cpu()[:, :-1] - cva.cpu()[:, 1:]).abs().min(dim=1)[0]
+        clear = gaps > 1e-4
+        assert torch.equal(cia.cpu()[clear][:, :K], cib.cpu()[clear][:, :K]), step
+        for name in ("cur_tok", "done", "fin_count", "anc", "prev_ks"):
+            a, b = bufs_a[name].cpu(), bufs_b[name].cpu()
+            if clear.all():
+                assert torch.equal(a, b), (step, name)
+        assert torch.isfinite(lse).all() and live.shape[0] == B
