@@ -51,6 +51,22 @@ _SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "care_cross_attn_step": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int,
                                      c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "care_group_attn": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
+                                c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "care_rows_mean": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "care_combine_means": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, POINTER(c_float), c_void_p, c_int64,
+                                   c_void_p]),
+    "care_nar_length_beam": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                     c_void_p]),
+    "care_nar_init": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "care_nar_best_logits": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "care_nar_best_partials": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "care_nar_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                               c_int, c_void_p]),
+    "care_nar_remask": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                c_void_p]),
+    "care_nar_select": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p,
+                                c_void_p, c_void_p, c_void_p]),
     "care_beam_init": (c_int, [c_void_p, POINTER(BeamState), c_int, c_void_p]),
     "care_beam_step": (c_int, [c_void_p, POINTER(BeamState), c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p,
                                c_void_p]),

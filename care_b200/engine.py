@@ -275,7 +275,20 @@ class CareEngine:
         return out
 
     def _length_logits(self, B, means, pred_tokens, n_pred):
-        raise NotImplementedError("the NACF length head lands with the mask-predict path")
+        """Predictor_length (pred_length.py:5-22): Linear -> ReLU -> Linear over the mean of all predictor
+        tokens, obtained from the per-stream means weighted by their token counts.  Returns fp32 logits
+        [B, >= max_len] (log_softmax is monotone; only the ranking is consumed, Translator.py:307-311)."""
+        w, d, T = self.w, self.d, self.tdtype
+        total = float(sum(pred_tokens))
+        weights = (ctypes.c_float * len(pred_tokens))(*[t / total for t in pred_tokens])
+        comb = self._buf("len_in", (B, d), T)
+        check(self.lib.care_combine_means(self.ctx, self.dt, ptr(means), B, n_pred, d, weights, ptr(comb), d,
+                                          self._stream()), "care_combine_means")
+        hid = self._buf("len_hid", (B, d), T)
+        self.gemm(comb, w["len_W0"], w["len_b0"], hid, B, d, d, act=ACT_RELU)
+        logits = torch.empty((B, _round_up(self.max_len, 8)), dtype=torch.float32, device=self.device)
+        self.gemm(hid, w["len_W3"], w["len_b3"], logits, B, self.max_len, d)
+        return logits
 
     def cross_kv(self, memory):
         """K/V of the cross-attention memory, projected once per video (hoisted out of the step loop)."""
@@ -395,6 +408,166 @@ class CareEngine:
         check(lib.care_beam_finalize(ctx, ctypes.byref(bst), float(beam_alpha), topk, ptr(out_tok), ptr(out_len),
                                      ptr(out_score), ptr(out_t), st), "care_beam_finalize")
         return out_tok, out_len, out_score, out_t
+
+
+    # ------------------------------------------------------------------------------------------
+    # full-sequence decoder pass (mask-predict passes and the stateless decoding_phase)
+    # ------------------------------------------------------------------------------------------
+    def _sequence_hidden(self, tokens, positions, R, L, kv, n_videos, causal, add_feats, gsg):
+        """Decoder layer over R sequences of L tokens (reference: Decoder/Transformer.py:161-237).
+        tokens / positions: int32 [R*L]; kv: cross K/V [n_videos, Lm, 2d]; the R rows are video-major
+        (R / n_videos consecutive rows per video).  Returns the hidden states [R*L, d]."""
+        lib, ctx, dt, w, d, T = self.lib, self.ctx, self.dt, self.w, self.d, self.tdtype
+        st = self._stream()
+        N = R * L
+        rpv = (R // n_videos) * L
+        x0 = self._buf("sq_x0", (N, d), T); x1 = self._buf("sq_x1", (N, d), T)
+        x2 = self._buf("sq_x2", (N, d), T); x3 = self._buf("sq_x3", (N, d), T)
+        cx = self._buf("sq_ctx", (N, d), T); qc = self._buf("sq_qc", (N, d), T)
+        qkv = self._buf("sq_qkv", (N, 3 * d), T)
+        y32 = self._buf("sq_y32", (N, d), torch.float32)
+        hb = self._buf("sq_ffn", (N, self.F), T)
+        check(lib.care_embed_ln(ctx, dt, ptr(tokens), ptr(positions), 0, ptr(w["word"]), ptr(w["pos"]), ptr(add_feats),
+                                ptr(gsg), rpv, ptr(w["emb_g"]), ptr(w["emb_b"]), self.eps, N, d, ptr(x0), st),
+              "care_embed_ln")
+        self.gemm(x0, w["Wqkv"], w["bqkv"], qkv, N, 3 * d, d)
+        check(lib.care_group_attn(ctx, dt, ptr(qkv), 3 * d, ptr(qkv), 3 * d, d, 2 * d, R, L, L, self.H, d, ptr(tokens),
+                                  1 if causal else 0, None, ptr(cx), st), "care_group_attn(self)")
+        self.gemm(cx, w["Wo"], w["bo"], y32, N, d, d)
+        check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x0), ptr(w["ln1_g"]), ptr(w["ln1_b"]), self.eps, N, d, ptr(x1),
+                              st), "care_add_ln")
+        self.gemm(x1, w["Wxq"], w["bxq"], qc, N, d, d)
+        check(lib.care_group_attn(ctx, dt, ptr(qc), d, ptr(kv), 2 * d, 0, d, n_videos, rpv, self.Lm, self.H, d, None, 0,
+                                  ptr(w["hybrid_bias"]), ptr(cx), st), "care_group_attn(cross)")
+        self.gemm(cx, w["Wxo"], w["bxo"], y32, N, d, d)
+        check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x1), ptr(w["ln2_g"]), ptr(w["ln2_b"]), self.eps, N, d, ptr(x2),
+                              st), "care_add_ln")
+        self.gemm(x2, w["W1"], w["b1"], hb, N, self.F, d, act=ACT_RELU)
+        self.gemm(hb, w["W2"], w["b2"], y32, N, d, self.F)
+        check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x2), ptr(w["ln3_g"]), ptr(w["ln3_b"]), self.eps, N, d, ptr(x3),
+                              st), "care_add_ln")
+        return x3
+
+    def _memory_mean(self, memory):
+        B = memory.shape[0]
+        out = torch.empty((B, self.d), dtype=torch.float32, device=self.device)
+        check(self.lib.care_rows_mean(self.ctx, self.dt, ptr(memory), B, memory.shape[1], self.d, ptr(out),
+                                      self._stream()), "care_rows_mean")
+        return out
+
+    def sequence_logits(self, input_ids, inputs, last_only=False, decoding_type=None):
+        """Stateless `decoding_phase` (Framework.py:240-269): logits for a whole batch of prefixes.
+        `inputs['encoder_hidden_states']` may hold one row per video or be already repeated per beam
+        (auto_enlarge): the cross K/V are projected for the rows that are given."""
+        decoding_type = decoding_type or self.opt["decoding_type"]
+        memory = inputs["encoder_hidden_states"]
+        if memory.dtype != self.tdtype or not memory.is_contiguous():
+            memory = memory.to(self.tdtype).contiguous()
+        n_mem = memory.shape[0]
+        R, L = input_ids.shape
+        if R % n_mem != 0:
+            raise ValueError("input_ids rows (%d) must be a multiple of the memory rows (%d)" % (R, n_mem))
+        if L > self.max_len:
+            raise ValueError("sequence length %d exceeds max_len %d" % (L, self.max_len))
+        tokens = input_ids.to(self.device, torch.int32).contiguous().view(-1)
+        positions = torch.arange(L, dtype=torch.int32, device=self.device).repeat(R)
+        gsg = inputs.get("semantic_hidden_states") if self.use_gsg else None
+        if gsg is not None:
+            gsg = gsg.to(self.device, torch.float32).contiguous()
+            if gsg.shape[0] != n_mem:
+                raise ValueError("semantic_hidden_states rows must match encoder_hidden_states rows")
+        nar = decoding_type == "NARFormer"
+        add = self._memory_mean(memory) if nar else None
+        kv = self.cross_kv(memory)
+        x3 = self._sequence_hidden(tokens, positions, R, L, kv, n_mem, not nar, add, gsg)
+        if last_only:
+            x3 = x3.view(R, L, self.d)[:, -1, :].contiguous()
+            rows = R
+        else:
+            rows = R * L
+        logits = torch.empty((rows, self.ldv), dtype=torch.float32, device=self.device)
+        self.gemm(x3, self.w["Wvocab"], None, logits, rows, self.V, self.d)
+        logits = logits[:, :self.V]
+        return logits if last_only else logits.view(R, L, self.V)
+
+    # ------------------------------------------------------------------------------------------
+    # mask-predict  (reference: models/Translator.py:240-318 + misc/Decoding/na_algorithms.py:146-197)
+    # ------------------------------------------------------------------------------------------
+    def mask_predict(self, enc, opt, length_beam_size, length_bias=0, beam_alpha=1.0, trace=None):
+        lib, ctx = self.lib, self.ctx
+        st = self._stream()
+        memory = enc["encoder_hidden_states"]
+        B = memory.shape[0]
+        i32 = torch.int32
+        if "preds_length_logits" in enc:
+            n = length_beam_size
+            lengths = torch.empty((B, n), dtype=i32, device=self.device)
+            lg = enc["preds_length_logits"]
+            check(lib.care_nar_length_beam(ctx, ptr(lg), lg.stride(0), B, self.max_len, n, int(length_bias), 4,
+                                           self.max_len, ptr(lengths), st), "care_nar_length_beam")
+        else:
+            lo, hi = opt.get("na_length_range", [5, 11])
+            lengths = torch.arange(lo, hi, dtype=i32, device=self.device).unsqueeze(0).repeat(B, 1).contiguous()
+            n = lengths.shape[1]
+        L = int(lengths.max().item())   # the one host read before the passes (reference: Translator.py:273)
+        R = B * n
+        use_ct = bool(opt.get("use_ct", False))
+        T = opt.get("iterations", 5) + (1 if use_ct else 0)
+        # floor(len * (1 - c/T)) exactly as na_algorithms.py:176 computes it (fp32 tensor times python float)
+        table = torch.stack([(torch.arange(self.max_len + 1).float() * (1.0 - (c / T))).long()
+                             for c in range(T)]).to(self.device, i32).contiguous()
+        tokens = torch.empty((R, L), dtype=i32, device=self.device)
+        positions = torch.empty((R * L,), dtype=i32, device=self.device)
+        probs = torch.empty((R, L), dtype=torch.float32, device=self.device)
+        new_idx = torch.empty((R * L,), dtype=i32, device=self.device)
+        new_prob = torch.empty((R * L,), dtype=torch.float32, device=self.device)
+        mask_ind = torch.empty((R, L), dtype=torch.uint8, device=self.device)
+        check(lib.care_nar_init(ctx, ptr(lengths), R, L, VIS if use_ct else MASK, ptr(tokens), ptr(positions),
+                                ptr(probs), st), "care_nar_init")
+        kv = self.cross_kv(memory)
+        add = self._memory_mean(memory)
+        gsg = enc.get("semantic_hidden_states") if self.use_gsg else None
+        N = R * L
+
+        def one_pass():
+            x3 = self._sequence_hidden(tokens.view(-1), positions, R, L, kv, B, False, add, gsg)
+            if self.fused_vocab:
+                nseg = int(lib.care_vocab_beam_nseg(ctx, N, self.V))
+                part = self._buf("nar_partials", (N, nseg, 6), torch.float32)
+                check(lib.care_vocab_beam_partials(ctx, ptr(x3), self.d, ptr(self.w["Wvocab"]),
+                                                   self.w["Wvocab"].stride(0), N, self.V, self.d, 1, ptr(part), nseg,
+                                                   st), "care_vocab_beam_partials")
+                check(lib.care_nar_best_partials(ctx, ptr(part), nseg, N, self.V, ptr(new_idx), ptr(new_prob), st),
+                      "care_nar_best_partials")
+            else:
+                logits = self._buf("nar_logits", (N, self.ldv), torch.float32)
+                self.gemm(x3, self.w["Wvocab"], None, logits, N, self.V, self.d)
+                check(lib.care_nar_best_logits(ctx, ptr(logits), self.ldv, N, self.V, ptr(new_idx), ptr(new_prob), st),
+                      "care_nar_best_logits")
+
+        one_pass()
+        check(lib.care_nar_apply(ctx, ptr(tokens), ptr(probs), ptr(new_idx), ptr(new_prob), None, ptr(lengths), R, L,
+                                 1 if use_ct else 0, st), "care_nar_apply")
+        if trace is not None:
+            trace.append(dict(c=0, tokens=tokens.cpu().clone(), probs=probs.cpu().clone()))
+        for c in range(1, T):
+            mode = 0 if (use_ct and c == 1) else 1
+            check(lib.care_nar_remask(ctx, ptr(tokens), ptr(probs), ptr(lengths), ptr(table[c]), mode, R, L,
+                                      ptr(mask_ind), st), "care_nar_remask")
+            one_pass()
+            check(lib.care_nar_apply(ctx, ptr(tokens), ptr(probs), ptr(new_idx), ptr(new_prob), ptr(mask_ind),
+                                     ptr(lengths), R, L, 0, st), "care_nar_apply")
+            if trace is not None:
+                trace.append(dict(c=c, tokens=tokens.cpu().clone(), probs=probs.cpu().clone(),
+                                  mask=mask_ind.cpu().clone()))
+        out_tok = torch.empty((B, 1, L), dtype=i32, device=self.device)
+        out_lp = torch.empty((B, 1, L), dtype=torch.float32, device=self.device)
+        best = torch.empty((B,), dtype=i32, device=self.device)
+        check(lib.care_nar_select(ctx, ptr(tokens), ptr(probs), ptr(lengths), B, n, L, float(beam_alpha), ptr(out_tok),
+                                  ptr(out_lp), ptr(best), st), "care_nar_select")
+        if trace is not None:
+            trace.append(dict(lengths=lengths.cpu().clone(), best=best.cpu().clone()))
+        return out_tok, out_lp
 
 
 def hyps_from_device(out_tok, out_len, out_score, out_t, beam_alpha, topk):

@@ -133,6 +133,8 @@ class TransformerSeq2Seq(nn.Module):
             out = eng.encode(feats)
         if eng.concat_concepts:
             out["semantic_embs"] = out["encoder_hidden_states"][:, eng.enc_len:, :]
+        if "preds_length_logits" in out:   # pred_length.py:22 (API decoration; the decode ranks the logits)
+            out["preds_length"] = torch.log_softmax(out["preds_length_logits"][:, :eng.max_len], dim=-1)
         return out
 
     def prepare_inputs_for_decoder(self, encoding_phase_outputs, batch):

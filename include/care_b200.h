@@ -131,6 +131,58 @@ int care_cross_attn_step(care_ctx* ctx, int dtype, const void* q, int64_t ldq, c
                          int B, int K, int H, int d, const float* hybrid_bias, const int32_t* done,
                          void* ctx_out, void* stream);
 
+/* Full-sequence attention over groups: every query row of group g attends the key rows
+ * [g*nk, (g+1)*nk) of the key/value matrix `kv` (row stride ldkv elements; K at column k_col + 64*head,
+ * V at v_col + 64*head).  Query / output rows of group g are [g*nq, (g+1)*nq).  Masks as in
+ * Transformer.py:15-47,169-174 + Attention.py:104-111: key_tokens (int32 [n_groups*nk], may be NULL)
+ * masks <pad> keys, causal masks keys k > query index (needs nq == nk), bias fp32 [H, nk] is added after
+ * masking.  Used by the mask-predict passes (Translator.py:240-305, na_algorithms.py:67-82: self
+ * attention with group = one candidate sequence; cross attention with group = one video and
+ * nq = candidates*L rows sharing the video's memory) and by the stateless decoding_phase
+ * (Framework.py:240-269).  q, kv, out are `dtype`. */
+int care_group_attn(care_ctx* ctx, int dtype, const void* q, int64_t ldq, const void* kv, int64_t ldkv,
+                    int k_col, int v_col, int n_groups, int nq, int nk, int H, int d,
+                    const int32_t* key_tokens, int causal, const float* bias, void* out, void* stream);
+
+/* out fp32 [B, d] = mean over the `rows` rows of x [B, rows, d] (Transformer.py:182-189,
+ * enhance_input == 2: mean of the decoder memory added to every input embedding of a NAR pass). */
+int care_rows_mean(care_ctx* ctx, int dtype, const void* x, int B, int rows, int d, float* out, void* stream);
+/* out T [B, ld_out] (first d columns) = sum_s weights[s] * means[b, s*d + :]; weights is a HOST array of
+ * n <= 8 floats (pred_length.py:14-17: mean over all predictor tokens, from the per-stream means). */
+int care_combine_means(care_ctx* ctx, int dtype, const void* means, int B, int n, int d, const float* weights,
+                       void* out, int64_t ld_out, void* stream);
+
+/* Mask-predict bookkeeping, all device side (replaces the host loops of models/Translator.py:240-318
+ * and misc/Decoding/na_algorithms.py:60-82,128-197).  R = B * n_cand candidate rows, L tokens each. */
+/* predict_length_beam (Translator.py:307-311): top-n_cand classes by (logit desc, index asc), + bias, clamp */
+int care_nar_length_beam(care_ctx* ctx, const float* logits, int64_t ld, int B, int n_classes, int n_cand,
+                         int length_bias, int min_len, int max_len, int32_t* lengths, void* stream);
+/* canvas (Translator.py:275-280; na_algorithms.py:60-65): tokens[r,p] = first_token if p < lengths[r] else
+ * <pad>; positions[r*L+p] = p; probs = 0 */
+int care_nar_init(care_ctx* ctx, const int32_t* lengths, int R, int L, int first_token, int32_t* tokens,
+                  int32_t* positions, float* probs, void* stream);
+/* generate_step_with_prob (na_algorithms.py:6-14): per token row arg max and its softmax probability,
+ * from fp32 logits, or from the records of care_vocab_beam_partials (K = 1) */
+int care_nar_best_logits(care_ctx* ctx, const float* logits, int64_t ldv, int rows, int V, int32_t* idx,
+                         float* prob, void* stream);
+int care_nar_best_partials(care_ctx* ctx, const float* partials, int nseg, int rows, int V, int32_t* idx,
+                           float* prob, void* stream);
+/* write-back (na_algorithms.py:67-82,185-190): where mask_ind (NULL = everywhere) tokens/probs := new, pad
+ * positions forced to (<pad>, 1); zero_mask_token: probs := 0 where the new token is <mask> (:64) */
+int care_nar_apply(care_ctx* ctx, int32_t* tokens, float* probs, const int32_t* new_idx, const float* new_prob,
+                   const uint8_t* mask_ind, const int32_t* lengths, int R, int L, int zero_mask_token,
+                   void* stream);
+/* what to re-predict (na_algorithms.py:128-137,172-182).  mode 0: positions holding <mask>; mode 1: the
+ * max(1, num_mask_by_len[lengths[r]]) lowest-probability positions (ties: lower position), which are set
+ * to <mask>.  mask_ind uint8 [R, L] out. */
+int care_nar_remask(care_ctx* ctx, int32_t* tokens, const float* probs, const int32_t* lengths,
+                    const int32_t* num_mask_by_len, int mode, int R, int L, uint8_t* mask_ind, void* stream);
+/* final choice (Translator.py:292-303): per video argmax over candidates of sum_p log(prob) / len^alpha
+ * (fp32); out_tokens int32 [B, L], out_lprobs fp32 [B, L], out_best int32 [B] (may be NULL) */
+int care_nar_select(care_ctx* ctx, const int32_t* tokens, const float* probs, const int32_t* lengths, int B,
+                    int n_cand, int L, float alpha, int32_t* out_tokens, float* out_lprobs, int32_t* out_best,
+                    void* stream);
+
 /* Beam state, all device resident (replaces misc/Decoding/Beam.py's per-video Python objects). */
 typedef struct care_beam_state {
   int32_t B, K, T_max, V, need;   /* need = max(K, topk)  (Beam.py:10) */

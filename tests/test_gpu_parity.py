@@ -187,3 +187,92 @@ def test_wrapper_checkpoint_roundtrip(tmp_path):
 def test_no_gpu_no_fallback_message():
     from care_b200 import _lib
     assert os.path.isfile(_lib.LIB_PATH)
+
+
+NAR_CASES = ["cfg5_plain", "cfg5_sharp", "cfg5_noct_sharp"]
+
+
+@pytest.mark.parametrize("name", NAR_CASES)
+def test_nar_fp32_matches_reference_golden(name):
+    """Mask-predict (config 5) in the fp32 parity mode: chosen lengths, tokens and per-token log-probs
+    against the unmodified reference's outputs; a differing video must be explained by an oracle
+    near-tie (length-candidate score gap or token probability gap)."""
+    import care_b200
+    rec = load_golden(name)
+    opt, sd, feats = rebuild_case(rec)
+    model = _gpu_model(opt, sd, "fp32")
+    tr = care_b200.get_translator(opt)
+    hyps, lprobs = tr.translate_batch([model], {"feats": [f.cuda() for f in feats]})
+    o_h, o_p, otr = co.nar_translate(sd, opt, feats, return_trace=True)
+    assert o_h == rec["hyps"]
+    enc = model.encoding_phase([f.cuda() for f in feats])
+    if "preds_length" in rec:
+        got = enc["preds_length"].cpu()
+        assert (got - torch.tensor(rec["preds_length"])).abs().max().item() < 1e-4
+    exact = 0
+    for v in range(len(hyps)):
+        if hyps[v] == rec["hyps"][v]:
+            exact += 1
+            a, b = torch.tensor(lprobs[v][0]), torch.tensor(rec["scores"][v][0])
+            assert (a - b).abs().max().item() < 2e-4 * max(1.0, b.abs().max().item()), (v, a, b)
+        else:
+            top2 = otr["avg"][v].topk(2)[0]
+            assert float(top2[0] - top2[1]) < 1e-3, "video %d differs with a clear candidate margin" % v
+    print("\n%s fp32: %d/%d mask-predict outputs identical to the reference" % (name, exact, len(hyps)))
+    assert exact >= 0.75 * len(hyps)
+
+
+@pytest.mark.parametrize("name", ["cfg5_sharp", "cfg5_plain"])
+def test_nar_bf16(name):
+    """bf16 mask-predict: well-formed output, same chosen length for most videos, token agreement."""
+    import care_b200
+    rec = load_golden(name)
+    opt, sd, feats = rebuild_case(rec)
+    model = _gpu_model(opt, sd, "bf16")
+    tr = care_b200.get_translator(opt)
+    hyps, lprobs = tr.translate_batch([model], {"feats": [f.cuda() for f in feats]})
+    assert len(hyps) == len(rec["hyps"])
+    agree, total = 0, 0
+    for v in range(len(hyps)):
+        assert len(hyps[v]) == 1 and len(hyps[v][0]) == len(lprobs[v][0])
+        ref = rec["hyps"][v][0]
+        got = hyps[v][0]
+        n_ref = sum(1 for t in ref if t != 0)
+        n_got = sum(1 for t in got if t != 0)
+        if n_ref == n_got:
+            total += n_ref
+            agree += sum(int(a == b) for a, b in zip(got[:n_ref], ref[:n_ref]))
+    print("\n%s bf16: %d/%d tokens identical on same-length outputs" % (name, agree, total))
+    assert total > 0 and agree >= 0.6 * total
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["cfg2_sharp", "cfg5_sharp"])
+def test_decoding_phase_stateless(name, precision):
+    """Framework.decoding_phase(input_ids, inputs) (full prefix, no cache) against the oracle, for
+    per-video and per-beam-row (auto_enlarge'd) memory layouts, all positions and last position."""
+    rec = load_golden(name)
+    opt, sd, feats = rebuild_case(rec, batch=3)
+    model = _gpu_model(opt, sd, precision)
+    enc = model.encoding_phase([f.cuda() for f in feats])
+    inputs = model.prepare_inputs_for_decoder(enc, {})
+    g = torch.Generator().manual_seed(5)
+    rep, L = 2, 7
+    ids = torch.randint(6, opt["vocab_size"], (3 * rep, L), generator=g)
+    if opt["decoding_type"] == "ARFormer":
+        ids[:, 0] = 2
+    ids[1, 4] = 0
+    ids[4, L - 1] = 0
+    o_inputs = {k: co.repeat_rows(v.float().cpu(), rep) for k, v in inputs.items()}
+    sd_o = sd if precision == "fp32" else {
+        k: (v.bfloat16().float() if v.dim() == 2 and "embeddings" not in k else v) for k, v in sd.items()}
+    ref_all = co.decoding_phase(sd_o, opt, ids, o_inputs)
+    ref_last = co.decoding_phase(sd_o, opt, ids, o_inputs, last_time_step_logits=True)
+    got_all = model.decoding_phase(ids.cuda(), inputs)["logits"].cpu()
+    enlarged = {k: co.repeat_rows(v, rep) for k, v in inputs.items()}
+    got_last = model.decoding_phase(ids.cuda(), enlarged, last_time_step_logits=True)["logits"].cpu()
+    tol = 2e-5 if precision == "fp32" else 1e-2
+    scale = ref_all.abs().max().item()
+    assert got_all.shape == ref_all.shape and got_last.shape == ref_last.shape
+    assert (got_all - ref_all).abs().max().item() < tol * scale
+    assert (got_last - ref_last).abs().max().item() < tol * scale
