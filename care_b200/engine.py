@@ -184,6 +184,12 @@ class CareEngine:
     def free_workspaces(self):
         self._ws.clear()
 
+    def copy_stream(self):
+        """Side stream for host->device feature copies that overlap the decode."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        return self._copy_stream
+
     def launch_count(self):
         return int(self.lib.care_ctx_launch_count(self.ctx))
 

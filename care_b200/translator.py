@@ -39,13 +39,118 @@ class Translator_ARFormer(object):
         if self.ar_token_id is not None:
             raise NotImplementedError("ar_token_id is outside the accelerated hot path")
 
+    # host-resident batches larger than this are decoded in chunks whose host->device copies overlap
+    # the previous chunk's decode (the copy of 4096 videos' fp32 features is 1.4 GB)
+    pipeline_chunk = 2048
+
     def translate_batch(self, models, batch, *args, **kwargs):
         model = _single_model(models)
+        feats = batch["feats"]
         with torch.no_grad():
-            out = self.decode_on_device(model, batch["feats"])
+            if feats[0].device.type == "cpu" and feats[0].shape[0] > self.pipeline_chunk:
+                out = self.decode_pipelined(model, feats, self.pipeline_chunk)
+            else:
+                out = self.decode_on_device(model, feats)
         return hyps_from_device(*out, self.beam_alpha, self.topk)
 
-    def decode_on_device(self, model, feats, trace=None):
+    def translate_stream(self, models, batches, device_hook=None, **kwargs):
+        """Throughput API for a stream of host-resident batches (the `for batch in loader` loop of
+        translate.py:34-43): yields `(hyps, scores)` per batch, in order, with the same values as
+        `translate_batch`.  While batch i decodes, the features of batch i+1 are copied host->device
+        on a side stream, and the ids of batch i-1 are read back and turned into Python lists.
+        `device_hook(out) -> out` (optional) runs on the device results before they are read back,
+        e.g. the all-gather of care_b200.sharding for a video-sharded multi-GPU run."""
+        model = _single_model(models)
+        eng = model.engine()
+        dev = eng.device
+        n_mod = len(eng.modality)
+        main = torch.cuda.current_stream(dev)
+        side = eng.copy_stream()
+        staging = [None, None]
+        freed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def stage(i, batch):
+            feats = list(batch["feats"][:n_mod])
+            if feats[0].device.type != "cpu":
+                return feats, None
+            shapes = [tuple(f.shape) for f in feats]
+            if staging[i % 2] is None or [tuple(t.shape) for t in staging[i % 2]] != shapes:
+                staging[i % 2] = [torch.empty(f.shape, dtype=f.dtype, device=dev) for f in feats]
+                for t in staging[i % 2]:
+                    t.record_stream(side)
+            ev = torch.cuda.Event()
+            with torch.cuda.stream(side):
+                if i >= 2:
+                    side.wait_event(freed[i % 2])
+                for dst, src in zip(staging[i % 2], feats):
+                    dst.copy_(src, non_blocking=True)
+                ev.record(side)
+            return staging[i % 2], ev
+
+        it = iter(batches)
+        try:
+            nxt = stage(0, next(it))
+        except StopIteration:
+            return
+        pending = None
+        i = 0
+        with torch.no_grad():
+            while nxt is not None:
+                cur = nxt
+                try:
+                    nxt = stage(i + 1, next(it))
+                except StopIteration:
+                    nxt = None
+                if cur[1] is not None:
+                    main.wait_event(cur[1])
+                out = self.decode_on_device(model, cur[0], early_exit_every=0)
+                freed[i % 2].record(main)
+                if device_hook is not None:
+                    out = device_hook(out)
+                if pending is not None:
+                    yield hyps_from_device(*pending, self.beam_alpha, self.topk)
+                pending = out
+                i += 1
+        if pending is not None:
+            yield hyps_from_device(*pending, self.beam_alpha, self.topk)
+
+    def decode_pipelined(self, model, host_feats, chunk):
+        """Chunked decode of a host-resident batch: chunk i+1's features are copied on a side stream into
+        the other staging set while chunk i decodes.  Videos are independent, so results are identical
+        to one big call."""
+        eng = model.engine()
+        dev = eng.device
+        n_mod = len(eng.modality)
+        host_feats = list(host_feats[:n_mod])
+        B = host_feats[0].shape[0]
+        bounds = [(a, min(a + chunk, B)) for a in range(0, B, chunk)]
+        main = torch.cuda.current_stream(dev)
+        side = eng.copy_stream()
+        staging = [[torch.empty((chunk,) + tuple(f.shape[1:]), dtype=f.dtype, device=dev) for f in host_feats]
+                   for _ in range(2)]
+        copied = [torch.cuda.Event() for _ in bounds]
+        freed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def enqueue_copy(i):
+            a, b = bounds[i]
+            with torch.cuda.stream(side):
+                if i >= 2:
+                    side.wait_event(freed[i % 2])
+                for dst, src in zip(staging[i % 2], host_feats):
+                    dst[:b - a].copy_(src[a:b], non_blocking=True)
+                copied[i].record(side)
+
+        enqueue_copy(0)
+        outs = []
+        for i, (a, b) in enumerate(bounds):
+            if i + 1 < len(bounds):
+                enqueue_copy(i + 1)
+            main.wait_event(copied[i])
+            outs.append(self.decode_on_device(model, [t[:b - a] for t in staging[i % 2]], early_exit_every=0))
+            freed[i % 2].record(main)
+        return tuple(torch.cat([o[j] for o in outs], dim=0) for j in range(4))
+
+    def decode_on_device(self, model, feats, trace=None, early_exit_every=4):
         """Returns device tensors (ids [B, topk, T] int32 PAD-filled, lengths, raw scores, steps)."""
         eng = model.engine()
         if eng.max_len != self.max_len:
@@ -53,7 +158,7 @@ class Translator_ARFormer(object):
         enc = model.encoding_phase(feats)
         B = enc["encoder_hidden_states"].shape[0]
         return eng.ar_decode(enc, B, beam_size=self.beam_size, topk=self.topk, beam_alpha=self.beam_alpha,
-                             trace=trace)
+                             trace=trace, early_exit_every=early_exit_every)
 
 
 class Translator_NARFormer(object):

@@ -276,3 +276,24 @@ def test_decoding_phase_stateless(name, precision):
     assert got_all.shape == ref_all.shape and got_last.shape == ref_last.shape
     assert (got_all - ref_all).abs().max().item() < tol * scale
     assert (got_last - ref_last).abs().max().item() < tol * scale
+
+
+def test_host_batches_chunked_and_streamed_match_single_call():
+    """Host-resident features: the chunk-pipelined translate_batch and the translate_stream generator
+    return exactly what one device-resident call returns (videos are independent units)."""
+    import care_b200
+    rec = load_golden("cfg2_sharp")
+    opt, sd, feats = rebuild_case(rec)
+    model = _gpu_model(opt, sd, "fp32")
+    tr = care_b200.get_translator(opt)
+    ref_h, ref_s = tr.translate_batch([model], {"feats": [f.cuda() for f in feats]})
+    tr.pipeline_chunk = 5
+    pinned = [f.pin_memory() for f in feats]
+    h, s = tr.translate_batch([model], {"feats": pinned})
+    assert h == ref_h and s == ref_s
+    batches = [{"feats": [f[a:b].contiguous().pin_memory() for f in feats]} for a, b in ((0, 4), (4, 8), (8, 12))]
+    got = list(tr.translate_stream([model], batches))
+    assert len(got) == 3
+    assert sum((g[0] for g in got), []) == ref_h
+    assert sum((g[1] for g in got), []) == ref_s
+    assert list(tr.translate_stream([model], [])) == []
