@@ -1,10 +1,11 @@
-// Decode-step attention for the bf16 mode: HBM-bound, one warp per (video, head).
+// Decode-step attention for the bf16 mode: HBM-bound, one 4-warp CTA per (video, head).
 //
 // The v0 SIMT kernel (attention.cu) spent ~10k issue slots per (video, head) on per-key FFMA/shuffle
 // chains and reached only ~22 % of HBM bandwidth (profiles/r01_ncu_full_v0_step15.txt).  Here:
 //   * the K and V tiles of one (video, head) - 114 x 64 (cross) or t*K x 64 (self) bf16 - are staged in
 //     shared memory by ONE TMA tensor copy each (SWIZZLE_128B), so the bytes in flight per SM are set
-//     by resident warps x 2 tiles, not by registers;
+//     by resident CTAs x 2 tiles, not by registers; the four warps of the CTA split the keys so the
+//     tile is held for a short compute phase only;
 //   * S = Q K^T and O = P V run as warp-level mma.sync.m16n8k16 (M = the K beams padded to 16) on
 //     ldmatrix fragments; this is only to cut issue slots - 0.15 MFLOP per 29 KB tile is far below
 //     what would justify a tcgen05/TMEM round trip - and leaves HBM as the bound;
@@ -100,34 +101,40 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // physical byte offset of 16-byte chunk `c16` of row `r` inside a SWIZZLE_128B tile (1024-B aligned)
 __device__ __forceinline__ uint32_t sw128(int r, int c16) { return (uint32_t)(r * 128 + ((c16 ^ (r & 7)) << 4)); }
 
-// NT = key tiles of 8 the registers are sized for (n_keys <= 8 * NT)
-template <int NT, bool SELF, int WARPS>
+// One CTA of 4 warps per (video, head).  The keys are split over the warps in steps of 16 (flash-decoding
+// inside the CTA): each warp computes S, a local softmax and a partial O for its key range, the partials
+// are merged through shared memory.  KKW = 16-key steps per warp the registers are sized for
+// (n_keys <= 64 * KKW).
+constexpr int COMB_LD = 72;   // floats per row of the merge buffer (64 + pad: <= 2-way bank conflicts)
+
+template <int KKW, bool SELF, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x * WARPS + warp;
-  if (item >= p.n_items) return;
-  const int v = item / p.H, h = item - v * p.H;
-  if (p.done != nullptr && p.done[v]) return;
+  const int v = blockIdx.x / p.H, h = blockIdx.x - v * p.H;
+  if (p.done != nullptr && p.done[v]) return;   // uniform for the CTA
   const int K = p.K, n_keys = p.n_keys;
 
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t tile_bytes = (uint32_t)p.rows_pad * 128u;
-  const uint32_t k_s = base + (uint32_t)warp * 2u * tile_bytes;
-  const uint32_t v_s = k_s + tile_bytes;
-  const uint32_t aux = base + (uint32_t)WARPS * 2u * tile_bytes;
-  const uint32_t bar_k = aux + (uint32_t)warp * 16u, bar_v = bar_k + 8u;
+  const uint32_t k_s = base, v_s = base + tile_bytes;
+  const uint32_t aux = base + 2u * tile_bytes;
+  const uint32_t bar_k = aux, bar_v = aux + 8u;
+  uint8_t* aux_gen = smem_raw + (aux - raw);
+  uint32_t* mw = reinterpret_cast<uint32_t*>(aux_gen + 16);                 // [8 beams][8 words] key masks
+  float* stat = reinterpret_cast<float*>(aux_gen + 16 + 256);               // [WARPS][8][2] (max, sum)
+  float* comb = reinterpret_cast<float*>(aux_gen + 16 + 256 + 256);         // [WARPS][8][COMB_LD] partial O
 
   // V rows [n_keys, rows_pad) are multiplied by P == 0: they must hold finite values
   {
     uint8_t* v_gen = smem_raw + (v_s - raw);
     const int n16 = (p.rows_pad - n_keys) * 8;
-    for (int i = lane; i < n16; i += 32)
+    for (int i = threadIdx.x; i < n16; i += WARPS * 32)
       *reinterpret_cast<uint4*>(v_gen + (size_t)n_keys * 128 + (size_t)i * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
-  if (lane == 0) {
+  if (threadIdx.x == 0) {
     mbar_init(bar_k, 1);
     mbar_init(bar_v, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -147,44 +154,46 @@ attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     const __nv_bfloat16* qrow = p.q + (int64_t)(v * K + (g < K ? g : 0)) * p.q_ld + h * DH;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      const uint32_t lo = *reinterpret_cast<const uint32_t*>(qrow + 16 * ks + 2 * tig);
-      const uint32_t hi = *reinterpret_cast<const uint32_t*>(qrow + 16 * ks + 2 * tig + 8);
-      qa[ks][0] = g < K ? lo : 0u;
-      qa[ks][1] = g < K ? hi : 0u;
+      qa[ks][0] = *reinterpret_cast<const uint32_t*>(qrow + 16 * ks + 2 * tig);
+      qa[ks][1] = *reinterpret_cast<const uint32_t*>(qrow + 16 * ks + 2 * tig + 8);
     }
   }
   // self: bit j of beam b's mask = key j (position j / K, slot j % K) is on b's prefix and not <pad>
-  uint32_t wmask[(NT + 3) / 4];
   if (SELF) {
-    uint32_t* mw = reinterpret_cast<uint32_t*>(smem_raw + (aux - raw) + WARPS * 16) + warp * 8 * ((NT + 3) / 4);
-    constexpr int WPB = (NT + 3) / 4;
-    for (int i = lane; i < 8 * WPB; i += 32) mw[i] = 0u;
-    __syncwarp();
-    for (int i = lane; i < K * p.n_pos; i += 32) {
+    for (int i = threadIdx.x; i < 64; i += WARPS * 32) mw[i] = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * p.n_pos; i += WARPS * 32) {
       const int b = i / p.n_pos, pp = i - b * p.n_pos;
       const int slot = (pp == p.n_pos - 1) ? b : (int)p.anc[((int64_t)v * K + b) * p.anc_stride + pp];
       const int tok = p.tok_hist[(int64_t)v * p.tok_stride + pp * K + slot];
       if (tok != CARE_PAD) {
         const int j = pp * K + slot;
-        atomicOr(&mw[b * WPB + (j >> 5)], 1u << (j & 31));
+        atomicOr(&mw[b * 8 + (j >> 5)], 1u << (j & 31));
       }
     }
-    __syncwarp();
-#pragma unroll
-    for (int w = 0; w < WPB; ++w) wmask[w] = mw[g * WPB + w];
   }
-  __syncwarp();
-
-  // ---- S = Q K^T ---------------------------------------------------------------------------------
-  float s[NT][2];
-  mbar_wait(bar_k, 0);
-  {
-    const int m = lane >> 3, rr = lane & 7;
+  __syncthreads();   // mbarrier init + mask words visible to every warp
+  if (g >= K) {
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
+    for (int ks = 0; ks < 4; ++ks) qa[ks][0] = qa[ks][1] = 0u;
+  }
+
+  // this warp's 16-key steps
+  const int n_kk = p.rows_pad >> 4;
+  const int kk0 = (warp * n_kk) / WARPS, kk1 = ((warp + 1) * n_kk) / WARPS;
+  const int m = lane >> 3, rr = lane & 7;
+
+  // ---- S = Q K^T over the warp's keys ----------------------------------------------------------------
+  float s[2 * KKW][2];
+  mbar_wait(bar_k, 0);
+#pragma unroll
+  for (int i = 0; i < KKW; ++i) {
+    const int kk = kk0 + i;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
       float c[4] = {0.f, 0.f, 0.f, 0.f};
-      if (nt * 8 < n_keys) {
-        const int r = nt * 8 + rr;
+      if (kk < kk1) {
+        const int r = kk * 16 + half * 8 + rr;
 #pragma unroll
         for (int kp = 0; kp < 2; ++kp) {
           uint32_t b[4];
@@ -193,95 +202,127 @@ attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           mma_bf16(c, qa[2 * kp + 1][0], qa[2 * kp + 1][1], b[2], b[3]);
         }
       }
-      s[nt][0] = c[0];
-      s[nt][1] = c[1];
+      s[2 * i + half][0] = c[0];
+      s[2 * i + half][1] = c[1];
     }
   }
-  // ---- scale, mask / bias, softmax (fp32) ----------------------------------------------------------
+  // ---- scale, mask / bias, local softmax (fp32) ---------------------------------------------------
   float mx = -INFINITY;
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
+  for (int i = 0; i < KKW; ++i) {
+    const int kk = kk0 + i;
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int j = nt * 8 + 2 * tig + e;
-      float x = s[nt][e] * 0.125f;   // / sqrt(64), Attention.py:84
-      if (SELF) {
-        if (!((wmask[nt >> 2] >> (j & 31)) & 1u)) x = -1e9f;
-      } else if (p.bias != nullptr && j < n_keys) {
-        x += __ldg(p.bias + (int64_t)h * p.Lm + j);
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = kk * 16 + half * 8 + 2 * tig + e;
+        float x = s[2 * i + half][e] * 0.125f;   // / sqrt(64), Attention.py:84
+        if (SELF) {
+          if (!((mw[g * 8 + ((j >> 5) & 7)] >> (j & 31)) & 1u)) x = -1e9f;
+        } else if (p.bias != nullptr && j < n_keys) {
+          x += __ldg(p.bias + (int64_t)h * p.Lm + j);
+        }
+        if (kk >= kk1 || j >= n_keys) x = -INFINITY;
+        s[2 * i + half][e] = x;
+        mx = fmaxf(mx, x);
       }
-      if (j >= n_keys) x = -INFINITY;
-      s[nt][e] = x;
-      mx = fmaxf(mx, x);
     }
   }
   mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
   mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  const float mref = mx == -INFINITY ? 0.f : mx;   // a warp without keys contributes nothing
   float sum = 0.f;
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
+  for (int i = 0; i < 2 * KKW; ++i) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const float pe = __expf(s[nt][e] - mx);
-      s[nt][e] = pe;
+      const float pe = __expf(s[i][e] - mref);
+      s[i][e] = pe;
       sum += pe;
     }
   }
   sum += __shfl_xor_sync(0xffffffffu, sum, 1);
   sum += __shfl_xor_sync(0xffffffffu, sum, 2);
 
-  // ---- O = P V ---------------------------------------------------------------------------------------
+  // ---- partial O = P V -----------------------------------------------------------------------------
   float o[8][4];
 #pragma unroll
   for (int dn = 0; dn < 8; ++dn)
 #pragma unroll
     for (int e = 0; e < 4; ++e) o[dn][e] = 0.f;
   mbar_wait(bar_v, 0);
-  {
-    const int m = lane >> 3, rr = lane & 7;
 #pragma unroll
-    for (int kk = 0; kk < NT / 2; ++kk) {
-      if (kk * 16 < n_keys) {
-        const float p0 = s[2 * kk][0], p1 = s[2 * kk][1], p2 = s[2 * kk + 1][0], p3 = s[2 * kk + 1][1];
-        const uint32_t a0h = pack_bf16(p0, p1), a2h = pack_bf16(p2, p3);
-        const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&a0h);
-        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&a2h);
-        const uint32_t a0l = pack_bf16(p0 - __low2float(h0), p1 - __high2float(h0));
-        const uint32_t a2l = pack_bf16(p2 - __low2float(h2), p3 - __high2float(h2));
-        const int r = kk * 16 + 8 * (m & 1) + rr;
+  for (int i = 0; i < KKW; ++i) {
+    const int kk = kk0 + i;
+    if (kk < kk1) {
+      const float p0 = s[2 * i][0], p1 = s[2 * i][1], p2 = s[2 * i + 1][0], p3 = s[2 * i + 1][1];
+      const uint32_t a0h = pack_bf16(p0, p1), a2h = pack_bf16(p2, p3);
+      const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&a0h);
+      const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&a2h);
+      const uint32_t a0l = pack_bf16(p0 - __low2float(h0), p1 - __high2float(h0));
+      const uint32_t a2l = pack_bf16(p2 - __low2float(h2), p3 - __high2float(h2));
+      const int r = kk * 16 + 8 * (m & 1) + rr;
 #pragma unroll
-        for (int dp = 0; dp < 4; ++dp) {
-          uint32_t b[4];
-          ldsm_x4_trans(b, v_s + sw128(r, 2 * dp + (m >> 1)));
-          mma_bf16(o[2 * dp], a0h, a2h, b[0], b[1]);
-          mma_bf16(o[2 * dp], a0l, a2l, b[0], b[1]);
-          mma_bf16(o[2 * dp + 1], a0h, a2h, b[2], b[3]);
-          mma_bf16(o[2 * dp + 1], a0l, a2l, b[2], b[3]);
-        }
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t b[4];
+        ldsm_x4_trans(b, v_s + sw128(r, 2 * dp + (m >> 1)));
+        mma_bf16(o[2 * dp], a0h, a2h, b[0], b[1]);
+        mma_bf16(o[2 * dp], a0l, a2l, b[0], b[1]);
+        mma_bf16(o[2 * dp + 1], a0h, a2h, b[2], b[3]);
+        mma_bf16(o[2 * dp + 1], a0l, a2l, b[2], b[3]);
       }
     }
   }
-  if (g < K) {
-    const float inv = 1.0f / sum;
-    __nv_bfloat16* orow = p.out + (int64_t)(v * K + g) * p.d + h * DH + 2 * tig;
+  if (WARPS == 1) {   // short key sets: one warp saw every key, no merge
+    if (g < K) {
+      const float inv = 1.0f / sum;
+      __nv_bfloat16* orow = p.out + (int64_t)(v * K + g) * p.d + h * DH + 2 * tig;
 #pragma unroll
-    for (int dn = 0; dn < 8; ++dn)
-      *reinterpret_cast<__nv_bfloat162*>(orow + 8 * dn) = __floats2bfloat162_rn(o[dn][0] * inv, o[dn][1] * inv);
+      for (int dn = 0; dn < 8; ++dn)
+        *reinterpret_cast<__nv_bfloat162*>(orow + 8 * dn) = __floats2bfloat162_rn(o[dn][0] * inv, o[dn][1] * inv);
+    }
+    return;
+  }
+  // ---- merge the partials of the warps ---------------------------------------------------------------
+  {
+    float* crow = comb + ((size_t)warp * 8 + g) * COMB_LD + 2 * tig;
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn) *reinterpret_cast<float2*>(crow + 8 * dn) = make_float2(o[dn][0], o[dn][1]);
+    if (tig == 0) {
+      stat[(warp * 8 + g) * 2 + 0] = mx;
+      stat[(warp * 8 + g) * 2 + 1] = sum;
+    }
+  }
+  __syncthreads();
+  {
+    const int col = threadIdx.x & 63;
+    for (int b = threadIdx.x >> 6; b < K; b += WARPS / 2) {
+      float M = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) M = fmaxf(M, stat[(w * 8 + b) * 2]);
+      float num = 0.f, den = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) {
+        const float mwv = stat[(w * 8 + b) * 2];
+        const float sc = mwv == -INFINITY ? 0.f : __expf(mwv - M);
+        den += stat[(w * 8 + b) * 2 + 1] * sc;
+        num += comb[((size_t)w * 8 + b) * COMB_LD + col] * sc;
+      }
+      p.out[(int64_t)(v * K + b) * p.d + h * DH + col] = __float2bfloat16_rn(num / den);
+    }
   }
 }
 
-template <int NT, bool SELF>
+template <int KKW, bool SELF, int WARPS>
 static int launch(care_ctx* ctx, const CUtensorMap& tmap, const Params& p, cudaStream_t stream) {
-  constexpr int WARPS = 1;
-  auto kern = attn_mma_kernel<NT, SELF, WARPS>;
-  const size_t smem = (size_t)WARPS * 2 * p.rows_pad * 128 + 1024 + WARPS * 16 + (SELF ? WARPS * 8 * ((NT + 3) / 4) * 4 : 0);
+  auto kern = attn_mma_kernel<KKW, SELF, WARPS>;
+  const size_t smem = (size_t)2 * p.rows_pad * 128 + 1024 + 16 + 256 + 256 + (size_t)WARPS * 8 * COMB_LD * 4;
   static size_t configured = 0;
   if (smem > configured) {
     CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  const int grid = (p.n_items + WARPS - 1) / WARPS;
-  kern<<<grid, WARPS * 32, smem, stream>>>(tmap, p);
+  kern<<<p.n_items, WARPS * 32, smem, stream>>>(tmap, p);
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -310,7 +351,7 @@ int cross_step(care_ctx* ctx, const void* q, int64_t ldq, const void* kv, int Lm
   p.done = done;
   p.out = static_cast<__nv_bfloat16*>(ctx_out);
   p.n_items = B * H;
-  return launch<16, false>(ctx, tmap, p, stream);
+  return launch<2, false, 4>(ctx, tmap, p, stream);   // Lm <= 128: 8 steps of 16 keys over 4 warps
 }
 
 int self_step(care_ctx* ctx, const void* cache, int n_pos, int B, int K, int H, int d, const uint8_t* anc,
@@ -342,9 +383,10 @@ int self_step(care_ctx* ctx, const void* cache, int n_pos, int B, int K, int H, 
   p.done = done;
   p.out = static_cast<__nv_bfloat16*>(ctx_out);
   p.n_items = B * H;
-  if (n_keys <= 48) return launch<6, true>(ctx, tmap, p, stream);
-  if (n_keys <= 96) return launch<12, true>(ctx, tmap, p, stream);
-  return launch<20, true>(ctx, tmap, p, stream);
+  if (n_keys <= 16) return launch<1, true, 1>(ctx, tmap, p, stream);
+  if (n_keys <= 64) return launch<4, true, 1>(ctx, tmap, p, stream);   // short prefixes: one warp, no merge
+  if (n_keys <= 128) return launch<2, true, 4>(ctx, tmap, p, stream);
+  return launch<3, true, 4>(ctx, tmap, p, stream);   // <= 160 keys: 10 steps of 16 over 4 warps
 }
 
 }  // namespace attn_mma
