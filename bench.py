@@ -343,6 +343,26 @@ def run_care_arm(args):
     d2h_bytes = B * world * (Tm + 3) * 4
     assert len(hyps) == world * B and all(1 <= len(h[0]) <= Tm for h in hyps[:64])
 
+    # per-step decode latency at small batches (launch-bound regime: the decode is replayed as one CUDA graph)
+    latency = {}
+    if world == 1:
+        timed.on = False
+        for lb in (1, 64):
+            small = [f[:lb].contiguous() for f in dev_feats]
+            for _ in range(3):
+                tr.decode_on_device(model, small)
+            torch.cuda.synchronize(dev)
+            reps = 10
+            l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0.record()
+            for _ in range(reps):
+                tr.decode_on_device(model, small)
+            l1.record()
+            torch.cuda.synchronize(dev)
+            ms = l0.elapsed_time(l1) / reps
+            latency["batch_%d" % lb] = {"ms_per_caption_batch": ms, "us_per_beam_step": ms / Tm * 1e3,
+                                        "captions_per_sec": lb / ms * 1e3}
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -371,6 +391,7 @@ def run_care_arm(args):
         "config": {"workload": workload_name(args.config, B, args.precision), "beam_size": opt["beam_size"],
                    "per_gpu_batch": B, "global_batch": B * world, "parallelism": "video-sharded x%d" % world,
                    "decode_ms_per_beam_step": step_ms / Tm,
+                   "small_batch_latency": latency,
                    "l2_note": "inputs larger than L2: per-step working set (cross K/V 1.9 GB, KV cache up to 3.6 GB, "
                               "features 1.4 GB) >> 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,

@@ -56,6 +56,11 @@ class CareEngine:
         self.fused_vocab = precision == "bf16" and bool(opt.get("care_fused_vocab", True))
         self._ws = {}
         self._nseg = {}
+        # launch-bound regime (few rows per step): replay the whole decode as one CUDA graph
+        self.use_graphs = bool(opt.get("care_cuda_graph", True))
+        self.graph_max_rows = int(opt.get("care_cuda_graph_max_rows", 6144))
+        self._graphs = {}
+        self._graph_launches = 0
         self._prepare_weights(state_dict)
 
     def __del__(self):
@@ -182,6 +187,7 @@ class CareEngine:
         return t
 
     def free_workspaces(self):
+        self._graphs.clear()   # graphs hold raw pointers into the workspaces
         self._ws.clear()
 
     def copy_stream(self):
@@ -191,7 +197,8 @@ class CareEngine:
         return self._copy_stream
 
     def launch_count(self):
-        return int(self.lib.care_ctx_launch_count(self.ctx))
+        """Kernels launched so far: eager launches counted by the library + launches replayed by graphs."""
+        return int(self.lib.care_ctx_launch_count(self.ctx)) + self._graph_launches
 
     def gemm(self, A, W, bias, C, M, N, K, act=ACT_NONE, lda=None, ldc=None):
         out_dt = F32 if C.dtype == torch.float32 else BF16
@@ -296,10 +303,13 @@ class CareEngine:
         self.gemm(hid, w["len_W3"], w["len_b3"], logits, B, self.max_len, d)
         return logits
 
-    def cross_kv(self, memory):
+    def cross_kv(self, memory, static=False):
         """K/V of the cross-attention memory, projected once per video (hoisted out of the step loop)."""
         B = memory.shape[0]
-        kv = torch.empty((B, self.Lm, 2 * self.d), dtype=self.tdtype, device=self.device)
+        if static:
+            kv = self._buf("cross_kv", (B, self.Lm, 2 * self.d), self.tdtype)
+        else:
+            kv = torch.empty((B, self.Lm, 2 * self.d), dtype=self.tdtype, device=self.device)
         self.gemm(memory.view(B * self.Lm, self.d), self.w["Wxkv"], self.w["bxkv"], kv.view(B * self.Lm, 2 * self.d),
                   B * self.Lm, 2 * self.d, self.d)
         return kv
@@ -389,6 +399,8 @@ class CareEngine:
         K = beam_size
         need = max(K, topk)
         lib, ctx = self.lib, self.ctx
+        if trace is None and self.use_graphs and B * K <= self.graph_max_rows:
+            return self._ar_decode_graph(enc, B, K, topk, float(beam_alpha))
         st = self._stream()
         kv = self.cross_kv(enc["encoder_hidden_states"])
         bufs, bst = self._beam_buffers(B, K, need)
@@ -414,6 +426,53 @@ class CareEngine:
         check(lib.care_beam_finalize(ctx, ctypes.byref(bst), float(beam_alpha), topk, ptr(out_tok), ptr(out_len),
                                      ptr(out_score), ptr(out_t), st), "care_beam_finalize")
         return out_tok, out_len, out_score, out_t
+
+    def _ar_decode_graph(self, enc, B, K, topk, beam_alpha):
+        """The whole decode (cross K/V projection, beam init, max_len-1 steps, finalisation) as ONE CUDA
+        graph per (B, K, topk, alpha): a fixed launch sequence over fixed workspaces with no host
+        sync inside, so small batches are not bound by per-launch host overhead.  Inputs are copied
+        into static buffers, outputs are cloned out of them."""
+        lib, ctx = self.lib, self.ctx
+        Tm = self.max_len - 1
+        need = max(K, topk)
+        mem_in = enc["encoder_hidden_states"]
+        gsg_in = enc.get("semantic_hidden_states") if self.use_gsg else None
+        memory = self._buf("g_memory", (B, self.Lm, self.d), self.tdtype)
+        gsg = self._buf("g_gsg", (B, self.d), torch.float32) if gsg_in is not None else None
+        outs = (self._buf("g_out_tok", (B, topk, Tm), torch.int32), self._buf("g_out_len", (B, topk), torch.int32),
+                self._buf("g_out_score", (B, topk), torch.float32), self._buf("g_out_t", (B, topk), torch.int32))
+        memory.copy_(mem_in)
+        if gsg is not None:
+            gsg.copy_(gsg_in)
+        static_enc = {"encoder_hidden_states": memory, "semantic_hidden_states": gsg}
+
+        def body():
+            st = self._stream()
+            kv = self.cross_kv(memory, static=True)
+            bufs, bst = self._beam_buffers(B, K, need)
+            check(lib.care_beam_init(ctx, ctypes.byref(bst), BOS, st), "care_beam_init")
+            for t in range(1, self.max_len):
+                self.decode_step(t, B, K, static_enc, kv, bufs, bst)
+            check(lib.care_beam_finalize(ctx, ctypes.byref(bst), beam_alpha, topk, ptr(outs[0]), ptr(outs[1]),
+                                         ptr(outs[2]), ptr(outs[3]), st), "care_beam_finalize")
+
+        key = (B, K, topk, beam_alpha)
+        entry = self._graphs.get(key)
+        if entry is None:
+            before = int(lib.care_ctx_launch_count(ctx))
+            body()          # eager pass: allocates every workspace, encodes the TMA descriptors, sets attributes
+            n_launch = int(lib.care_ctx_launch_count(ctx)) - before
+            torch.cuda.current_stream(self.device).synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                body()
+            self._graphs[key] = (graph, n_launch)
+            self._graph_launches -= n_launch   # the capture pass went through the library's counter without running
+            # the eager pass already produced this call's result
+        else:
+            entry[0].replay()
+            self._graph_launches += entry[1]
+        return tuple(o.clone() for o in outs)
 
 
     # ------------------------------------------------------------------------------------------

@@ -297,3 +297,29 @@ def test_host_batches_chunked_and_streamed_match_single_call():
     assert sum((g[0] for g in got), []) == ref_h
     assert sum((g[1] for g in got), []) == ref_s
     assert list(tr.translate_stream([model], [])) == []
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cuda_graph_replay_matches_eager(precision):
+    """Small batches replay the whole decode as one CUDA graph: first call (eager + capture), replays,
+    and a graph-free engine must all return the same hypotheses; replays count their launches."""
+    import care_b200
+    rec = load_golden("cfg2_sharp")
+    opt, sd, feats = rebuild_case(rec)
+    dev = [f.cuda() for f in feats]
+    tr = care_b200.get_translator(opt)
+    eager = _gpu_model(dict(opt, care_cuda_graph=False), sd, precision)
+    ref = tr.translate_batch([eager], {"feats": dev})
+    model = _gpu_model(opt, sd, precision)
+    first = tr.translate_batch([model], {"feats": dev})
+    n0 = model.engine().launch_count()
+    second = tr.translate_batch([model], {"feats": dev})
+    n1 = model.engine().launch_count()
+    other = [f[[3, 1, 2, 0, 5, 4, 7, 6, 9, 8, 11, 10]].contiguous() for f in dev]   # same shape, other inputs
+    third = tr.translate_batch([model], {"feats": other})
+    assert first == ref and second == ref
+    assert n1 - n0 > 29 * 10, "graph replays must be counted as launches"
+    perm = [3, 1, 2, 0, 5, 4, 7, 6, 9, 8, 11, 10]
+    assert third[0] == [ref[0][i] for i in perm]
+    if precision == "fp32":
+        assert first[0] == rec["hyps"]
