@@ -106,6 +106,13 @@ int care_ctx_sm_count(const care_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
 int64_t care_ctx_launch_count(const care_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int care_ctx_set_early_exit(care_ctx* ctx, const int32_t* counter, int target) {
+  CARE_CHECK_ARG(ctx != nullptr, "care_ctx_set_early_exit: ctx is NULL");
+  ctx->skip_counter = counter;
+  ctx->skip_target = target;
+  return 0;
+}
+
 int care_ctx_set_option(care_ctx* ctx, const char* name, int value) {
   CARE_CHECK_ARG(ctx && name, "care_ctx_set_option: bad args");
   if (strcmp(name, "attn_impl") == 0) {

@@ -77,6 +77,10 @@ struct care_ctx {
   int sm_count = 0;
   int64_t launches = 0;
   int attn_impl = 1;   // 1: TMA + mma.sync attention for bf16 (default), 0: SIMT kernel everywhere
+  // device-side early exit: kernels without a per-video `done` predicate return at once when
+  // *skip_counter >= skip_target (all videos of the batch have finished); NULL disables
+  const int32_t* skip_counter = nullptr;
+  int skip_target = 0;
   care_tmap_encode_fn encode = nullptr;
   std::mutex mu;
   std::unordered_map<care::TmapKey, CUtensorMap, care::TmapKeyHash> tmaps;
@@ -86,12 +90,22 @@ namespace care {
 
 // Encodes (or fetches from the ctx cache) a bf16 SWIZZLE_128B tiled TMA descriptor.  gdim/box are
 // fastest-dimension first; gstride_bytes has rank-1 entries (dimension 0 is dense).  api.cu.
+struct EarlyExit {
+  const int32_t* counter;
+  int target;
+};
+inline EarlyExit early_exit_of(const care_ctx* ctx) { return EarlyExit{ctx->skip_counter, ctx->skip_target}; }
+
 int get_tmap_bf16(care_ctx* ctx, const void* ptr, int rank, const uint64_t* gdim, const uint64_t* gstride_bytes,
                   const uint32_t* box, CUtensorMap* out);
 
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool all_done(const EarlyExit& e) {
+  return e.counter != nullptr && *reinterpret_cast<const volatile int32_t*>(e.counter) >= e.target;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -13,7 +13,8 @@ template <typename OutT>
 __global__ void __launch_bounds__(THREADS)
 gemm_f32_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ W, int64_t ldw,
                 const float* __restrict__ bias, OutT* __restrict__ C, int64_t ldc, int M, int N, int n_store, int K,
-                int relu) {
+                int relu, const EarlyExit ee) {
+  if (all_done(ee)) return;
   __shared__ __align__(16) float As[2][BK][BM + 4];
   __shared__ __align__(16) float Ws[2][BK][BN + 4];
   const int tid = threadIdx.x;
@@ -114,11 +115,11 @@ int gemm_f32(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t l
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   if (out_dtype == CARE_F32)
     gemm_f32_kernel<float><<<grid, THREADS, 0, stream>>>((const float*)A, lda, (const float*)W, ldw, bias, (float*)C,
-                                                         ldc, M, N, n_pad, K, act == CARE_ACT_RELU);
+                                                         ldc, M, N, n_pad, K, act == CARE_ACT_RELU, early_exit_of(ctx));
   else
     gemm_f32_kernel<__nv_bfloat16><<<grid, THREADS, 0, stream>>>((const float*)A, lda, (const float*)W, ldw, bias,
                                                                  (__nv_bfloat16*)C, ldc, M, N, n_pad, K,
-                                                                 act == CARE_ACT_RELU);
+                                                                 act == CARE_ACT_RELU, early_exit_of(ctx));
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -8,6 +8,9 @@
 //   warps 4-7: epilogue      (tcgen05.ld 32x32b -> +bias/ReLU -> smem transpose -> coalesced 16 B stores)
 // The accumulator is double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Edges: TMA zero-fills out-of-bounds rows/columns of A and W; stores are predicated.
+#include <cstdint>
+#include <initializer_list>
+
 #include "tcgen05_util.cuh"
 
 namespace care {
@@ -17,7 +20,8 @@ template <int BN, typename OutT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                          const float* __restrict__ bias, OutT* __restrict__ C, int64_t ldc, int M, int N,
-                         int n_store, int K, int relu) {
+                         int n_store, int K, int relu, const EarlyExit ee) {
+  if (all_done(ee)) return;   // uniform over the grid: written by an earlier kernel of the stream
   using cfg = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -211,7 +215,7 @@ static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, c
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + BN - 1) / BN;
   const int grid = std::min(m_tiles * n_tiles, ctx->sm_count);
   kern<<<grid, NUM_THREADS, cfg::SMEM_BYTES, stream>>>(ta, tb, bias, reinterpret_cast<OutT*>(C), ldc, M, N, n_store, K,
-                                                       act == CARE_ACT_RELU ? 1 : 0);
+                                                       act == CARE_ACT_RELU ? 1 : 0, early_exit_of(ctx));
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -229,9 +233,18 @@ int gemm_bf16(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t 
   const int n_store = n_pad <= ldc ? n_pad : N;
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   auto tiles = [&](int bn) { return m_tiles * ((N + bn - 1) / bn); };
+  // tile width: fewest (waves x per-tile cost); per-tile cost ~ BN + a fixed part (A tile load, epilogue
+  // set-up), so narrow tiles win when 256-wide tiles would leave most SMs idle in the last wave
   int bn = 256;
-  if (tiles(256) < ctx->sm_count) bn = 128;
-  if (bn == 128 && tiles(128) < ctx->sm_count) bn = 64;
+  int64_t best = INT64_MAX;
+  for (int cand : {256, 128, 64}) {
+    const int64_t waves = (tiles(cand) + ctx->sm_count - 1) / ctx->sm_count;
+    const int64_t cost = waves * (cand + 64);
+    if (cost < best) {
+      best = cost;
+      bn = cand;
+    }
+  }
   CUtensorMap ta, tb;
   int rc = get_tmap(ctx, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BLOCK_M, &ta);
   if (rc) return rc;

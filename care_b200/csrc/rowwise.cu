@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(256)
 embed_ln_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ positions, int position,
                 const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ add,
                 const float* __restrict__ gsg, int rpv, const float* __restrict__ gamma,
-                const float* __restrict__ beta, float eps, int R, int d, T* __restrict__ out) {
+                const float* __restrict__ beta, float eps, int R, int d, T* __restrict__ out, const EarlyExit ee) {
+  if (all_done(ee)) return;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= R) return;
   const int nch = d / 128;
@@ -171,7 +172,8 @@ embed_ln_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(256)
 add_ln_kernel(const float* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
-              const float* __restrict__ beta, float eps, int R, int d, T* __restrict__ out) {
+              const float* __restrict__ beta, float eps, int R, int d, T* __restrict__ out, const EarlyExit ee) {
+  if (all_done(ee)) return;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= R) return;
   const int nch = d / 128;
@@ -263,11 +265,12 @@ int care_embed_ln(care_ctx* ctx, int dtype, const int32_t* tokens, const int32_t
   const int grid = (R + 7) / 8;
   if (dtype == CARE_F32)
     rw::embed_ln_kernel<float><<<grid, 256, 0, s>>>(tokens, positions, position, word_emb, pos_emb, add_feats, gsg,
-                                                    rows_per_video, gamma, beta, eps, R, d, (float*)out);
+                                                    rows_per_video, gamma, beta, eps, R, d, (float*)out,
+                                                    early_exit_of(ctx));
   else
     rw::embed_ln_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(tokens, positions, position, word_emb, pos_emb, add_feats,
                                                             gsg, rows_per_video, gamma, beta, eps, R, d,
-                                                            (__nv_bfloat16*)out);
+                                                            (__nv_bfloat16*)out, early_exit_of(ctx));
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -279,10 +282,11 @@ int care_add_ln(care_ctx* ctx, int dtype, const float* x, const void* residual, 
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = (R + 7) / 8;
   if (dtype == CARE_F32)
-    rw::add_ln_kernel<float><<<grid, 256, 0, s>>>(x, (const float*)residual, gamma, beta, eps, R, d, (float*)out);
+    rw::add_ln_kernel<float><<<grid, 256, 0, s>>>(x, (const float*)residual, gamma, beta, eps, R, d, (float*)out,
+                                                  early_exit_of(ctx));
   else
     rw::add_ln_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(x, (const __nv_bfloat16*)residual, gamma, beta, eps, R, d,
-                                                          (__nv_bfloat16*)out);
+                                                          (__nv_bfloat16*)out, early_exit_of(ctx));
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -44,7 +44,8 @@ __host__ __device__ inline int run_of_tile(int64_t t, int64_t T, int64_t G) { re
 template <int KB>
 __global__ void __launch_bounds__(VB_THREADS, 1)
 vocab_beam_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                          float* __restrict__ partials, int nseg, int M, int N, int K) {
+                          float* __restrict__ partials, int nseg, int M, int N, int K, const EarlyExit ee) {
+  if (all_done(ee)) return;
   using cfg = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -281,7 +282,8 @@ static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
     CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
     configured = true;
   }
-  kern<<<grid_for(ctx, R, V), VB_THREADS, cfg::SMEM_BYTES, stream>>>(ta, tb, partials, nseg, R, V, d);
+  kern<<<grid_for(ctx, R, V), VB_THREADS, cfg::SMEM_BYTES, stream>>>(ta, tb, partials, nseg, R, V, d,
+                                                                             early_exit_of(ctx));
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -405,19 +405,23 @@ class CareEngine:
         kv = self.cross_kv(enc["encoder_hidden_states"])
         bufs, bst = self._beam_buffers(B, K, need)
         check(lib.care_beam_init(ctx, ctypes.byref(bst), BOS, st), "care_beam_init")
-        for t in range(1, self.max_len):
-            audit = None
-            if trace is not None:
-                audit = (torch.empty((B, K + 1), dtype=torch.float32, device=self.device),
-                         torch.empty((B, K + 1), dtype=torch.int32, device=self.device))
-                pre = {k: bufs[k].cpu().clone() for k in ("anc", "tok_hist", "done", "scores", "cur_tok")}
-            logits = self.decode_step(t, B, K, enc, kv, bufs, bst, audit, want_logits=trace_logits)
-            if trace is not None:
-                trace.append(dict(step=t, pre=pre, cand_val=audit[0].cpu(), cand_idx=audit[1].cpu(),
-                                  logits=logits[:, :self.V].cpu().clone() if trace_logits else None))
-            if early_exit_every and t % early_exit_every == 0 and t < self.max_len - 1:
-                if int(bufs["n_done"].item()) == B:
-                    break
+        lib.care_ctx_set_early_exit(ctx, ptr(bufs["n_done"]), B)
+        try:
+            for t in range(1, self.max_len):
+                audit = None
+                if trace is not None:
+                    audit = (torch.empty((B, K + 1), dtype=torch.float32, device=self.device),
+                             torch.empty((B, K + 1), dtype=torch.int32, device=self.device))
+                    pre = {k: bufs[k].cpu().clone() for k in ("anc", "tok_hist", "done", "scores", "cur_tok")}
+                logits = self.decode_step(t, B, K, enc, kv, bufs, bst, audit, want_logits=trace_logits)
+                if trace is not None:
+                    trace.append(dict(step=t, pre=pre, cand_val=audit[0].cpu(), cand_idx=audit[1].cpu(),
+                                      logits=logits[:, :self.V].cpu().clone() if trace_logits else None))
+                if early_exit_every and t % early_exit_every == 0 and t < self.max_len - 1:
+                    if int(bufs["n_done"].item()) == B:
+                        break
+        finally:
+            lib.care_ctx_set_early_exit(ctx, None, 0)
         Tm = self.max_len - 1
         out_tok = torch.empty((B, topk, Tm), dtype=torch.int32, device=self.device)
         out_len = torch.empty((B, topk), dtype=torch.int32, device=self.device)
@@ -451,8 +455,12 @@ class CareEngine:
             kv = self.cross_kv(memory, static=True)
             bufs, bst = self._beam_buffers(B, K, need)
             check(lib.care_beam_init(ctx, ctypes.byref(bst), BOS, st), "care_beam_init")
-            for t in range(1, self.max_len):
-                self.decode_step(t, B, K, static_enc, kv, bufs, bst)
+            lib.care_ctx_set_early_exit(ctx, ptr(bufs["n_done"]), B)
+            try:
+                for t in range(1, self.max_len):
+                    self.decode_step(t, B, K, static_enc, kv, bufs, bst)
+            finally:
+                lib.care_ctx_set_early_exit(ctx, None, 0)
             check(lib.care_beam_finalize(ctx, ctypes.byref(bst), beam_alpha, topk, ptr(outs[0]), ptr(outs[1]),
                                          ptr(outs[2]), ptr(outs[3]), st), "care_beam_finalize")
 

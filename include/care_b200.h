@@ -51,6 +51,12 @@ void care_ctx_destroy(care_ctx* ctx);
 int care_ctx_sm_count(const care_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches claim) */
 int64_t care_ctx_launch_count(const care_ctx* ctx);
+/* Device-side early exit for a decode loop with no host polling: while `counter` is non-NULL every
+ * kernel without a per-video predicate (GEMMs, embedding / residual LayerNorm) launched through this
+ * ctx returns at once when *counter >= target.  The beam kernels keep care_beam_state.n_done, so
+ * (st.n_done, B) makes the steps after the last video finished cost only their launches
+ * (replaces the host-side `if not active: break`, Translator.py:77).  Pass NULL to disable. */
+int care_ctx_set_early_exit(care_ctx* ctx, const int32_t* counter, int target);
 /* implementation switches for A/B tests.  "attn_impl": 1 = TMA + tensor-core attention for bf16
  * (default), 0 = the SIMT attention kernel for every dtype. */
 int care_ctx_set_option(care_ctx* ctx, const char* name, int value);

@@ -450,3 +450,39 @@ def test_fused_vocab_beam_matches_unfused(env, B, K, V, d):
             if clear.all():
                 assert torch.equal(a, b), (step, name)
         assert torch.isfinite(lse).all() and live.shape[0] == B
+
+
+def test_early_exit_flag_skips_gemm_and_ln(env):
+    """care_ctx_set_early_exit: once *counter >= target the GEMM / LayerNorm kernels return without
+    touching their outputs; below the target, or with the flag cleared, they run normally."""
+    lib, h, L = env
+    M, N, K = 200, 512, 512
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    W = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+    counter = torch.tensor([3], device="cuda", dtype=torch.int32)
+    ref = A.float() @ W.float().t()
+
+    def run():
+        C = torch.full((M, N), 7.0, device="cuda")
+        L.check(lib.care_gemm(h, BF16, A.data_ptr(), K, W.data_ptr(), K, None, C.data_ptr(), N, F32, M, N, K, 0,
+                              _stream()), "gemm")
+        x = torch.randn(M, N, device="cuda")
+        res = torch.randn(M, N, device="cuda").bfloat16()
+        g, b = torch.ones(N, device="cuda"), torch.zeros(N, device="cuda")
+        out = torch.full((M, N), 5.0, device="cuda", dtype=torch.bfloat16)
+        L.check(lib.care_add_ln(h, BF16, x.data_ptr(), res.data_ptr(), g.data_ptr(), b.data_ptr(), 1e-12, M, N,
+                                out.data_ptr(), _stream()), "add_ln")
+        torch.cuda.synchronize()
+        return C, out
+
+    try:
+        L.check(lib.care_ctx_set_early_exit(h, counter.data_ptr(), 3), "flag")
+        C, out = run()
+        assert (C == 7.0).all() and (out.float() == 5.0).all()
+        L.check(lib.care_ctx_set_early_exit(h, counter.data_ptr(), 4), "flag")
+        C, out = run()
+        assert (C - ref).abs().max().item() < 2e-3 * ref.abs().max().item() and not (out.float() == 5.0).all()
+    finally:
+        L.check(lib.care_ctx_set_early_exit(h, None, 0), "flag")
+    C, out = run()
+    assert (C - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
