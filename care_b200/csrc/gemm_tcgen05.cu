@@ -74,7 +74,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       // ===== TMA producer =====
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;  // n fastest: an A row block is read once
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const int s = it % cfg::STAGES;
           const uint32_t ph = (it / cfg::STAGES) & 1u;
@@ -120,7 +120,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     uint8_t* stage_gen = smem_gen + (epi_base - smem_base) + ew * 32 * EPI_PITCH;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-      const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;  // n fastest: an A row block is read once
       const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
       mbar_wait(tfull_bar(acc), aph);
       tc_fence_after();
