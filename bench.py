@@ -375,6 +375,16 @@ def run_care_arm(args):
     except Exception:
         pass
     kernels = summarise_kernels(timed.records, peaks)
+    # DRAM traffic per launch from the committed `ncu --set full` capture of one decode step (profiles/)
+    import glob
+    tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic_*.json")))
+    if tfiles and args.config == "cfg4" and B == 4096 and args.precision == "bf16":
+        tr_json = json.load(open(tfiles[-1]))
+        for r in kernels:
+            if r["kernel"] in tr_json:
+                r["traffic"] = tr_json[r["kernel"]]["traffic_bytes_per_launch"]
+                r["traffic_source"] = "%s (dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches " \
+                                      "of one decode step, t=15)" % os.path.relpath(tfiles[-1], ROOT)
     use_bf16 = args.precision == "bf16"
     if rank != 0:
         if world > 1:
@@ -408,8 +418,9 @@ def run_care_arm(args):
                         "i's decode; N>1 adds the per-step all-gather of ids).  single_call_value: one synchronous "
                         "Translator.translate_batch per step (H2D chunked in 2048-video halves)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-        "roofline_other_kernels": [{k: r[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac",
-                                                       "launches_timed", "avg_launch_ms", "total_ms")}
+        "roofline_other_kernels": [{k: r[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic",
+                                                       "launches_timed", "avg_launch_ms", "total_ms",
+                                                       "algorithmic_units_per_launch")}
                                    for r in kernels[1:]],
         "cpu_baseline": cpu,
     }
