@@ -153,6 +153,18 @@ class CareEngine:
         w["ln2_g"] = f32(xa + "LayerNorm.weight"); w["ln2_b"] = f32(xa + "LayerNorm.bias")
         hb = xa + "SDPA.hybrid_bias"
         w["hybrid_bias"] = f32(hb) if hb in sd else None
+        # attr_attention (CABase): a second cross-attention over the concept embeddings (Layers.py:117-119)
+        aa = L + "attr_attention."
+        self.attr_pos = None
+        if (aa + "SDPA.query.weight") in sd:
+            self.attr_pos = opt.get("attr_layer_pos", "cross2attr")
+            if self.attr_pos not in ("cross2attr", "attr2cross"):
+                raise ValueError("attr_layer_pos %r is outside the accelerated hot path" % self.attr_pos)
+            w["Waq"] = mat(sd[aa + "SDPA.query.weight"]); w["baq"] = f32(aa + "SDPA.query.bias")
+            w["Wakv"] = mat(torch.cat([sd[aa + "SDPA.key.weight"], sd[aa + "SDPA.value.weight"]], 0))
+            w["bakv"] = torch.cat([f32(aa + "SDPA.key.bias"), f32(aa + "SDPA.value.bias")])
+            w["Wao"] = mat(sd[aa + "dense.weight"]); w["bao"] = f32(aa + "dense.bias")
+            w["lna_g"] = f32(aa + "LayerNorm.weight"); w["lna_b"] = f32(aa + "LayerNorm.bias")
         w["W1"] = mat(sd[L + "ffn.dense1.weight"]); w["b1"] = f32(L + "ffn.dense1.bias")
         w["W2"] = mat(sd[L + "ffn.dense2.weight"]); w["b2"] = f32(L + "ffn.dense2.bias")
         w["ln3_g"] = f32(L + "ffn.LayerNorm.weight"); w["ln3_b"] = f32(L + "ffn.LayerNorm.bias")
@@ -268,11 +280,16 @@ class CareEngine:
                 kpad = w["s2h_W"].shape[1] if self.use_gsg else _round_up(self.n_attr, 64)
                 predsT = self._buf("preds_T", (B, kpad), T)
                 labels = torch.empty((B, self.n_concepts), dtype=torch.int64, device=self.device)
+                sem = None
+                if not self.concat_concepts and self.attr_pos is not None:
+                    sem = torch.empty((B, self.n_concepts, d), dtype=T, device=self.device)
+                    out["semantic_embs"] = sem
                 check(lib.care_concept_head(
                     ctx, dt, ptr(scores), ld_sc, B, self.n_attr, self.n_concepts, ptr(w["attr_word"]),
                     ptr(w["attr_pos"]), ptr(w["attr_g"]), ptr(w["attr_b"]), self.eps, d, ptr(preds), ptr(predsT),
-                    kpad, ptr(labels), ptr(memory) if self.concat_concepts else None, self.Lm, self.enc_len, st),
-                    "care_concept_head")
+                    kpad, ptr(labels), ptr(memory) if self.concat_concepts else ptr(sem),
+                    self.Lm if self.concat_concepts else self.n_concepts, self.enc_len if self.concat_concepts else 0,
+                    st), "care_concept_head")
                 out["semantic_labels"] = labels
                 if self.use_gsg:
                     gsg = torch.empty((B, d), dtype=torch.float32, device=self.device)
@@ -314,6 +331,38 @@ class CareEngine:
                   B * self.Lm, 2 * self.d, self.d)
         return kv
 
+    def attr_kv(self, enc, static=False):
+        """K/V of the concept embeddings for the attr_attention block, projected once per video."""
+        if self.attr_pos is None:
+            return None
+        sem = enc.get("semantic_embs")
+        if sem is None:
+            raise KeyError("this model has an attr_attention layer: `semantic_embs` is required")
+        if sem.dtype != self.tdtype or not sem.is_contiguous():
+            sem = sem.to(self.tdtype).contiguous()
+        B, n = sem.shape[0], sem.shape[1]
+        if static:
+            akv = self._buf("attr_kv", (B, n, 2 * self.d), self.tdtype)
+        else:
+            akv = torch.empty((B, n, 2 * self.d), dtype=self.tdtype, device=self.device)
+        self.gemm(sem.view(B * n, self.d), self.w["Wakv"], self.w["bakv"], akv.view(B * n, 2 * self.d), B * n,
+                  2 * self.d, self.d)
+        return akv
+
+    def _attr_block_step(self, x_in, x_out, akv, B, K, done):
+        """attr_attention for the newest position of every beam row: LN(dense(attn(q(x), concepts)) + x)."""
+        lib, ctx, dt, w, d, T = self.lib, self.ctx, self.dt, self.w, self.d, self.tdtype
+        st = self._stream()
+        R = B * K
+        qa = self._buf("qa", (R, d), T); cxa = self._buf("ctx_a", (R, d), T)
+        y32 = self._buf("y32", (R, d), torch.float32)
+        self.gemm(x_in, w["Waq"], w["baq"], qa, R, d, d)
+        check(lib.care_cross_attn_step(ctx, dt, ptr(qa), d, ptr(akv), akv.shape[1], B, K, self.H, d, None, done,
+                                       ptr(cxa), st), "care_cross_attn_step(attr)")
+        self.gemm(cxa, w["Wao"], w["bao"], y32, R, d, d)
+        check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x_in), ptr(w["lna_g"]), ptr(w["lna_b"]), self.eps, R, d,
+                              ptr(x_out), st), "care_add_ln")
+
     # ------------------------------------------------------------------------------------------
     # auto-regressive beam decode  (reference: models/Translator.py:35-220 + misc/Decoding/Beam.py)
     # ------------------------------------------------------------------------------------------
@@ -338,7 +387,7 @@ class CareEngine:
         st = BeamState(B=B, K=K, T_max=Tm, V=self.V, need=need, **{k: ptr(v) for k, v in bufs.items()})
         return bufs, st
 
-    def decode_step(self, t, B, K, enc, kv, bufs, bst, audit=None, want_logits=False):
+    def decode_step(self, t, B, K, enc, kv, bufs, bst, audit=None, want_logits=False, akv=None):
         """One beam step (len_input_ids == t) for every video; 14 kernel launches (15 unfused)."""
         lib, ctx, dt, w, d, T = self.lib, self.ctx, self.dt, self.w, self.d, self.tdtype
         st = self._stream()
@@ -363,12 +412,20 @@ class CareEngine:
         self.gemm(cx, w["Wo"], w["bo"], y32, R, d, d)
         check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x0), ptr(w["ln1_g"]), ptr(w["ln1_b"]), self.eps, R, d, ptr(x1),
                               st), "care_add_ln")
+        if self.attr_pos == "attr2cross":   # Layers.py:180-187
+            xa = self._buf("xa", (R, d), T)
+            self._attr_block_step(x1, xa, akv, B, K, done)
+            x1 = xa
         self.gemm(x1, w["Wxq"], w["bxq"], qc, R, d, d)
         check(lib.care_cross_attn_step(ctx, dt, ptr(qc), d, ptr(kv), self.Lm, B, K, self.H, d, ptr(w["hybrid_bias"]),
                                        done, ptr(cx), st), "care_cross_attn_step")
         self.gemm(cx, w["Wxo"], w["bxo"], y32, R, d, d)
         check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x1), ptr(w["ln2_g"]), ptr(w["ln2_b"]), self.eps, R, d, ptr(x2),
                               st), "care_add_ln")
+        if self.attr_pos == "cross2attr":   # Layers.py:217-225
+            xa = self._buf("xa", (R, d), T)
+            self._attr_block_step(x2, xa, akv, B, K, done)
+            x2 = xa
         self.gemm(x2, w["W1"], w["b1"], hb, R, self.F, d, act=ACT_RELU)
         self.gemm(hb, w["W2"], w["b2"], y32, R, d, self.F)
         check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x2), ptr(w["ln3_g"]), ptr(w["ln3_b"]), self.eps, R, d, ptr(x3),
@@ -403,6 +460,7 @@ class CareEngine:
             return self._ar_decode_graph(enc, B, K, topk, float(beam_alpha))
         st = self._stream()
         kv = self.cross_kv(enc["encoder_hidden_states"])
+        akv = self.attr_kv(enc)
         bufs, bst = self._beam_buffers(B, K, need)
         check(lib.care_beam_init(ctx, ctypes.byref(bst), BOS, st), "care_beam_init")
         lib.care_ctx_set_early_exit(ctx, ptr(bufs["n_done"]), B)
@@ -413,7 +471,7 @@ class CareEngine:
                     audit = (torch.empty((B, K + 1), dtype=torch.float32, device=self.device),
                              torch.empty((B, K + 1), dtype=torch.int32, device=self.device))
                     pre = {k: bufs[k].cpu().clone() for k in ("anc", "tok_hist", "done", "scores", "cur_tok")}
-                logits = self.decode_step(t, B, K, enc, kv, bufs, bst, audit, want_logits=trace_logits)
+                logits = self.decode_step(t, B, K, enc, kv, bufs, bst, audit, want_logits=trace_logits, akv=akv)
                 if trace is not None:
                     trace.append(dict(step=t, pre=pre, cand_val=audit[0].cpu(), cand_idx=audit[1].cpu(),
                                       logits=logits[:, :self.V].cpu().clone() if trace_logits else None))
@@ -449,16 +507,21 @@ class CareEngine:
         if gsg is not None:
             gsg.copy_(gsg_in)
         static_enc = {"encoder_hidden_states": memory, "semantic_hidden_states": gsg}
+        if self.attr_pos is not None:
+            sem = self._buf("g_sem", (B, self.n_concepts, self.d), self.tdtype)
+            sem.copy_(enc["semantic_embs"])
+            static_enc["semantic_embs"] = sem
 
         def body():
             st = self._stream()
             kv = self.cross_kv(memory, static=True)
+            akv = self.attr_kv(static_enc, static=True)
             bufs, bst = self._beam_buffers(B, K, need)
             check(lib.care_beam_init(ctx, ctypes.byref(bst), BOS, st), "care_beam_init")
             lib.care_ctx_set_early_exit(ctx, ptr(bufs["n_done"]), B)
             try:
                 for t in range(1, self.max_len):
-                    self.decode_step(t, B, K, static_enc, kv, bufs, bst)
+                    self.decode_step(t, B, K, static_enc, kv, bufs, bst, akv=akv)
             finally:
                 lib.care_ctx_set_early_exit(ctx, None, 0)
             check(lib.care_beam_finalize(ctx, ctypes.byref(bst), beam_alpha, topk, ptr(outs[0]), ptr(outs[1]),
@@ -486,7 +549,19 @@ class CareEngine:
     # ------------------------------------------------------------------------------------------
     # full-sequence decoder pass (mask-predict passes and the stateless decoding_phase)
     # ------------------------------------------------------------------------------------------
-    def _sequence_hidden(self, tokens, positions, R, L, kv, n_videos, causal, add_feats, gsg):
+    def _attr_block_seq(self, x_in, x_out, akv, n_videos, rpv, N):
+        lib, ctx, dt, w, d, T = self.lib, self.ctx, self.dt, self.w, self.d, self.tdtype
+        st = self._stream()
+        qa = self._buf("sq_qa", (N, d), T); cxa = self._buf("sq_ctx_a", (N, d), T)
+        y32 = self._buf("sq_y32", (N, d), torch.float32)
+        self.gemm(x_in, w["Waq"], w["baq"], qa, N, d, d)
+        check(lib.care_group_attn(ctx, dt, ptr(qa), d, ptr(akv), 2 * d, 0, d, n_videos, rpv, akv.shape[1], self.H, d,
+                                  None, 0, None, ptr(cxa), st), "care_group_attn(attr)")
+        self.gemm(cxa, w["Wao"], w["bao"], y32, N, d, d)
+        check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x_in), ptr(w["lna_g"]), ptr(w["lna_b"]), self.eps, N, d,
+                              ptr(x_out), st), "care_add_ln")
+
+    def _sequence_hidden(self, tokens, positions, R, L, kv, n_videos, causal, add_feats, gsg, akv=None):
         """Decoder layer over R sequences of L tokens (reference: Decoder/Transformer.py:161-237).
         tokens / positions: int32 [R*L]; kv: cross K/V [n_videos, Lm, 2d]; the R rows are video-major
         (R / n_videos consecutive rows per video).  Returns the hidden states [R*L, d]."""
@@ -509,12 +584,20 @@ class CareEngine:
         self.gemm(cx, w["Wo"], w["bo"], y32, N, d, d)
         check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x0), ptr(w["ln1_g"]), ptr(w["ln1_b"]), self.eps, N, d, ptr(x1),
                               st), "care_add_ln")
+        if self.attr_pos == "attr2cross":
+            xa = self._buf("sq_xa", (N, d), T)
+            self._attr_block_seq(x1, xa, akv, n_videos, rpv, N)
+            x1 = xa
         self.gemm(x1, w["Wxq"], w["bxq"], qc, N, d, d)
         check(lib.care_group_attn(ctx, dt, ptr(qc), d, ptr(kv), 2 * d, 0, d, n_videos, rpv, self.Lm, self.H, d, None, 0,
                                   ptr(w["hybrid_bias"]), ptr(cx), st), "care_group_attn(cross)")
         self.gemm(cx, w["Wxo"], w["bxo"], y32, N, d, d)
         check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x1), ptr(w["ln2_g"]), ptr(w["ln2_b"]), self.eps, N, d, ptr(x2),
                               st), "care_add_ln")
+        if self.attr_pos == "cross2attr":
+            xa = self._buf("sq_xa", (N, d), T)
+            self._attr_block_seq(x2, xa, akv, n_videos, rpv, N)
+            x2 = xa
         self.gemm(x2, w["W1"], w["b1"], hb, N, self.F, d, act=ACT_RELU)
         self.gemm(hb, w["W2"], w["b2"], y32, N, d, self.F)
         check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x2), ptr(w["ln3_g"]), ptr(w["ln3_b"]), self.eps, N, d, ptr(x3),
@@ -552,7 +635,10 @@ class CareEngine:
         nar = decoding_type == "NARFormer"
         add = self._memory_mean(memory) if nar else None
         kv = self.cross_kv(memory)
-        x3 = self._sequence_hidden(tokens, positions, R, L, kv, n_mem, not nar, add, gsg)
+        akv = self.attr_kv(inputs)
+        if akv is not None and akv.shape[0] != n_mem:
+            raise ValueError("semantic_embs rows must match encoder_hidden_states rows")
+        x3 = self._sequence_hidden(tokens, positions, R, L, kv, n_mem, not nar, add, gsg, akv)
         if last_only:
             x3 = x3.view(R, L, self.d)[:, -1, :].contiguous()
             rows = R
@@ -598,12 +684,13 @@ class CareEngine:
         check(lib.care_nar_init(ctx, ptr(lengths), R, L, VIS if use_ct else MASK, ptr(tokens), ptr(positions),
                                 ptr(probs), st), "care_nar_init")
         kv = self.cross_kv(memory)
+        akv = self.attr_kv(enc)
         add = self._memory_mean(memory)
         gsg = enc.get("semantic_hidden_states") if self.use_gsg else None
         N = R * L
 
         def one_pass():
-            x3 = self._sequence_hidden(tokens.view(-1), positions, R, L, kv, B, False, add, gsg)
+            x3 = self._sequence_hidden(tokens.view(-1), positions, R, L, kv, B, False, add, gsg, akv)
             if self.fused_vocab:
                 nseg = int(lib.care_vocab_beam_nseg(ctx, N, self.V))
                 part = self._buf("nar_partials", (N, nseg, 6), torch.float32)

@@ -55,9 +55,14 @@ class TransformerSeq2Seq(nn.Module):
                      "compositional_inter", "compositional_ffn", "pretrained_embs_path"):
             if opt.get(flag):
                 raise ValueError("option %r is outside the accelerated hot path" % flag)
-        if opt.get("use_attr", False) and opt.get("use_attr_type", "") not in ("emb_concat",):
-            raise ValueError("use_attr_type %r is outside the accelerated hot path (CARE uses G1Lc = emb_concat)"
-                             % opt.get("use_attr_type"))
+        if opt.get("use_attr", False) and opt.get("use_attr_type", "") not in ("emb_concat", "_att", "emb_att", "_concat"):
+            raise ValueError("use_attr_type %r is outside the accelerated hot path (CARE: G1Lc = emb_concat, "
+                             "CABase: G0L1 = _att)" % opt.get("use_attr_type"))
+        if layout.has_attr_attention(opt):
+            if opt.get("attr_layer_pos", "cross2attr") not in ("cross2attr", "attr2cross"):
+                raise ValueError("attr_layer_pos %r is outside the accelerated hot path" % opt.get("attr_layer_pos"))
+            if opt.get("add_hybrid_attention_bias", False):
+                raise ValueError("attr_attention with a hybrid attention bias is not a valid reference configuration")
         if not opt.get("trainable_pe", False):
             raise ValueError("sinusoidal position embeddings are outside the accelerated hot path")
         self.backbone = None  # translate.py:213 reads `.captioner.backbone`
@@ -66,6 +71,8 @@ class TransformerSeq2Seq(nn.Module):
             _register(self, name, torch.zeros(shape, dtype=dtype), kind in layout.BUFFER_KINDS)
         # reference: models/Framework.py:21-33
         self.input_keys_for_decoder = ["encoder_hidden_states"]
+        if opt.get("use_attr", False) and "att" in opt.get("use_attr_type", "").lower():
+            self.input_keys_for_decoder.append("semantic_embs")
         if "emb" in opt.get("use_attr_type", ""):
             self.input_keys_for_decoder.append("semantic_hidden_states")
         self._kinds = {n: k for n, (_, k) in layout.param_specs(opt).items()}
@@ -131,7 +138,7 @@ class TransformerSeq2Seq(nn.Module):
         feats = [f.to(eng.device, non_blocking=True) for f in feats]
         with torch.no_grad():
             out = eng.encode(feats)
-        if eng.concat_concepts:
+        if eng.concat_concepts and "semantic_embs" not in out:
             out["semantic_embs"] = out["encoder_hidden_states"][:, eng.enc_len:, :]
         if "preds_length_logits" in out:   # pred_length.py:22 (API decoration; the decode ranks the logits)
             out["preds_length"] = torch.log_softmax(out["preds_length_logits"][:, :eng.max_len], dim=-1)

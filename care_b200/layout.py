@@ -19,6 +19,11 @@ def hybrid_length(opt):
     return n
 
 
+def has_attr_attention(opt):
+    """reference: models/components/Layers.py:117-119 (`'att' in use_attr_type`, default 'att')."""
+    return bool(opt.get("use_attr", False)) and "att" in opt.get("use_attr_type", "att")
+
+
 def predictor_nets(opt):
     """Order of `predictor.nets.*` (reference: models/Predictor/__init__.py:26-60)."""
     nets = [c for c in opt["crits"] if c != "lang"] + list(opt.get("predictors_to_be_added", []))
@@ -79,8 +84,11 @@ def param_specs(opt):
     sp["decoder.embedding.position_embeddings.weight"] = ((opt["max_len"], d), "emb")
     ln("decoder.embedding.LayerNorm")
     L = "decoder.layers.0."
-    for att in ("intra_attention", "inter_attention"):
-        if att == "inter_attention" and opt.get("add_hybrid_attention_bias", False):
+    atts = ["intra_attention", "inter_attention"]
+    if has_attr_attention(opt):
+        atts.append("attr_attention")   # reference: deepcopy of inter_attention, Layers.py:117-119
+    for att in atts:
+        if att != "intra_attention" and opt.get("add_hybrid_attention_bias", False):
             sp[L + att + ".SDPA.hybrid_bias"] = ((opt["num_attention_heads"], hybrid_length(opt)), "zeros")
         for nm_ in ("query", "key", "value"):
             linear(L + att + ".SDPA." + nm_, d, d)

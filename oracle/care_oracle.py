@@ -136,6 +136,8 @@ def encoding_phase(sd, opt, feats: List[torch.Tensor]) -> Dict[str, torch.Tensor
 def decoder_input_keys(opt):
     """models/Framework.py:21-33 restricted to the branches the configs reach."""
     keys = ["encoder_hidden_states"]
+    if opt.get("use_attr", False) and "att" in opt.get("use_attr_type", "").lower():
+        keys.append("semantic_embs")
     if "emb" in opt.get("use_attr_type", ""):
         keys.append("semantic_hidden_states")
     return keys
@@ -153,7 +155,8 @@ def _attention(sd, p, opt, q_in, kv_in, mask):
     v = _heads(_lin(sd, p + ".SDPA.value", kv_in), H)
     s = torch.matmul(q, k.transpose(-1, -2))
     s = s / math.sqrt(q.shape[-1])
-    s = s.masked_fill(mask.unsqueeze(1), -1e9)
+    if mask is not None:
+        s = s.masked_fill(mask.unsqueeze(1), -1e9)
     if (p + ".SDPA.hybrid_bias") in sd:
         s = s + sd[p + ".SDPA.hybrid_bias"][None, :, None, :]
     pr = torch.softmax(s, dim=-1)
@@ -190,7 +193,17 @@ def decoder_hidden(sd, opt, input_ids, inputs, decoding_type=None):
 
     lp = "decoder.layers.0"
     x = _attention(sd, lp + ".intra_attention", opt, x, x, self_mask)
+    # attr_attention: a second cross-attention over the concept embeddings, no mask
+    # (models/components/Layers.py:117-119,140-155,180-225); position per `attr_layer_pos`
+    has_attr = opt.get("use_attr", False) and "att" in opt.get("use_attr_type", "att")
+    pos = opt.get("attr_layer_pos", "cross2attr")
+    if has_attr and pos == "parallel":
+        raise ValueError("attr_layer_pos='parallel' is outside the restated path")
+    if has_attr and pos == "attr2cross":
+        x = _attention(sd, lp + ".attr_attention", opt, x, inputs["semantic_embs"], None)
     x = _attention(sd, lp + ".inter_attention", opt, x, mem, cross_mask)
+    if has_attr and pos == "cross2attr":
+        x = _attention(sd, lp + ".attr_attention", opt, x, inputs["semantic_embs"], None)
     h = _lin(sd, lp + ".ffn.dense2", torch.relu(_lin(sd, lp + ".ffn.dense1", x)))
     return _ln(sd, lp + ".ffn.LayerNorm", h + x, opt["layer_norm_eps"])
 

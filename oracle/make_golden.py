@@ -34,6 +34,9 @@ CASES = [
     ("cfg5_sharp", "cfg5", {}, 6, dict(seed=6, perturb=True, sharpen=SHARP)),
     ("cfg5_noct_sharp", "cfg5", dict(use_ct=False, decoder="TransformerDecoder"), 4,
      dict(seed=7, perturb=True, sharpen=SHARP)),
+    # CABase (attr_attention layer, "Cross -> Semantic" and the reverse order)
+    ("cab_sharp", "cab", {}, 8, dict(seed=8, perturb=True, sharpen=SHARP)),
+    ("cab_attr2cross_sharp", "cab", dict(attr_layer_pos="attr2cross"), 6, dict(seed=9, perturb=True, sharpen=SHARP)),
 ]
 
 
@@ -51,7 +54,8 @@ def run_case(name, cfg, over, bsz, wkw, feat_seed=11):
     if "semantic_labels" in enc:
         rec["semantic_labels"] = enc["semantic_labels"].tolist()
         rec["preds_attr_head"] = enc["preds_attr"][:, :8].double().tolist()
-        rec["semantic_hidden_states_head"] = enc["semantic_hidden_states"][:, :8].double().tolist()
+        if enc.get("semantic_hidden_states") is not None:
+            rec["semantic_hidden_states_head"] = enc["semantic_hidden_states"][:, :8].double().tolist()
     if "preds_length" in enc:
         rec["preds_length"] = enc["preds_length"].double().tolist()
     rec["memory_head"] = enc["encoder_hidden_states"][:, ::17, :4].double().tolist()
@@ -62,7 +66,10 @@ def run_case(name, cfg, over, bsz, wkw, feat_seed=11):
 def main():
     os.makedirs(OUT, exist_ok=True)
     assert rh.reference_available(), "needs /root/reference"
+    only = set(sys.argv[1:])
     for case in CASES:
+        if only and case[0] not in only:
+            continue
         rec = run_case(*case)
         with open(os.path.join(OUT, rec["name"] + ".json"), "w") as f:
             json.dump(rec, f)
@@ -70,7 +77,7 @@ def main():
         print(rec["name"], "params", rec["n_params"], "lens", lens)
     # state_dict layout known-answers (module tree printed in notebooks/retrieval_robustness.ipynb:97-187)
     layout = {}
-    for cfg in ("cfg1", "cfg2", "cfg5"):
+    for cfg in ("cfg1", "cfg2", "cfg5", "cab"):
         opt = make_opt(**CONFIGS[cfg])
         model = rh.build_reference_model(opt)
         layout[cfg] = dict(

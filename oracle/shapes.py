@@ -40,6 +40,17 @@ def make_opt(task="CARE", arch="base", vocab_size=10547, beam_size=5, method="Tr
             add_hybrid_attention_bias=True, retrieval_topk=20, retrieval_arch="ViT",
             predictors_to_be_added=["SemanticContainer"], crits=["lang", "attribute"],
         )
+    elif task == "CABase":
+        # config/tasks.yaml:56-60: no GSG, LSG by a second cross-attention over the concept embeddings
+        # ("Cross -> Semantic"), visual-driven concept detection, no hybrid attention bias
+        opt.update(
+            modality="ami", modality_for_decoder="ami", modality_for_predictor="mi",
+            attribute_prediction=True, attribute_prediction_flags="V", attribute_prediction_k=500,
+            attribute_prediction_mean_pooling=True, attribute_prediction_channel_concat=True,
+            use_attr=True, use_attr_flags="G0L1", use_attr_type="_att", use_attr_topk=30,
+            attr_layer_pos="cross2attr", add_hybrid_attention_bias=False, retrieval_topk=20,
+            predictors_to_be_added=["SemanticContainer"], crits=["lang", "attribute"],
+        )
     else:
         raise ValueError(task)
     if method == "NACF":
@@ -75,4 +86,6 @@ CONFIGS = {
     "cfg3": dict(task="CARE", arch="median", vocab_size=14745, beam_size=5),
     "cfg4": dict(task="CARE", arch="large", vocab_size=14745, beam_size=5),
     "cfg5": dict(task="CARE", arch="base", vocab_size=10547, method="NACF"),
+    # the paper's second model (CABase, attr_attention decoder layer)
+    "cab": dict(task="CABase", arch="base", vocab_size=10547, beam_size=5),
 }

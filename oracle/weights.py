@@ -81,7 +81,8 @@ def make_state_dict(opt, seed=0, perturb=False, sharpen=None):
         sd[p + ".attr_embs.word_embeddings.weight"] = _xavier(gen, opt["attribute_prediction_k"], d)
         sd[p + ".attr_embs.position_embeddings.weight"] = _xavier(gen, opt["use_attr_topk"], d)
         _layernorm(sd, p + ".attr_embs.LayerNorm", d)
-        _linear(sd, gen, p + ".semantic2hidden", d, opt["attribute_prediction_k"], bias=False)
+        if "emb" in opt.get("use_attr_type", ""):   # pred_attribute.py:258-260
+            _linear(sd, gen, p + ".semantic2hidden", d, opt["attribute_prediction_k"], bias=False)
         net += 1
     if length_net:
         _linear(sd, gen, "predictor.nets.%d.net.0" % net, d, d)
@@ -93,8 +94,11 @@ def make_state_dict(opt, seed=0, perturb=False, sharpen=None):
     sd["decoder.embedding.position_embeddings.weight"] = _xavier(gen, opt["max_len"], d)
     _layernorm(sd, "decoder.embedding.LayerNorm", d)
     L = "decoder.layers.0."
-    for att in ("intra_attention", "inter_attention"):
-        if att == "inter_attention" and opt.get("add_hybrid_attention_bias", False):
+    atts = ["intra_attention", "inter_attention"]
+    if opt.get("use_attr", False) and "att" in opt.get("use_attr_type", "att"):
+        atts.append("attr_attention")   # deepcopy of inter_attention (models/components/Layers.py:117-119)
+    for att in atts:
+        if att != "intra_attention" and opt.get("add_hybrid_attention_bias", False):
             sd[L + att + ".SDPA.hybrid_bias"] = torch.zeros(opt["num_attention_heads"], hybrid_length(opt))
         for nm_ in ("query", "key", "value"):
             _linear(sd, gen, L + att + ".SDPA." + nm_, d, d)
