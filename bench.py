@@ -257,6 +257,15 @@ def run_care_arm(args):
             return sharding.gather_hypotheses(sharding.pack_hypotheses(*out), world * B)
         return out
 
+    # N > 1: every rank ends a step holding (a) the all-gathered ids of ALL videos, read back to a pinned host
+    # tensor, and (b) Python lists for its own shard (what a per-rank caption writer consumes)
+    gathered_host = torch.empty((world * B, 1, Tm + 3), dtype=torch.int32).pin_memory() if world > 1 else None
+
+    def gather_hook(out):
+        full = sharding.gather_hypotheses(sharding.pack_hypotheses(*out), world * B)
+        gathered_host.copy_(full, non_blocking=True)
+        return out
+
     def step_e2e():
         if world > 1:
             with torch.no_grad():
@@ -264,8 +273,8 @@ def run_care_arm(args):
                     out = tr.decode_pipelined(model, host_feats, tr.pipeline_chunk)
                 else:
                     out = tr.decode_on_device(model, host_feats)
-            full = sharding.gather_hypotheses(sharding.pack_hypotheses(*out), world * B)
-            return care_b200.engine.hyps_from_device(*sharding.unpack_hypotheses(full), tr.beam_alpha, tr.topk)
+            out = gather_hook(out)
+            return care_b200.engine.hyps_from_device(*out, tr.beam_alpha, tr.topk)
         return tr.translate_batch([model], {"feats": host_feats})
 
     def sync_all():
@@ -323,9 +332,6 @@ def run_care_arm(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_call_value = world * B * e2e_steps / (float(t.item()) / 1e3)
 
-        def gather_hook(out):
-            return sharding.unpack_hypotheses(sharding.gather_hypotheses(sharding.pack_hypotheses(*out), world * B))
-
         def stream_steps(n):
             got = 0
             hook = gather_hook if world > 1 else None
@@ -340,14 +346,17 @@ def run_care_arm(args):
         got = stream_steps(e2e_stream_steps)
         torch.cuda.synchronize(dev)
         e2e_ms = (time.perf_counter() - t0) * 1e3
-        assert got == world * B * e2e_stream_steps
+        assert got == B * e2e_stream_steps
         t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_value = world * B * e2e_stream_steps / (float(t.item()) / 1e3)
     clocks = sampler.stop() if rank == 0 else None
     d2h_bytes = B * world * (Tm + 3) * 4
-    assert hyps is None or (len(hyps) == world * B and all(1 <= len(h[0]) <= Tm for h in hyps[:64]))
+    assert hyps is None or (len(hyps) == B and all(1 <= len(h[0]) <= Tm for h in hyps[:64]))
+    if hyps is not None and world > 1:   # the gathered record of this rank's first video matches its own list
+        lo = rank * B
+        assert gathered_host[lo, 0, :len(hyps[0][0])].tolist() == hyps[0][0]
 
     # per-step decode latency at small batches (launch-bound regime: the decode is replayed as one CUDA graph)
     latency = {}
@@ -415,7 +424,8 @@ def run_care_arm(args):
                 "single_call_value": e2e_call_value,
                 "note": "value: Translator.translate_stream over the steps' pinned HOST batches -> Python lists "
                         "(every step's H2D copy and D2H read inside the timed region; step i+1's copy overlaps step "
-                        "i's decode; N>1 adds the per-step all-gather of ids).  single_call_value: one synchronous "
+                        "i's decode; N>1: + the per-step NCCL all-gather of ids, read back in full to pinned host memory on every rank, "
+                        "Python lists built for the rank's own shard).  single_call_value: one synchronous "
                         "Translator.translate_batch per step (H2D chunked in 2048-video halves)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "roofline_other_kernels": [{k: r[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic",
