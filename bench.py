@@ -170,7 +170,7 @@ class TimedLib:
 def kernel_work_table(esz):
     """name -> f(args) = (kernel label, bound, algorithmic units of one launch); DESIGN.md section 4."""
     return {
-        "care_gemm": lambda a: ("gemm_bf16_tcgen05_kernel", "tensor", 2.0 * a[10] * a[11] * a[12]),
+        "care_gemm": lambda a: ("gemm_bf16_tcgen05_kernel / gemm_bf16_2sm_kernel", "tensor", 2.0 * a[10] * a[11] * a[12]),
         "care_vocab_beam_partials": lambda a: ("vocab_beam_tcgen05_kernel", "tensor", 2.0 * a[5] * a[6] * a[7]),
         # cross: K/V of every video once + q in + ctx out
         "care_cross_attn_step": lambda a: ("attn_mma_kernel<cross>", "hbm",
@@ -390,8 +390,9 @@ def run_care_arm(args):
     if tfiles and args.config == "cfg4" and B == 4096 and args.precision == "bf16":
         tr_json = json.load(open(tfiles[-1]))
         for r in kernels:
-            if r["kernel"] in tr_json:
-                r["traffic"] = tr_json[r["kernel"]]["traffic_bytes_per_launch"]
+            tkey = r["kernel"].split(" / ")[0]
+            if tkey in tr_json:
+                r["traffic"] = tr_json[tkey]["traffic_bytes_per_launch"]
                 r["traffic_source"] = "%s (dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches " \
                                       "of one decode step, t=15)" % os.path.relpath(tfiles[-1], ROOT)
     use_bf16 = args.precision == "bf16"

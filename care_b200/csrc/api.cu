@@ -119,6 +119,10 @@ int care_ctx_set_option(care_ctx* ctx, const char* name, int value) {
     ctx->attn_impl = value;
     return 0;
   }
+  if (strcmp(name, "gemm_2sm") == 0) {
+    ctx->gemm_2sm = value;
+    return 0;
+  }
   care::set_error("care_ctx_set_option: unknown option '%s'", name);
   return -1;
 }

@@ -77,6 +77,10 @@ struct care_ctx {
   int sm_count = 0;
   int64_t launches = 0;
   int attn_impl = 1;   // 1: TMA + mma.sync attention for bf16 (default), 0: SIMT kernel everywhere
+  // 0: single-CTA tiles only, 1: CTA-pair (cta_group::2) tiles whenever the shape allows, 2 (default): pick per
+  // (M, N, K, out dtype) by timing both once on the first call with that shape (skipped while capturing)
+  int gemm_2sm = 2;
+  std::unordered_map<uint64_t, int> gemm_choice;
   // device-side early exit: kernels without a per-video `done` predicate return at once when
   // *skip_counter >= skip_target (all videos of the batch have finished); NULL disables
   const int32_t* skip_counter = nullptr;

@@ -5,8 +5,10 @@
 //   warp 0  : TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B tiles, 4-8 stage mbarrier ring)
 //   warp 1  : MMA issuer     (one lane issues tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16)
 //   warp 2  : TMEM allocator (2 accumulator stages x BN fp32 columns)
-//   warps 4-7: epilogue      (tcgen05.ld 32x32b -> +bias/ReLU -> smem transpose -> coalesced 16 B stores)
-// The accumulator is double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warps 4-7 / 8-11: two epilogue groups taking alternate tiles (tcgen05.ld 32x32b -> swizzled smem
+//                     transpose -> +bias/ReLU -> coalesced 16 B stores)
+// The accumulator is double buffered in TMEM (one buffer per epilogue group) so the epilogue of tile i
+// overlaps the MMAs of tiles i+1 and i+2.
 // Edges: TMA zero-fills out-of-bounds rows/columns of A and W; stores are predicated.
 #include <cstdint>
 #include <initializer_list>
@@ -14,10 +16,19 @@
 #include "tcgen05_util.cuh"
 
 namespace care {
+namespace tc2 {  // gemm_tcgen05_2sm.cu: returns 1 when the shape should use the single-CTA kernel
+int gemm_bf16_2sm(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
+                  int64_t ldc, int out_dtype, int M, int N, int n_store, int K, int act, cudaStream_t stream);
+}
 namespace tc {
 
+constexpr int GEMM_EPI_BYTES = 8 * 4096;   // one 32x32 fp32 staging block per epilogue warp
+template <int BN>
+constexpr int gemm_smem_bytes() { return Cfg<BN>::STAGES * Cfg<BN>::STAGE_BYTES + GEMM_EPI_BYTES + 256 + 1024; }
+constexpr int GEMM_THREADS = 384;   // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-7, 8-11: two epilogue groups
+
 template <int BN, typename OutT>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                          const float* __restrict__ bias, OutT* __restrict__ C, int64_t ldc, int M, int N,
                          int n_store, int K, int relu, const EarlyExit ee) {
@@ -28,7 +39,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - raw_addr);
   const uint32_t epi_base = smem_base + cfg::STAGES * cfg::STAGE_BYTES;
-  const uint32_t bar_base = epi_base + cfg::EPI_BYTES;
+  const uint32_t bar_base = epi_base + GEMM_EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (cfg::STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * cfg::STAGES + a); };
@@ -115,14 +126,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> (+bias, ReLU) -> smem transpose -> coalesced global stores =====
-    const int ew = warp - 4;  // == warp % 4: this warp may access TMEM lanes [32*ew, 32*ew+32)
-    uint8_t* stage_gen = smem_gen + (epi_base - smem_base) + ew * 32 * EPI_PITCH;
-    uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+    // ===== epilogue: TMEM -> registers -> (+bias, ReLU) -> global.  Two groups of 4 warps take alternate
+    // tiles (group g drains TMEM accumulator g), so each group has two mainloop times per tile; a thread
+    // owns one row and writes its 32 consecutive columns of a chunk as 16-byte stores. =====
+    const int grp = (warp - 4) >> 2;
+    const int ew = (warp - 4) & 3;  // == warp % 4: this warp may access TMEM lanes [32*ew, 32*ew+32)
+    uint8_t* stage_gen = smem_gen + (epi_base - smem_base) + (warp - 4) * 4096;   // 32 rows x 128 B per warp
+    uint32_t gcount = 0;
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, ++gcount) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;  // n fastest: an A row block is read once
-      const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
-      mbar_wait(tfull_bar(acc), aph);
+      mbar_wait(tfull_bar(grp), gcount & 1u);
       tc_fence_after();
       const int row_base = m_blk * BLOCK_M + ew * 32;
       if (row_base < M) {
@@ -131,56 +144,77 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           const int col0 = n_blk * BN + c * 32;
           if (col0 >= n_store) break;
           uint32_t v[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + c * 32, v);
-          float bl = 0.f;
-          if (bias != nullptr && col0 + lane < N) bl = __ldg(bias + col0 + lane);
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bl, j);
-            f[j] = relu ? fmaxf(x, 0.f) : x;
-          }
-          __syncwarp();
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + grp * BN + c * 32, v);
+          __syncwarp();   // the previous chunk's staged rows have been read
           if constexpr (sizeof(OutT) == 4) {
-            float4* dst = reinterpret_cast<float4*>(stage_gen + lane * EPI_PITCH);
+            // stage the 32x32 fp32 block (row = lane) with a 16-byte XOR swizzle, read it back row-major:
+            // every global store instruction then writes 4 full 128-byte rows
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(stage_gen + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             __syncwarp();
+            const int ch = lane & 7, col = col0 + ch * 4;
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias != nullptr) {
+              if (col + 3 < N) {
+                bv = __ldg(reinterpret_cast<const float4*>(bias + col));
+              } else {
+                if (col < N) bv.x = __ldg(bias + col);
+                if (col + 1 < N) bv.y = __ldg(bias + col + 1);
+                if (col + 2 < N) bv.z = __ldg(bias + col + 2);
+              }
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int r = i * 4 + (lane >> 3), ch = lane & 7;
-              const float4 val = *reinterpret_cast<const float4*>(stage_gen + r * EPI_PITCH + ch * 16);
-              const int row = row_base + r, col = col0 + ch * 4;
+              const int r = i * 4 + (lane >> 3);
+              float4 val = *reinterpret_cast<const float4*>(stage_gen + r * 128 + ((ch ^ (r & 7)) << 4));
+              val.x += bv.x; val.y += bv.y; val.z += bv.z; val.w += bv.w;
+              if (relu) {
+                val.x = fmaxf(val.x, 0.f); val.y = fmaxf(val.y, 0.f);
+                val.z = fmaxf(val.z, 0.f); val.w = fmaxf(val.w, 0.f);
+              }
+              const int row = row_base + r;
               if (row < M && col < n_store)
                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(C) + static_cast<int64_t>(row) * ldc + col) = val;
             }
           } else {
-            constexpr int PITCH16 = 80;  // 32 bf16 = 64 B + 16 B pad
-            uint4* dst = reinterpret_cast<uint4*>(stage_gen + lane * PITCH16);
+            // bf16 out: bias / ReLU in registers needs the column's bias per element -> do it after the
+            // transpose too: stage fp32, read back 8 columns per thread, convert, one 16-byte store each
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(stage_gen + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+            const int c8 = lane & 3, col = col0 + c8 * 8;   // 8 consecutive columns = staged chunks 2*c8, 2*c8+1
+            float bb[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) bb[q] = (bias != nullptr && col + q < N) ? __ldg(bias + col + q) : 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = i * 8 + (lane >> 2);
+              const float4 lo = *reinterpret_cast<const float4*>(stage_gen + r * 128 + (((2 * c8) ^ (r & 7)) << 4));
+              const float4 hi = *reinterpret_cast<const float4*>(stage_gen + r * 128 + (((2 * c8 + 1) ^ (r & 7)) << 4));
+              float f[8] = {lo.x + bb[0], lo.y + bb[1], lo.z + bb[2], lo.w + bb[3],
+                            hi.x + bb[4], hi.y + bb[5], hi.z + bb[6], hi.w + bb[7]};
+              if (relu) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[q] = fmaxf(f[q], 0.f);
+              }
               uint4 pk;
               __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
-              dst[j] = pk;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = i * 8 + (lane >> 2), ch = lane & 3;
-              const uint4 val = *reinterpret_cast<const uint4*>(stage_gen + r * PITCH16 + ch * 16);
-              const int row = row_base + r, col = col0 + ch * 8;
+              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+              const int row = row_base + r;
               if (row < M && col < n_store)
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(C) + static_cast<int64_t>(row) * ldc + col) =
-                    val;
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(C) + static_cast<int64_t>(row) * ldc + col) = pk;
             }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) mbar_arrive(tempty_bar(grp));
     }
   }
 
@@ -209,12 +243,12 @@ static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, c
   static bool configured = false;
   auto kern = gemm_bf16_tcgen05_kernel<BN, OutT>;
   if (!configured) {
-    CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
+    CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BN>()));
     configured = true;
   }
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + BN - 1) / BN;
   const int grid = std::min(m_tiles * n_tiles, ctx->sm_count);
-  kern<<<grid, NUM_THREADS, cfg::SMEM_BYTES, stream>>>(ta, tb, bias, reinterpret_cast<OutT*>(C), ldc, M, N, n_store, K,
+  kern<<<grid, GEMM_THREADS, gemm_smem_bytes<BN>(), stream>>>(ta, tb, bias, reinterpret_cast<OutT*>(C), ldc, M, N, n_store, K,
                                                        act == CARE_ACT_RELU ? 1 : 0, early_exit_of(ctx));
   CARE_LAUNCH_CHECK(ctx);
   return 0;
@@ -231,6 +265,68 @@ int gemm_bf16(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t 
   const int n_pad = (N + 7) & ~7;
   CARE_CHECK_ARG(n_pad <= ldc || N % 8 == 0, "care_gemm(bf16): ldc %lld too small for N=%d", (long long)ldc, N);
   const int n_store = n_pad <= ldc ? n_pad : N;
+  int use_2sm = ctx->gemm_2sm;
+  if (use_2sm == 2) {
+    // per-shape choice between the CTA-pair kernel and single-CTA tiles, measured once
+    const uint64_t key = ((uint64_t)(uint32_t)M << 40) ^ ((uint64_t)(uint32_t)N << 20) ^ ((uint64_t)(uint32_t)K << 1) ^
+                         (uint64_t)(out_dtype & 1);
+    int choice = -1;
+    {
+      std::lock_guard<std::mutex> g(ctx->mu);
+      auto it = ctx->gemm_choice.find(key);
+      if (it != ctx->gemm_choice.end()) choice = it->second;
+    }
+    if (choice < 0) {
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(stream, &cap);
+      if (cap != cudaStreamCaptureStatusNone) {
+        choice = 0;   // cannot time inside a capture; not cached
+      } else {
+        float best_ms[2] = {0.f, 0.f};
+        bool ok2 = true;
+        cudaEvent_t e0, e1;
+        CARE_CUDA(cudaEventCreate(&e0));
+        CARE_CUDA(cudaEventCreate(&e1));
+        const int saved = ctx->gemm_2sm;
+        for (int v = 0; v < 2 && ok2; ++v) {
+          ctx->gemm_2sm = v;
+          for (int rep = 0; rep < 4; ++rep) {   // rep 0 = warm-up
+            if (rep == 1) cudaEventRecord(e0, stream);
+            int rc = 0;
+            if (v == 1) {
+              rc = tc2::gemm_bf16_2sm(ctx, A, lda, W, ldw, bias, C, ldc, out_dtype, M, N, n_store, K, act, stream);
+              if (rc == 1) ok2 = false;
+            } else {
+              rc = gemm_bf16(ctx, A, lda, W, ldw, bias, C, ldc, out_dtype, M, N, K, act, stream);
+            }
+            if (rc != 0 && rc != 1) {
+              ctx->gemm_2sm = saved;
+              cudaEventDestroy(e0);
+              cudaEventDestroy(e1);
+              return rc;
+            }
+            if (!ok2) break;
+          }
+          if (!ok2) break;
+          cudaEventRecord(e1, stream);
+          cudaEventSynchronize(e1);
+          cudaEventElapsedTime(&best_ms[v], e0, e1);
+        }
+        ctx->gemm_2sm = saved;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        choice = (ok2 && best_ms[1] < best_ms[0]) ? 1 : 0;
+        std::lock_guard<std::mutex> g(ctx->mu);
+        ctx->gemm_choice[key] = choice;
+        return 0;   // C already holds the result (both variants compute the same GEMM)
+      }
+    }
+    use_2sm = choice;
+  }
+  if (use_2sm == 1) {
+    const int rc2 = tc2::gemm_bf16_2sm(ctx, A, lda, W, ldw, bias, C, ldc, out_dtype, M, N, n_store, K, act, stream);
+    if (rc2 != 1) return rc2;
+  }
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   auto tiles = [&](int bn) { return m_tiles * ((N + bn - 1) / bn); };
   // tile width: fewest (waves x per-tile cost); per-tile cost ~ BN + a fixed part (A tile load, epilogue

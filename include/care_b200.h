@@ -58,7 +58,10 @@ int64_t care_ctx_launch_count(const care_ctx* ctx);
  * (replaces the host-side `if not active: break`, Translator.py:77).  Pass NULL to disable. */
 int care_ctx_set_early_exit(care_ctx* ctx, const int32_t* counter, int target);
 /* implementation switches for A/B tests.  "attn_impl": 1 = TMA + tensor-core attention for bf16
- * (default), 0 = the SIMT attention kernel for every dtype. */
+ * (default), 0 = the SIMT attention kernel for every dtype.  "gemm_2sm": 0 = single-CTA GEMM tiles
+ * only, 1 = CTA-pair (tcgen05 cta_group::2) tiles whenever the shape allows, 2 (default) = choose per
+ * (M, N, K, out dtype) by timing both variants ONCE, on the first care_gemm call with that shape - the
+ * only place the library waits on the stream (never while the stream is being captured). */
 int care_ctx_set_option(care_ctx* ctx, const char* name, int value);
 
 /* C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) — every nn.Linear on the path:

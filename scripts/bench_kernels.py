@@ -69,6 +69,9 @@ def main():
                     n_pos, impl, ms, nbytes / ms / 1e6, 100 * nbytes / ms / 1e6 / PEAK))
         del cache
     if "gemm" in what:
+      for two in (0, 1, 2):
+        lib.care_ctx_set_option(h, b"gemm_2sm", two)
+        print("gemm_2sm =", two)
         for (M, N, Kd, name, odt) in [(R, 3 * d, d, "qkv", torch.bfloat16), (R, d, d, "out-proj", torch.float32),
                                       (R, 4 * d, d, "ffn1", torch.bfloat16), (R, d, 4 * d, "ffn2", torch.float32),
                                       (R, V, d, "vocab", torch.float32), (B * Lm, 2 * d, d, "cross-kv", torch.bfloat16)]:
@@ -79,7 +82,9 @@ def main():
             ms = timed(lambda: _lib.check(lib.care_gemm(
                 h, BF16, A.data_ptr(), Kd, W.data_ptr(), Kd, None, C.data_ptr(), ldc,
                 F32 if odt == torch.float32 else BF16, M, N, Kd, 0, st), "g"))
-            print("gemm %-9s M=%d N=%d K=%d: %.3f ms  %.0f TFLOP/s" % (name, M, N, Kd, ms, 2.0 * M * N * Kd / ms / 1e9))
+            err = (C[:512, :N].float() - A[:512].float() @ W.float().t()).abs().max().item()
+            print("gemm %-9s M=%d N=%d K=%d: %.3f ms  %.0f TFLOP/s  (max err first 512 rows %.3g)" % (
+                name, M, N, Kd, ms, 2.0 * M * N * Kd / ms / 1e9, err))
             del A, W, C
     if "beam" in what:
         from care_b200._lib import BeamState
