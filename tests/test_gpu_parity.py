@@ -327,3 +327,44 @@ def test_cuda_graph_replay_matches_eager(precision):
     assert third[0] == [ref[0][i] for i in perm]
     if precision == "fp32":
         assert first[0] == rec["hyps"]
+
+
+@pytest.mark.parametrize("over", [
+    dict(beam_size=8, topk=4, max_len=14, vocab_size=1203),
+    dict(beam_size=7, topk=1, max_len=30, vocab_size=9468, beam_alpha=0.5),
+    dict(beam_size=2, topk=2, max_len=6, vocab_size=517),
+])
+def test_unusual_shapes_fp32_vs_oracle(over):
+    """Beam widths up to the kernels' limit (8), n_best > 1, short max_len, odd vocabulary sizes: the fp32
+    CUDA path against the oracle (no golden for these; the oracle itself is pinned to the reference)."""
+    import care_b200
+    from oracle.shapes import CONFIGS, make_feats, make_opt
+    from oracle.weights import SHARP, make_state_dict
+    opt = make_opt(**{**CONFIGS["cfg2"], **over})
+    sd = make_state_dict(opt, seed=31, perturb=True, sharpen=SHARP)
+    feats = make_feats(opt, 7, seed=13)
+    model = _gpu_model(opt, sd, "fp32")
+    tr = care_b200.get_translator(opt)
+    hyps, scores = tr.translate_batch([model], {"feats": [f.cuda() for f in feats]})
+    o_h, o_s, margins, _ = _oracle_margins(sd, opt, feats)
+    exact = 0
+    for v in range(len(hyps)):
+        if hyps[v] == o_h[v]:
+            exact += 1
+            for a, b in zip(scores[v], o_s[v]):
+                assert abs(a - b) < 1e-4 * max(1.0, abs(b)), (v, a, b)
+        else:
+            assert margins[v] < 1e-4, "video %d differs although the oracle margin is %g" % (v, margins[v])
+    assert exact >= 5, "only %d/7 sequences identical" % exact
+
+
+def test_single_video_and_many_videos_agree():
+    """A video decodes to the same caption alone (batch 1, graph path) and inside a larger batch."""
+    import care_b200
+    rec = load_golden("cfg2_sharp")
+    opt, sd, feats = rebuild_case(rec)
+    model = _gpu_model(opt, sd, "fp32")
+    tr = care_b200.get_translator(opt)
+    for v in (0, 5, 11):
+        h, s = tr.translate_batch([model], {"feats": [f[v:v + 1].cuda() for f in feats]})
+        assert h[0] == rec["hyps"][v]
