@@ -96,11 +96,32 @@ int care_ctx_create(care_ctx** out, int device) {
     return -4;
   }
   c->encode = (care_tmap_encode_fn)fn;
+  if (cudaMalloc(&c->self_attn_rows, sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemset(c->self_attn_rows, 0, sizeof(unsigned long long)) != cudaSuccess) {
+    care::set_error("care_ctx_create: cannot allocate the ctx counters");
+    delete c;
+    return -5;
+  }
   *out = c;
   return 0;
 }
 
-void care_ctx_destroy(care_ctx* ctx) { delete ctx; }
+void care_ctx_destroy(care_ctx* ctx) {
+  if (ctx && ctx->self_attn_rows) cudaFree(ctx->self_attn_rows);
+  delete ctx;
+}
+
+int care_ctx_counter(care_ctx* ctx, const char* name, int64_t* value) {
+  CARE_CHECK_ARG(ctx && name && value, "care_ctx_counter: bad args");
+  if (strcmp(name, "self_attn_rows") == 0) {
+    unsigned long long v = 0;
+    CARE_CUDA(cudaMemcpy(&v, ctx->self_attn_rows, sizeof(v), cudaMemcpyDeviceToHost));   // synchronises
+    *value = (int64_t)v;
+    return 0;
+  }
+  care::set_error("care_ctx_counter: unknown counter '%s'", name);
+  return -1;
+}
 
 int care_ctx_sm_count(const care_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
@@ -117,6 +138,10 @@ int care_ctx_set_option(care_ctx* ctx, const char* name, int value) {
   CARE_CHECK_ARG(ctx && name, "care_ctx_set_option: bad args");
   if (strcmp(name, "attn_impl") == 0) {
     ctx->attn_impl = value;
+    return 0;
+  }
+  if (strcmp(name, "self_compact") == 0) {
+    ctx->self_compact = value;
     return 0;
   }
   if (strcmp(name, "gemm_2sm") == 0) {

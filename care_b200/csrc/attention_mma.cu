@@ -101,11 +101,159 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // physical byte offset of 16-byte chunk `c16` of row `r` inside a SWIZZLE_128B tile (1024-B aligned)
 __device__ __forceinline__ uint32_t sw128(int r, int c16) { return (uint32_t)(r * 128 + ((c16 ^ (r & 7)) << 4)); }
 
+constexpr int COMB_LD = 72;   // floats per row of the merge buffer (64 + pad: <= 2-way bank conflicts)
+
+// S = Q K^T, softmax and O = P V over the staged tiles (shared by the TMA kernel and the compacting
+// self-attention kernel).  bar_k / bar_v: mbarriers to wait on, or 0 when the tiles are already in place.
+template <int KKW, bool SELF, int WARPS>
+__device__ __forceinline__ void attend(const Params& p, int v, int h, int warp, int lane, uint32_t (&qa)[4][2],
+                                       uint32_t k_s, uint32_t v_s, int n_keys, int rows_pad, uint32_t bar_k,
+                                       uint32_t bar_v, const uint32_t* mw, float* stat, float* comb) {
+  const int K = p.K;
+  const int g = lane >> 2, tig = lane & 3;
+  if (g >= K) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) qa[ks][0] = qa[ks][1] = 0u;
+  }
+  // this warp's 16-key steps
+  const int n_kk = rows_pad >> 4;
+  const int kk0 = (warp * n_kk) / WARPS, kk1 = ((warp + 1) * n_kk) / WARPS;
+  const int m = lane >> 3, rr = lane & 7;
+
+  // ---- S = Q K^T over the warp's keys ----------------------------------------------------------------
+  float s[2 * KKW][2];
+  if (bar_k) mbar_wait(bar_k, 0);
+#pragma unroll
+  for (int i = 0; i < KKW; ++i) {
+    const int kk = kk0 + i;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      if (kk < kk1) {
+        const int r = kk * 16 + half * 8 + rr;
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+          uint32_t b[4];
+          ldsm_x4(b, k_s + sw128(r, 4 * kp + m));
+          mma_bf16(c, qa[2 * kp][0], qa[2 * kp][1], b[0], b[1]);
+          mma_bf16(c, qa[2 * kp + 1][0], qa[2 * kp + 1][1], b[2], b[3]);
+        }
+      }
+      s[2 * i + half][0] = c[0];
+      s[2 * i + half][1] = c[1];
+    }
+  }
+  // ---- scale, mask / bias, local softmax (fp32) ---------------------------------------------------
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < KKW; ++i) {
+    const int kk = kk0 + i;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = kk * 16 + half * 8 + 2 * tig + e;
+        float x = s[2 * i + half][e] * 0.125f;   // / sqrt(64), Attention.py:84
+        if (SELF) {
+          if (!((mw[g * 8 + ((j >> 5) & 7)] >> (j & 31)) & 1u)) x = -1e9f;
+        } else if (p.bias != nullptr && j < n_keys) {
+          x += __ldg(p.bias + (int64_t)h * p.Lm + j);
+        }
+        if (kk >= kk1 || j >= n_keys) x = -INFINITY;
+        s[2 * i + half][e] = x;
+        mx = fmaxf(mx, x);
+      }
+    }
+  }
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  const float mref = mx == -INFINITY ? 0.f : mx;   // a warp without keys contributes nothing
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2 * KKW; ++i) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float pe = __expf(s[i][e] - mref);
+      s[i][e] = pe;
+      sum += pe;
+    }
+  }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+
+  // ---- partial O = P V -----------------------------------------------------------------------------
+  float o[8][4];
+#pragma unroll
+  for (int dn = 0; dn < 8; ++dn)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[dn][e] = 0.f;
+  if (bar_v) mbar_wait(bar_v, 0);
+#pragma unroll
+  for (int i = 0; i < KKW; ++i) {
+    const int kk = kk0 + i;
+    if (kk < kk1) {
+      const float p0 = s[2 * i][0], p1 = s[2 * i][1], p2 = s[2 * i + 1][0], p3 = s[2 * i + 1][1];
+      const uint32_t a0h = pack_bf16(p0, p1), a2h = pack_bf16(p2, p3);
+      const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&a0h);
+      const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&a2h);
+      const uint32_t a0l = pack_bf16(p0 - __low2float(h0), p1 - __high2float(h0));
+      const uint32_t a2l = pack_bf16(p2 - __low2float(h2), p3 - __high2float(h2));
+      const int r = kk * 16 + 8 * (m & 1) + rr;
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t b[4];
+        ldsm_x4_trans(b, v_s + sw128(r, 2 * dp + (m >> 1)));
+        mma_bf16(o[2 * dp], a0h, a2h, b[0], b[1]);
+        mma_bf16(o[2 * dp], a0l, a2l, b[0], b[1]);
+        mma_bf16(o[2 * dp + 1], a0h, a2h, b[2], b[3]);
+        mma_bf16(o[2 * dp + 1], a0l, a2l, b[2], b[3]);
+      }
+    }
+  }
+  if (WARPS == 1) {   // short key sets: one warp saw every key, no merge
+    if (g < K) {
+      const float inv = 1.0f / sum;
+      __nv_bfloat16* orow = p.out + (int64_t)(v * K + g) * p.d + h * DH + 2 * tig;
+#pragma unroll
+      for (int dn = 0; dn < 8; ++dn)
+        *reinterpret_cast<__nv_bfloat162*>(orow + 8 * dn) = __floats2bfloat162_rn(o[dn][0] * inv, o[dn][1] * inv);
+    }
+    return;
+  }
+  // ---- merge the partials of the warps ---------------------------------------------------------------
+  {
+    float* crow = comb + ((size_t)warp * 8 + g) * COMB_LD + 2 * tig;
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn) *reinterpret_cast<float2*>(crow + 8 * dn) = make_float2(o[dn][0], o[dn][1]);
+    if (tig == 0) {
+      stat[(warp * 8 + g) * 2 + 0] = mx;
+      stat[(warp * 8 + g) * 2 + 1] = sum;
+    }
+  }
+  __syncthreads();
+  {
+    const int col = threadIdx.x & 63;
+    for (int b = threadIdx.x >> 6; b < K; b += WARPS / 2) {
+      float M = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) M = fmaxf(M, stat[(w * 8 + b) * 2]);
+      float num = 0.f, den = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) {
+        const float mwv = stat[(w * 8 + b) * 2];
+        const float sc = mwv == -INFINITY ? 0.f : __expf(mwv - M);
+        den += stat[(w * 8 + b) * 2 + 1] * sc;
+        num += comb[((size_t)w * 8 + b) * COMB_LD + col] * sc;
+      }
+      p.out[(int64_t)(v * K + b) * p.d + h * DH + col] = __float2bfloat16_rn(num / den);
+    }
+  }
+}
+
 // One CTA of 4 warps per (video, head).  The keys are split over the warps in steps of 16 (flash-decoding
 // inside the CTA): each warp computes S, a local softmax and a partial O for its key range, the partials
 // are merged through shared memory.  KKW = 16-key steps per warp the registers are sized for
 // (n_keys <= 64 * KKW).
-constexpr int COMB_LD = 72;   // floats per row of the merge buffer (64 + pad: <= 2-way bank conflicts)
 
 template <int KKW, bool SELF, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
@@ -173,144 +321,7 @@ attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     }
   }
   __syncthreads();   // mbarrier init + mask words visible to every warp
-  if (g >= K) {
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) qa[ks][0] = qa[ks][1] = 0u;
-  }
-
-  // this warp's 16-key steps
-  const int n_kk = p.rows_pad >> 4;
-  const int kk0 = (warp * n_kk) / WARPS, kk1 = ((warp + 1) * n_kk) / WARPS;
-  const int m = lane >> 3, rr = lane & 7;
-
-  // ---- S = Q K^T over the warp's keys ----------------------------------------------------------------
-  float s[2 * KKW][2];
-  mbar_wait(bar_k, 0);
-#pragma unroll
-  for (int i = 0; i < KKW; ++i) {
-    const int kk = kk0 + i;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float c[4] = {0.f, 0.f, 0.f, 0.f};
-      if (kk < kk1) {
-        const int r = kk * 16 + half * 8 + rr;
-#pragma unroll
-        for (int kp = 0; kp < 2; ++kp) {
-          uint32_t b[4];
-          ldsm_x4(b, k_s + sw128(r, 4 * kp + m));
-          mma_bf16(c, qa[2 * kp][0], qa[2 * kp][1], b[0], b[1]);
-          mma_bf16(c, qa[2 * kp + 1][0], qa[2 * kp + 1][1], b[2], b[3]);
-        }
-      }
-      s[2 * i + half][0] = c[0];
-      s[2 * i + half][1] = c[1];
-    }
-  }
-  // ---- scale, mask / bias, local softmax (fp32) ---------------------------------------------------
-  float mx = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < KKW; ++i) {
-    const int kk = kk0 + i;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int j = kk * 16 + half * 8 + 2 * tig + e;
-        float x = s[2 * i + half][e] * 0.125f;   // / sqrt(64), Attention.py:84
-        if (SELF) {
-          if (!((mw[g * 8 + ((j >> 5) & 7)] >> (j & 31)) & 1u)) x = -1e9f;
-        } else if (p.bias != nullptr && j < n_keys) {
-          x += __ldg(p.bias + (int64_t)h * p.Lm + j);
-        }
-        if (kk >= kk1 || j >= n_keys) x = -INFINITY;
-        s[2 * i + half][e] = x;
-        mx = fmaxf(mx, x);
-      }
-    }
-  }
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-  const float mref = mx == -INFINITY ? 0.f : mx;   // a warp without keys contributes nothing
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < 2 * KKW; ++i) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const float pe = __expf(s[i][e] - mref);
-      s[i][e] = pe;
-      sum += pe;
-    }
-  }
-  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-
-  // ---- partial O = P V -----------------------------------------------------------------------------
-  float o[8][4];
-#pragma unroll
-  for (int dn = 0; dn < 8; ++dn)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) o[dn][e] = 0.f;
-  mbar_wait(bar_v, 0);
-#pragma unroll
-  for (int i = 0; i < KKW; ++i) {
-    const int kk = kk0 + i;
-    if (kk < kk1) {
-      const float p0 = s[2 * i][0], p1 = s[2 * i][1], p2 = s[2 * i + 1][0], p3 = s[2 * i + 1][1];
-      const uint32_t a0h = pack_bf16(p0, p1), a2h = pack_bf16(p2, p3);
-      const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&a0h);
-      const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&a2h);
-      const uint32_t a0l = pack_bf16(p0 - __low2float(h0), p1 - __high2float(h0));
-      const uint32_t a2l = pack_bf16(p2 - __low2float(h2), p3 - __high2float(h2));
-      const int r = kk * 16 + 8 * (m & 1) + rr;
-#pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {
-        uint32_t b[4];
-        ldsm_x4_trans(b, v_s + sw128(r, 2 * dp + (m >> 1)));
-        mma_bf16(o[2 * dp], a0h, a2h, b[0], b[1]);
-        mma_bf16(o[2 * dp], a0l, a2l, b[0], b[1]);
-        mma_bf16(o[2 * dp + 1], a0h, a2h, b[2], b[3]);
-        mma_bf16(o[2 * dp + 1], a0l, a2l, b[2], b[3]);
-      }
-    }
-  }
-  if (WARPS == 1) {   // short key sets: one warp saw every key, no merge
-    if (g < K) {
-      const float inv = 1.0f / sum;
-      __nv_bfloat16* orow = p.out + (int64_t)(v * K + g) * p.d + h * DH + 2 * tig;
-#pragma unroll
-      for (int dn = 0; dn < 8; ++dn)
-        *reinterpret_cast<__nv_bfloat162*>(orow + 8 * dn) = __floats2bfloat162_rn(o[dn][0] * inv, o[dn][1] * inv);
-    }
-    return;
-  }
-  // ---- merge the partials of the warps ---------------------------------------------------------------
-  {
-    float* crow = comb + ((size_t)warp * 8 + g) * COMB_LD + 2 * tig;
-#pragma unroll
-    for (int dn = 0; dn < 8; ++dn) *reinterpret_cast<float2*>(crow + 8 * dn) = make_float2(o[dn][0], o[dn][1]);
-    if (tig == 0) {
-      stat[(warp * 8 + g) * 2 + 0] = mx;
-      stat[(warp * 8 + g) * 2 + 1] = sum;
-    }
-  }
-  __syncthreads();
-  {
-    const int col = threadIdx.x & 63;
-    for (int b = threadIdx.x >> 6; b < K; b += WARPS / 2) {
-      float M = -INFINITY;
-#pragma unroll
-      for (int w = 0; w < WARPS; ++w) M = fmaxf(M, stat[(w * 8 + b) * 2]);
-      float num = 0.f, den = 0.f;
-#pragma unroll
-      for (int w = 0; w < WARPS; ++w) {
-        const float mwv = stat[(w * 8 + b) * 2];
-        const float sc = mwv == -INFINITY ? 0.f : __expf(mwv - M);
-        den += stat[(w * 8 + b) * 2 + 1] * sc;
-        num += comb[((size_t)w * 8 + b) * COMB_LD + col] * sc;
-      }
-      p.out[(int64_t)(v * K + b) * p.d + h * DH + col] = __float2bfloat16_rn(num / den);
-    }
-  }
+  attend<KKW, SELF, WARPS>(p, v, h, warp, lane, qa, k_s, v_s, n_keys, p.rows_pad, bar_k, bar_v, mw, stat, comb);
 }
 
 template <int KKW, bool SELF, int WARPS>
@@ -323,6 +334,134 @@ static int launch(care_ctx* ctx, const CUtensorMap& tmap, const Params& p, cudaS
     configured = smem;
   }
   kern<<<p.n_items, WARPS * 32, smem, stream>>>(tmap, p);
+  CARE_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Self-attention with slot compaction.  The KV cache keeps K slots per position, but the K beams of a
+// video share most of their ancestry: on average only ~2.5 of 5 slots per position are on some beam's
+// prefix with the benchmark weights, ~1.2 with peaked distributions (scripts/ancestry_stats.py).  This
+// kernel derives the live (position, slot) set from the ancestry table, gathers ONLY those K/V rows
+// into the swizzled shared-memory tiles with 16-byte cp.async copies, and runs the same MMA pipeline on
+// the compacted key list - HBM traffic and MMA work both shrink by K / (live slots per position).
+// ---------------------------------------------------------------------------------------------
+constexpr int MAX_POS = 64;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <int KKW>
+__global__ void __launch_bounds__(128)
+attn_self_compact_kernel(const Params p, const __nv_bfloat16* __restrict__ cache, int64_t R,
+                         unsigned long long* __restrict__ row_counter) {
+  constexpr int WARPS = 4;
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int v = blockIdx.x / p.H, h = blockIdx.x - v * p.H;
+  if (p.done != nullptr && p.done[v]) return;
+  const int K = p.K, n_pos = p.n_pos;
+
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t tile_bytes = (uint32_t)p.rows_pad * 128u;     // sized for all n_pos * K rows
+  const uint32_t k_s = base, v_s = base + tile_bytes;
+  const uint32_t aux = base + 2u * tile_bytes;
+  uint8_t* aux_gen = smem_raw + (aux - raw);
+  uint32_t* mw = reinterpret_cast<uint32_t*>(aux_gen + 16);
+  float* stat = reinterpret_cast<float*>(aux_gen + 16 + 256);
+  float* comb = reinterpret_cast<float*>(aux_gen + 16 + 256 + 256);
+  uint8_t* sa = aux_gen + 16 + 256 + 256 + WARPS * 8 * COMB_LD * 4;          // [8][MAX_POS] slot of (beam, pos)
+  uint8_t* live = sa + 8 * MAX_POS;                                           // [MAX_POS] slot bitmask per position
+  uint16_t* off = reinterpret_cast<uint16_t*>(live + MAX_POS);                // [MAX_POS + 1] first row of a position
+  uint16_t* rowsrc = off + MAX_POS + 2;                                       // [rows] cache row (pos * K + slot)
+  __shared__ int n_live_s;
+
+  // Q fragments first: their latency overlaps the ancestry bookkeeping
+  const int g = lane >> 2, tig = lane & 3;
+  uint32_t qa[4][2];
+  {
+    const __nv_bfloat16* qrow = p.q + (int64_t)(v * K + (g < K ? g : 0)) * p.q_ld + h * DH;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      qa[ks][0] = *reinterpret_cast<const uint32_t*>(qrow + 16 * ks + 2 * tig);
+      qa[ks][1] = *reinterpret_cast<const uint32_t*>(qrow + 16 * ks + 2 * tig + 8);
+    }
+  }
+  for (int i = threadIdx.x; i < 64; i += 128) mw[i] = 0u;
+  for (int i = threadIdx.x; i < K * n_pos; i += 128) {
+    const int b = i / n_pos, pp = i - b * n_pos;
+    sa[b * MAX_POS + pp] = (pp == n_pos - 1) ? (uint8_t)b : p.anc[((int64_t)v * K + b) * p.anc_stride + pp];
+  }
+  __syncthreads();
+  if (threadIdx.x < n_pos) {
+    uint32_t bits = 0u;
+    for (int b = 0; b < K; ++b) bits |= 1u << sa[b * MAX_POS + threadIdx.x];
+    live[threadIdx.x] = (uint8_t)bits;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int pp = 0; pp < n_pos; ++pp) {
+      off[pp] = (uint16_t)acc;
+      acc += __popc((uint32_t)live[pp]);
+    }
+    off[n_pos] = (uint16_t)acc;
+    n_live_s = acc;
+    if (h == 0 && row_counter != nullptr) atomicAdd(row_counter, (unsigned long long)acc);
+  }
+  __syncthreads();
+  const int n_live = n_live_s;
+  const int rows_pad = (n_live + 15) & ~15;
+  // row table + per-beam key masks in the compacted index space
+  for (int i = threadIdx.x; i < K * n_pos; i += 128) {
+    const int s = i / n_pos, pp = i - s * n_pos;        // here: candidate slot s of position pp
+    const uint32_t bits = live[pp];
+    if ((bits >> s) & 1u) rowsrc[off[pp] + __popc(bits & ((1u << s) - 1u))] = (uint16_t)(pp * K + s);
+    // beam b == s of this loop index: its key at position pp
+    const int b = s;
+    const int slot = sa[b * MAX_POS + pp];
+    const int tok = p.tok_hist[(int64_t)v * p.tok_stride + pp * K + slot];
+    if (tok != CARE_PAD) {
+      const int j = off[pp] + __popc(bits & ((1u << slot) - 1u));
+      atomicOr(&mw[b * 8 + (j >> 5)], 1u << (j & 31));
+    }
+  }
+  __syncthreads();
+  // gather: 16 chunks of 16 B per live row (8 of K, 8 of V)
+  {
+    const __nv_bfloat16* kbase = cache + (int64_t)v * K * (3LL * p.d) + p.k_col + h * DH;
+    const __nv_bfloat16* vbase = cache + (int64_t)v * K * (3LL * p.d) + p.v_col + h * DH;
+    const int n_chunks = n_live * 16;
+    for (int c = threadIdx.x; c < n_chunks; c += 128) {
+      const int j = c >> 4, isv = (c >> 3) & 1, c16 = c & 7;
+      const int src = rowsrc[j];
+      const int pp = src / K, sl = src - pp * K;
+      const int64_t roff = ((int64_t)pp * R + sl) * (3LL * p.d) + c16 * 8;
+      cp_async16((isv ? v_s : k_s) + sw128(j, c16), (isv ? vbase : kbase) + roff);
+    }
+    // rows [n_live, rows_pad) of V are multiplied by P == 0: they must hold finite values
+    uint8_t* v_gen = smem_raw + (v_s - raw);
+    for (int i = threadIdx.x; i < (rows_pad - n_live) * 8; i += 128)
+      *reinterpret_cast<uint4*>(v_gen + (size_t)n_live * 128 + (size_t)i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
+  attend<KKW, true, WARPS>(p, v, h, warp, lane, qa, k_s, v_s, n_live, rows_pad, 0u, 0u, mw, stat, comb);
+}
+
+template <int KKW>
+static int launch_compact(care_ctx* ctx, const Params& p, const void* cache, int64_t R, cudaStream_t stream) {
+  auto kern = attn_self_compact_kernel<KKW>;
+  const size_t smem = (size_t)2 * p.rows_pad * 128 + 1024 + 16 + 256 + 256 + (size_t)4 * 8 * COMB_LD * 4 +
+                      8 * MAX_POS + MAX_POS + (MAX_POS + 2) * 2 + (size_t)p.rows_pad * 2 + 64;
+  static size_t configured = 0;
+  if (smem > configured) {
+    CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  kern<<<p.n_items, 128, smem, stream>>>(p, static_cast<const __nv_bfloat16*>(cache), R, ctx->self_attn_rows);
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -383,6 +522,11 @@ int self_step(care_ctx* ctx, const void* cache, int n_pos, int B, int K, int H, 
   p.done = done;
   p.out = static_cast<__nv_bfloat16*>(ctx_out);
   p.n_items = B * H;
+  if (ctx->self_compact && n_pos >= 8 && n_pos <= MAX_POS) {
+    // long enough prefixes: gather only the cache slots some beam still references
+    if (n_keys <= 128) return launch_compact<2>(ctx, p, cache, R, stream);
+    return launch_compact<3>(ctx, p, cache, R, stream);
+  }
   if (n_keys <= 16) return launch<1, true, 1>(ctx, tmap, p, stream);
   if (n_keys <= 64) return launch<4, true, 1>(ctx, tmap, p, stream);   // short prefixes: one warp, no merge
   if (n_keys <= 128) return launch<2, true, 4>(ctx, tmap, p, stream);

@@ -242,10 +242,14 @@ def test_cross_attention(env, dt, T, K, H):
     assert (out.float() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("compact", [0, 1])
 @pytest.mark.parametrize("dt,T", [(F32, torch.float32), (BF16, torch.bfloat16)])
 @pytest.mark.parametrize("K,H,n_pos", [(5, 8, 1), (5, 8, 13), (5, 16, 29), (1, 8, 9), (3, 12, 20)])
-def test_self_attention(env, dt, T, K, H, n_pos):
+def test_self_attention(env, dt, T, K, H, n_pos, compact):
     lib, h, L = env
+    if compact and dt == F32:
+        pytest.skip("slot compaction exists for the bf16 kernel only")
+    lib.care_ctx_set_option(h, b"self_compact", compact)
     B, d, Tm = 4, H * 64, 29
     R = B * K
     g = torch.Generator().manual_seed(n_pos * 10 + K)
@@ -282,6 +286,7 @@ def test_self_attention(env, dt, T, K, H, n_pos):
     tol = 2e-5 if dt == F32 else 2e-2
     assert (got[:live] - ref[:live]).abs().max().item() < tol * max(1.0, ref.abs().max().item())
     assert (got[live:] == 123.0).all()  # finished video untouched
+    lib.care_ctx_set_option(h, b"self_compact", 0)
 
 
 def _beam_buffers(B, K, Tm, V, need):
