@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=16, help="videos per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--self-compact", action="store_true", help="opt-in slot-compacting self-attention kernel")
     ap.add_argument("--no-latency", action="store_true", help="skip the small-batch latency section (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-fed e2e section (profiling runs)")
     return ap.parse_args()
@@ -233,7 +234,7 @@ def run_care_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     opt = make_opt(**CONFIGS[args.config])
     sd = make_state_dict(opt, seed=0)
-    model = care_b200.get_framework(dict(opt, care_precision=args.precision))
+    model = care_b200.get_framework(dict(opt, care_precision=args.precision, care_self_compact=args.self_compact))
     model.load_state_dict(sd)
     model = model.eval().to(dev)
     del sd

@@ -108,6 +108,7 @@ int care_ctx_create(care_ctx** out, int device) {
 
 void care_ctx_destroy(care_ctx* ctx) {
   if (ctx && ctx->self_attn_rows) cudaFree(ctx->self_attn_rows);
+  if (ctx && ctx->compact_info) cudaFree(ctx->compact_info);
   delete ctx;
 }
 
@@ -142,6 +143,17 @@ int care_ctx_set_option(care_ctx* ctx, const char* name, int value) {
   }
   if (strcmp(name, "self_compact") == 0) {
     ctx->self_compact = value;
+    if (value && ctx->compact_info == nullptr) {   // scratch for the per-video records (16384 videos x 640 B)
+      ctx->compact_info_videos = 16384;
+      if (cudaMalloc(&ctx->compact_info, (size_t)ctx->compact_info_videos * 160 * sizeof(uint32_t)) != cudaSuccess) {
+        ctx->compact_info = nullptr;
+        ctx->compact_info_videos = 0;
+      }
+    }
+    return 0;
+  }
+  if (strcmp(name, "gemm_smallm") == 0) {
+    ctx->gemm_smallm = value;
     return 0;
   }
   if (strcmp(name, "gemm_2sm") == 0) {

@@ -352,10 +352,68 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
+// Per-video record consumed by attn_self_compact_kernel, built once per step instead of once per head:
+//   word 0: n_live;  words 1..64: key masks [8 beams][8 words] in the compacted index space;
+//   words 65..: uint16 rowsrc[row] = position * K + slot of the cache row gathered into tile row `row`.
+constexpr int INFO_WORDS = 160;   // 1 + 64 + 80 (160 uint16) padded: 640 B per video
+
+__global__ void __launch_bounds__(128)
+compact_info_kernel(const uint8_t* __restrict__ anc, int anc_stride, const int32_t* __restrict__ tok_hist,
+                    int tok_stride, const int32_t* __restrict__ done, int B, int K, int n_pos,
+                    uint32_t* __restrict__ info) {
+  __shared__ uint32_t rec_all[4][INFO_WORDS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int v = blockIdx.x * 4 + warp;
+  if (v >= B) return;
+  if (done != nullptr && done[v]) return;
+  uint32_t* rec = rec_all[warp];
+  for (int i = lane; i < INFO_WORDS; i += 32) rec[i] = 0u;
+  __syncwarp();
+  uint16_t* rowsrc = reinterpret_cast<uint16_t*>(rec + 65);
+  int carry = 0;
+  for (int p0 = 0; p0 < n_pos; p0 += 32) {
+    const int pp = p0 + lane;
+    uint32_t bits = 0u;
+    uint32_t slots = 0u;   // 4 bits per beam
+    if (pp < n_pos) {
+      for (int b = 0; b < K; ++b) {
+        const uint32_t slot = (pp == n_pos - 1) ? (uint32_t)b : (uint32_t)anc[((int64_t)v * K + b) * anc_stride + pp];
+        bits |= 1u << slot;
+        slots |= slot << (4 * b);
+      }
+    }
+    const int cnt = __popc(bits);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    const int off = carry + incl - cnt;
+    if (pp < n_pos) {
+      for (int sl = 0; sl < K; ++sl)
+        if ((bits >> sl) & 1u) rowsrc[off + __popc(bits & ((1u << sl) - 1u))] = (uint16_t)(pp * K + sl);
+      for (int b = 0; b < K; ++b) {
+        const uint32_t slot = (slots >> (4 * b)) & 15u;
+        const int tok = tok_hist[(int64_t)v * tok_stride + pp * K + slot];
+        if (tok != CARE_PAD) {
+          const int j = off + __popc(bits & ((1u << slot) - 1u));
+          atomicOr(&rec[1 + b * 8 + (j >> 5)], 1u << (j & 31));
+        }
+      }
+    }
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  __syncwarp();
+  if (lane == 0) rec[0] = (uint32_t)carry;
+  __syncwarp();
+  for (int i = lane; i < INFO_WORDS; i += 32) info[(int64_t)v * INFO_WORDS + i] = rec[i];
+}
+
 template <int KKW>
 __global__ void __launch_bounds__(128)
 attn_self_compact_kernel(const Params p, const __nv_bfloat16* __restrict__ cache, int64_t R,
-                         unsigned long long* __restrict__ row_counter) {
+                         unsigned long long* __restrict__ row_counter, const uint32_t* __restrict__ info) {
   constexpr int WARPS = 4;
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -389,46 +447,63 @@ attn_self_compact_kernel(const Params p, const __nv_bfloat16* __restrict__ cache
       qa[ks][1] = *reinterpret_cast<const uint32_t*>(qrow + 16 * ks + 2 * tig + 8);
     }
   }
-  for (int i = threadIdx.x; i < 64; i += 128) mw[i] = 0u;
-  for (int i = threadIdx.x; i < K * n_pos; i += 128) {
-    const int b = i / n_pos, pp = i - b * n_pos;
-    sa[b * MAX_POS + pp] = (pp == n_pos - 1) ? (uint8_t)b : p.anc[((int64_t)v * K + b) * p.anc_stride + pp];
-  }
-  __syncthreads();
-  if (threadIdx.x < n_pos) {
-    uint32_t bits = 0u;
-    for (int b = 0; b < K; ++b) bits |= 1u << sa[b * MAX_POS + threadIdx.x];
-    live[threadIdx.x] = (uint8_t)bits;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int pp = 0; pp < n_pos; ++pp) {
-      off[pp] = (uint16_t)acc;
-      acc += __popc((uint32_t)live[pp]);
+  int n_live, rows_pad;
+  if (info != nullptr) {
+    // the step's per-video record (compact_info_kernel): one coalesced read instead of the derivation below
+    const uint32_t* rec = info + (int64_t)v * INFO_WORDS;
+    uint32_t* rs32 = reinterpret_cast<uint32_t*>(rowsrc);
+    for (int i = threadIdx.x; i < INFO_WORDS; i += 128) {
+      const uint32_t w = __ldg(rec + i);
+      if (i == 0) n_live_s = (int)w;
+      else if (i <= 64) mw[i - 1] = w;
+      else rs32[i - 65] = w;
     }
-    off[n_pos] = (uint16_t)acc;
-    n_live_s = acc;
-    if (h == 0 && row_counter != nullptr) atomicAdd(row_counter, (unsigned long long)acc);
-  }
-  __syncthreads();
-  const int n_live = n_live_s;
-  const int rows_pad = (n_live + 15) & ~15;
-  // row table + per-beam key masks in the compacted index space
-  for (int i = threadIdx.x; i < K * n_pos; i += 128) {
-    const int s = i / n_pos, pp = i - s * n_pos;        // here: candidate slot s of position pp
-    const uint32_t bits = live[pp];
-    if ((bits >> s) & 1u) rowsrc[off[pp] + __popc(bits & ((1u << s) - 1u))] = (uint16_t)(pp * K + s);
-    // beam b == s of this loop index: its key at position pp
-    const int b = s;
-    const int slot = sa[b * MAX_POS + pp];
-    const int tok = p.tok_hist[(int64_t)v * p.tok_stride + pp * K + slot];
-    if (tok != CARE_PAD) {
-      const int j = off[pp] + __popc(bits & ((1u << slot) - 1u));
-      atomicOr(&mw[b * 8 + (j >> 5)], 1u << (j & 31));
+    __syncthreads();
+    n_live = n_live_s;
+    rows_pad = (n_live + 15) & ~15;
+    if (threadIdx.x == 0 && h == 0 && row_counter != nullptr) atomicAdd(row_counter, (unsigned long long)n_live);
+  } else {
+    for (int i = threadIdx.x; i < 64; i += 128) mw[i] = 0u;
+    for (int i = threadIdx.x; i < K * n_pos; i += 128) {
+      const int b = i / n_pos, pp = i - b * n_pos;
+      sa[b * MAX_POS + pp] = (pp == n_pos - 1) ? (uint8_t)b : p.anc[((int64_t)v * K + b) * p.anc_stride + pp];
     }
+    __syncthreads();
+    if (threadIdx.x < n_pos) {
+      uint32_t bits = 0u;
+      for (int b = 0; b < K; ++b) bits |= 1u << sa[b * MAX_POS + threadIdx.x];
+      live[threadIdx.x] = (uint8_t)bits;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int acc = 0;
+      for (int pp = 0; pp < n_pos; ++pp) {
+        off[pp] = (uint16_t)acc;
+        acc += __popc((uint32_t)live[pp]);
+      }
+      off[n_pos] = (uint16_t)acc;
+      n_live_s = acc;
+      if (h == 0 && row_counter != nullptr) atomicAdd(row_counter, (unsigned long long)acc);
+    }
+    __syncthreads();
+    n_live = n_live_s;
+    rows_pad = (n_live + 15) & ~15;
+    // row table + per-beam key masks in the compacted index space
+    for (int i = threadIdx.x; i < K * n_pos; i += 128) {
+      const int s = i / n_pos, pp = i - s * n_pos;        // here: candidate slot s of position pp
+      const uint32_t bits = live[pp];
+      if ((bits >> s) & 1u) rowsrc[off[pp] + __popc(bits & ((1u << s) - 1u))] = (uint16_t)(pp * K + s);
+      // beam b == s of this loop index: its key at position pp
+      const int b = s;
+      const int slot = sa[b * MAX_POS + pp];
+      const int tok = p.tok_hist[(int64_t)v * p.tok_stride + pp * K + slot];
+      if (tok != CARE_PAD) {
+        const int j = off[pp] + __popc(bits & ((1u << slot) - 1u));
+        atomicOr(&mw[b * 8 + (j >> 5)], 1u << (j & 31));
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
   // gather: 16 chunks of 16 B per live row (8 of K, 8 of V)
   {
     const __nv_bfloat16* kbase = cache + (int64_t)v * K * (3LL * p.d) + p.k_col + h * DH;
@@ -455,13 +530,21 @@ template <int KKW>
 static int launch_compact(care_ctx* ctx, const Params& p, const void* cache, int64_t R, cudaStream_t stream) {
   auto kern = attn_self_compact_kernel<KKW>;
   const size_t smem = (size_t)2 * p.rows_pad * 128 + 1024 + 16 + 256 + 256 + (size_t)4 * 8 * COMB_LD * 4 +
-                      8 * MAX_POS + MAX_POS + (MAX_POS + 2) * 2 + (size_t)p.rows_pad * 2 + 64;
+                      8 * MAX_POS + MAX_POS + (MAX_POS + 2) * 2 + 384 /* rowsrc: 190 uint16 of a record */ + 64;
   static size_t configured = 0;
   if (smem > configured) {
     CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  kern<<<p.n_items, 128, smem, stream>>>(p, static_cast<const __nv_bfloat16*>(cache), R, ctx->self_attn_rows);
+  const uint32_t* info = nullptr;
+  if (ctx->compact_info != nullptr && p.n_items / p.H <= ctx->compact_info_videos) {
+    const int B = p.n_items / p.H;
+    compact_info_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p.anc, p.anc_stride, p.tok_hist, p.tok_stride, p.done, B, p.K,
+                                                         p.n_pos, ctx->compact_info);
+    CARE_LAUNCH_CHECK(ctx);
+    info = ctx->compact_info;
+  }
+  kern<<<p.n_items, 128, smem, stream>>>(p, static_cast<const __nv_bfloat16*>(cache), R, ctx->self_attn_rows, info);
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

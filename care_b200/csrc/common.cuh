@@ -80,6 +80,9 @@ struct care_ctx {
   // 1: the bf16 self-attention gathers only the cache slots still referenced by a beam (less HBM traffic, but
   // measured slower than the dense TMA tiles on the benchmark model: profiles/), 0 (default): dense tiles
   int self_compact = 0;
+  int gemm_smallm = 1;   // M <= 16: weight-streaming mma.sync kernel instead of 128-row tensor-core tiles
+  uint32_t* compact_info = nullptr;   // [compact_info_videos][160] per-video records of the compacting kernel
+  int compact_info_videos = 0;
   unsigned long long* self_attn_rows = nullptr;   // device counter: K/V rows gathered per (video) by head 0
   // 0: single-CTA tiles only, 1: CTA-pair (cta_group::2) tiles whenever the shape allows, 2 (default): pick per
   // (M, N, K, out dtype) by timing both once on the first call with that shape (skipped while capturing)

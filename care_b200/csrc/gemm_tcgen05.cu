@@ -20,6 +20,10 @@ namespace tc2 {  // gemm_tcgen05_2sm.cu: returns 1 when the shape should use the
 int gemm_bf16_2sm(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
                   int64_t ldc, int out_dtype, int M, int N, int n_store, int K, int act, cudaStream_t stream);
 }
+namespace smallm {  // gemm_smallm.cu: returns 1 when the shape is not covered (M > 16, ...)
+int gemm_bf16_smallm(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
+                     int64_t ldc, int out_dtype, int M, int N, int n_store, int K, int act, cudaStream_t stream);
+}
 namespace tc {
 
 constexpr int GEMM_EPI_BYTES = 8 * 4096;   // one 32x32 fp32 staging block per epilogue warp
@@ -265,6 +269,10 @@ int gemm_bf16(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t 
   const int n_pad = (N + 7) & ~7;
   CARE_CHECK_ARG(n_pad <= ldc || N % 8 == 0, "care_gemm(bf16): ldc %lld too small for N=%d", (long long)ldc, N);
   const int n_store = n_pad <= ldc ? n_pad : N;
+  if (ctx->gemm_smallm) {   // latency mode: a handful of rows -> weight-streaming kernel
+    const int rcs = smallm::gemm_bf16_smallm(ctx, A, lda, W, ldw, bias, C, ldc, out_dtype, M, N, n_store, K, act, stream);
+    if (rcs != 1) return rcs;
+  }
   int use_2sm = ctx->gemm_2sm;
   if (use_2sm == 2) {
     // per-shape choice between the CTA-pair kernel and single-CTA tiles, measured once

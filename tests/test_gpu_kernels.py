@@ -84,6 +84,33 @@ def test_gemm_bf16_tcgen05(env, M, N, K, out_dtype):
         assert (C[:, N:].float() == 0).all()
 
 
+@pytest.mark.parametrize("M,N,K", [(5, 1024, 1024), (1, 3072, 1024), (16, 14745, 1024), (5, 1024, 4096), (8, 500, 2048),
+                                   (5, 10547, 512), (3, 768, 768)])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_gemm_small_m_matches_tile_kernel(env, M, N, K, out_dtype):
+    """Latency-mode GEMM (M <= 16, weight streaming) against the fp32 product and the tcgen05 tile kernel."""
+    lib, h, L = env
+    g = torch.Generator(device="cuda").manual_seed(M * 13 + N)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    act = 1 if out_dtype == torch.bfloat16 else 0
+    lib.care_ctx_set_option(h, b"gemm_smallm", 1)
+    C1 = _gemm(env, BF16, A, W, b, out_dtype, act)
+    lib.care_ctx_set_option(h, b"gemm_smallm", 0)
+    C0 = _gemm(env, BF16, A, W, b, out_dtype, act)
+    lib.care_ctx_set_option(h, b"gemm_smallm", 1)
+    ref = A.float() @ W.float().t() + b
+    if act:
+        ref = ref.relu()
+    tol = 2e-3 if out_dtype == torch.float32 else 2e-2
+    assert torch.isfinite(C1.float()).all()
+    assert (C1[:, :N].float() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+    assert (C1.float() - C0.float()).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+    if C1.shape[1] > N:
+        assert (C1[:, N:].float() == 0).all()
+
+
 def test_gemm_bf16_strided_output(env):
     """QKV GEMM writes straight into a [T, R, 3d] cache slice and reads strided A."""
     lib, h, L = env
