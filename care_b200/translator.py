@@ -46,6 +46,8 @@ class Translator_ARFormer(object):
     def translate_batch(self, models, batch, *args, **kwargs):
         model = _single_model(models)
         feats = batch["feats"]
+        if feats[0].shape[0] == 0:
+            return [], []
         with torch.no_grad():
             if feats[0].device.type == "cpu" and feats[0].shape[0] > self.pipeline_chunk:
                 out = self.decode_pipelined(model, feats, self.pipeline_chunk)
@@ -178,6 +180,8 @@ class Translator_NARFormer(object):
         if teacher_model_wrapper is not None:
             raise NotImplementedError("teacher rescoring is outside the accelerated hot path")
         model = _single_model(models)
+        if batch["feats"][0].shape[0] == 0:
+            return [], []
         eng = model.engine()
         with torch.no_grad():
             enc = model.encoding_phase(batch["feats"])

@@ -368,3 +368,12 @@ def test_single_video_and_many_videos_agree():
     for v in (0, 5, 11):
         h, s = tr.translate_batch([model], {"feats": [f[v:v + 1].cuda() for f in feats]})
         assert h[0] == rec["hyps"][v]
+
+
+def test_empty_batch():
+    import care_b200
+    rec = load_golden("cfg2_sharp")
+    opt, sd, feats = rebuild_case(rec)
+    model = _gpu_model(opt, sd, "fp32")
+    tr = care_b200.get_translator(opt)
+    assert tr.translate_batch([model], {"feats": [f[:0].cuda() for f in feats]}) == ([], [])
