@@ -220,7 +220,8 @@ __device__ __forceinline__ void attend(const Params& p, int v, int h, int warp, 
     }
     return;
   }
-  // ---- merge the partials of the warps ---------------------------------------------------------------
+  // ---- merge the partials of the warps (the merge buffer aliases the K tile) --------------------------
+  __syncthreads();
   {
     float* crow = comb + ((size_t)warp * 8 + g) * COMB_LD + 2 * tig;
 #pragma unroll
@@ -273,7 +274,8 @@ attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   uint8_t* aux_gen = smem_raw + (aux - raw);
   uint32_t* mw = reinterpret_cast<uint32_t*>(aux_gen + 16);                 // [8 beams][8 words] key masks
   float* stat = reinterpret_cast<float*>(aux_gen + 16 + 256);               // [WARPS][8][2] (max, sum)
-  float* comb = reinterpret_cast<float*>(aux_gen + 16 + 256 + 256);         // [WARPS][8][COMB_LD] partial O
+  // [WARPS][8][COMB_LD] partial O: reuses the K tile, which is dead once every warp has its scores
+  float* comb = reinterpret_cast<float*>(smem_raw + (k_s - raw));
 
   // V rows [n_keys, rows_pad) are multiplied by P == 0: they must hold finite values
   {
@@ -327,7 +329,9 @@ attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
 template <int KKW, bool SELF, int WARPS>
 static int launch(care_ctx* ctx, const CUtensorMap& tmap, const Params& p, cudaStream_t stream) {
   auto kern = attn_mma_kernel<KKW, SELF, WARPS>;
-  const size_t smem = (size_t)2 * p.rows_pad * 128 + 1024 + 16 + 256 + 256 + (size_t)WARPS * 8 * COMB_LD * 4;
+  const size_t tiles = (size_t)2 * p.rows_pad * 128;
+  const size_t comb_bytes = WARPS > 1 ? (size_t)WARPS * 8 * COMB_LD * 4 : 0;   // aliases the K tile
+  const size_t smem = std::max(tiles, comb_bytes) + 1024 + 16 + 256 + 256;
   static size_t configured = 0;
   if (smem > configured) {
     CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
