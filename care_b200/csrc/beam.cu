@@ -246,6 +246,7 @@ beam_row_kernel(const care_beam_state st, const float* __restrict__ logits, int6
       warp_merge<KB>(l, ov, oi);
       float ssum = lane < ROW_WARPS ? sm_red[lane] : 0.f;
       ssum = warp_sum(ssum);
+      __syncwarp();   // every lane has read keep_* before lane 0 overwrites it
       if (lane == 0) {
 #pragma unroll
         for (int q = 0; q < KB; ++q) {
