@@ -8,7 +8,7 @@
 // mma.sync.m16n8k16.  The 8 consecutive K elements a thread loads are used as the k-fragments of two MMA
 // steps for BOTH operands, i.e. the contraction index is permuted identically in A and B, which leaves the
 // product unchanged and avoids any shared-memory transpose.  Partial sums of the 4 warps meet in smem.
-#include "common.cuh"
+#include "dev_util.cuh"
 
 namespace care {
 namespace smallm {
@@ -17,12 +17,9 @@ constexpr int WARPS = 4;
 constexpr int COLS = 8;   // output columns (W rows) per CTA
 
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
-      "{%0, %1, %2, %3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  care::dev::mma_m16n8k16(c, a[0], a[1], a[2], a[3], b0, b1);
 }
+
 
 template <typename OutT>
 __global__ void __launch_bounds__(WARPS * 32)
