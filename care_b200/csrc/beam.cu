@@ -305,51 +305,94 @@ beam_update_kernel(const care_beam_state st, const SegLayout sl, int step, int m
   const int nsel = K + 1;
 
   if (sl.partials != nullptr) {
-    // merge the row's segment records into one (max, sum-exp, top-KB) record; the whole warp works on one
-    // row at a time (small batches put every tile in its own run: ~2 x n_tiles segments per row)
-    for (int b = 0; b < K; ++b) {
-      const int r = v * K + b;
-      const int m_blk = r >> 7;
-      const int c0 = (int)((((int64_t)m_blk * sl.n_tiles + 1) * sl.G - 1) / sl.T);
-      const int c1 = (int)((((int64_t)m_blk * sl.n_tiles + sl.n_tiles) * sl.G - 1) / sl.T);
-      const float* base = sl.partials + (int64_t)r * sl.nseg * (2 + 2 * KB);
-      const int64_t mlo = (int64_t)m_blk * sl.n_tiles, mhi = mlo + sl.n_tiles;
-      const int nslot = 2 * (c1 - c0 + 1);
-      float M = -INFINITY, S = 0.f;
-      TopList<KB> l;
-      l.init();
-      for (int sidx = lane; sidx < nslot; sidx += 32) {
-        const int c = c0 + (sidx >> 1), g = sidx & 1;
-        // segment 2*(c - c0) + g exists iff epilogue group g of run c saw a tile of this m-block
-        const int64_t start = (int64_t)c * sl.T / sl.G, end = (int64_t)(c + 1) * sl.T / sl.G;
-        const int64_t lo = start > mlo ? start : mlo, hi = end < mhi ? end : mhi;
-        if (!(lo + ((g - (lo - start)) & 1) < hi)) continue;
-        const float* rec = base + sidx * (2 + 2 * KB);
-        const float m = rec[0];
-        if (m > M) {
-          S *= __expf(M - m);
-          M = m;
+    // merge the row's segment records into one (max, sum-exp, top-KB) record
+    const int max_slots = 2 * (int)((sl.n_tiles * sl.G + sl.T - 1) / sl.T + 1);   // upper bound of segments per row
+    if (max_slots <= 8) {
+      // large batches: a few segments per row -> one lane per row, no cross-lane traffic
+      if (lane < K) {
+        const int r = v * K + lane;
+        const int m_blk = r >> 7;
+        const int c0 = (int)((((int64_t)m_blk * sl.n_tiles + 1) * sl.G - 1) / sl.T);
+        const int c1 = (int)((((int64_t)m_blk * sl.n_tiles + sl.n_tiles) * sl.G - 1) / sl.T);
+        const float* base = sl.partials + (int64_t)r * sl.nseg * (2 + 2 * KB);
+        const int64_t mlo = (int64_t)m_blk * sl.n_tiles, mhi = mlo + sl.n_tiles;
+        float M = -INFINITY, S = 0.f;
+        TopList<KB> l;
+        l.init();
+        for (int sidx = 0; sidx < 2 * (c1 - c0 + 1); ++sidx) {
+          const int c = c0 + (sidx >> 1), g = sidx & 1;
+          const int64_t start = (int64_t)c * sl.T / sl.G, end = (int64_t)(c + 1) * sl.T / sl.G;
+          const int64_t lo = start > mlo ? start : mlo, hi = end < mhi ? end : mhi;
+          if (!(lo + ((g - (lo - start)) & 1) < hi)) continue;
+          const float* rec = base + sidx * (2 + 2 * KB);
+          const float m = rec[0];
+          if (m > M) {
+            S *= __expf(M - m);
+            M = m;
+          }
+          S += rec[1] * __expf(rec[0] - M);
+#pragma unroll
+          for (int q = 0; q < KB; ++q) {
+            const int idx = reinterpret_cast<const int*>(rec)[2 + KB + q];
+            if (idx != INT_MAX) l.insert(rec[2 + q], idx);
+          }
         }
-        S += rec[1] * __expf(rec[0] - M);
+        float* out = st.scratch + (int64_t)r * (2 + 2 * KB);
+        out[0] = M;
+        out[1] = S;
 #pragma unroll
         for (int q = 0; q < KB; ++q) {
-          const int idx = reinterpret_cast<const int*>(rec)[2 + KB + q];
-          if (idx != INT_MAX) l.insert(rec[2 + q], idx);
+          out[2 + q] = l.v[q];
+          reinterpret_cast<int*>(out)[2 + KB + q] = l.i[q];
         }
       }
-      const float Mw = warp_max(M);
-      const float Sw = warp_sum(M == -INFINITY ? 0.f : S * __expf(M - Mw));
-      float mv[KB];
-      int mi[KB];
-      warp_merge<KB>(l, mv, mi);
-      if (lane == 0) {
-        float* out = st.scratch + (int64_t)r * (2 + 2 * KB);
-        out[0] = Mw;
-        out[1] = Sw;
-#pragma unroll
-        for (int q = 0; q < KB; ++q) {
-          out[2 + q] = mv[q];
-          reinterpret_cast<int*>(out)[2 + KB + q] = mi[q];
+    } else {
+      // small batches put every tile in its own run (~2 x n_tiles segments per row): the whole warp works on
+      // one row at a time
+      for (int b = 0; b < K; ++b) {
+        const int r = v * K + b;
+        const int m_blk = r >> 7;
+        const int c0 = (int)((((int64_t)m_blk * sl.n_tiles + 1) * sl.G - 1) / sl.T);
+        const int c1 = (int)((((int64_t)m_blk * sl.n_tiles + sl.n_tiles) * sl.G - 1) / sl.T);
+        const float* base = sl.partials + (int64_t)r * sl.nseg * (2 + 2 * KB);
+        const int64_t mlo = (int64_t)m_blk * sl.n_tiles, mhi = mlo + sl.n_tiles;
+        const int nslot = 2 * (c1 - c0 + 1);
+        float M = -INFINITY, S = 0.f;
+        TopList<KB> l;
+        l.init();
+        for (int sidx = lane; sidx < nslot; sidx += 32) {
+          const int c = c0 + (sidx >> 1), g = sidx & 1;
+          // segment 2*(c - c0) + g exists iff epilogue group g of run c saw a tile of this m-block
+          const int64_t start = (int64_t)c * sl.T / sl.G, end = (int64_t)(c + 1) * sl.T / sl.G;
+          const int64_t lo = start > mlo ? start : mlo, hi = end < mhi ? end : mhi;
+          if (!(lo + ((g - (lo - start)) & 1) < hi)) continue;
+          const float* rec = base + sidx * (2 + 2 * KB);
+          const float m = rec[0];
+          if (m > M) {
+            S *= __expf(M - m);
+            M = m;
+          }
+          S += rec[1] * __expf(rec[0] - M);
+  #pragma unroll
+          for (int q = 0; q < KB; ++q) {
+            const int idx = reinterpret_cast<const int*>(rec)[2 + KB + q];
+            if (idx != INT_MAX) l.insert(rec[2 + q], idx);
+          }
+        }
+        const float Mw = warp_max(M);
+        const float Sw = warp_sum(M == -INFINITY ? 0.f : S * __expf(M - Mw));
+        float mv[KB];
+        int mi[KB];
+        warp_merge<KB>(l, mv, mi);
+        if (lane == 0) {
+          float* out = st.scratch + (int64_t)r * (2 + 2 * KB);
+          out[0] = Mw;
+          out[1] = Sw;
+  #pragma unroll
+          for (int q = 0; q < KB; ++q) {
+            out[2 + q] = mv[q];
+            reinterpret_cast<int*>(out)[2 + KB + q] = mi[q];
+          }
         }
       }
     }
