@@ -561,7 +561,9 @@ int self_step(care_ctx* ctx, const void* cache, int n_pos, int B, int K, int H, 
     return launch_compact<3>(ctx, p, cache, R, stream);
   }
   if (n_keys <= 16) return launch<1, true, 1>(ctx, tmap, p, stream);
-  if (n_keys <= 64) return launch<4, true, 1>(ctx, tmap, p, stream);   // short prefixes: one warp, no merge
+  if (n_keys <= 32) return launch<2, true, 1>(ctx, tmap, p, stream);   // short prefixes: one warp, no merge
+  if (n_keys <= 64) return launch<2, true, 2>(ctx, tmap, p, stream);
+  if (n_keys <= 96) return launch<3, true, 2>(ctx, tmap, p, stream);    // <= 6 steps of 16 keys: two warps balance better
   if (n_keys <= 128) return launch<2, true, 4>(ctx, tmap, p, stream);
   return launch<3, true, 4>(ctx, tmap, p, stream);   // <= 160 keys: 10 steps of 16 over 4 warps
 }

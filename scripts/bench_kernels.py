@@ -58,7 +58,7 @@ def main():
         cache = torch.randn(Tm, R, 3 * d, device="cuda").bfloat16()
         anc = torch.randint(0, K, (B, K, Tm), device="cuda", dtype=torch.uint8)
         tok = torch.randint(4, 100, (B, Tm + 1, K), device="cuda", dtype=torch.int32)
-        for n_pos in (1, 8, 15, 29):
+        for n_pos in (1, 4, 6, 8, 10, 12, 15, 22, 29):
             for impl in (0, 1):
                 lib.care_ctx_set_option(h, b"attn_impl", impl)
                 ms = timed(lambda: _lib.check(lib.care_self_attn_step(
