@@ -274,7 +274,8 @@ template <int NT>
 static int launch_mma(care_ctx* ctx, const CUtensorMap& tmap, const Params& p, cudaStream_t stream) {
   auto kern = group_attn_mma_kernel<NT>;
   const size_t smem = (size_t)2 * p.rows_pad * 128 + 1024 + 16;
-  static size_t configured = 0;
+  static size_t configured_all[64] = {0};   // per device: function attributes are per device
+  size_t& configured = configured_all[ctx->device & 63];
   if (smem > configured) {
     CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

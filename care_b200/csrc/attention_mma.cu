@@ -278,7 +278,8 @@ static int launch(care_ctx* ctx, const CUtensorMap& tmap, const Params& p, cudaS
   const size_t tiles = (size_t)2 * p.rows_pad * 128;
   const size_t comb_bytes = WARPS > 1 ? (size_t)WARPS * 8 * COMB_LD * 4 : 0;   // aliases the K tile
   const size_t smem = std::max(tiles, comb_bytes) + 1024 + 16 + 256 + 256;
-  static size_t configured = 0;
+  static size_t configured_all[64] = {0};   // per device: function attributes are per device
+  size_t& configured = configured_all[ctx->device & 63];
   if (smem > configured) {
     CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
@@ -481,7 +482,8 @@ static int launch_compact(care_ctx* ctx, const Params& p, const void* cache, int
   auto kern = attn_self_compact_kernel<KKW>;
   const size_t smem = (size_t)2 * p.rows_pad * 128 + 1024 + 16 + 256 + 256 + (size_t)4 * 8 * COMB_LD * 4 +
                       8 * MAX_POS + MAX_POS + (MAX_POS + 2) * 2 + 384 /* rowsrc: 190 uint16 of a record */ + 64;
-  static size_t configured = 0;
+  static size_t configured_all[64] = {0};   // per device: function attributes are per device
+  size_t& configured = configured_all[ctx->device & 63];
   if (smem > configured) {
     CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

@@ -244,7 +244,8 @@ template <int BN, typename OutT>
 static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, void* C, int64_t ldc,
                   int M, int N, int n_store, int K, int act, cudaStream_t stream) {
   using cfg = Cfg<BN>;
-  static bool configured = false;
+  static bool configured_all[64] = {false};   // per device: function attributes are per device
+  bool& configured = configured_all[ctx->device & 63];
   auto kern = gemm_bf16_tcgen05_kernel<BN, OutT>;
   if (!configured) {
     CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BN>()));

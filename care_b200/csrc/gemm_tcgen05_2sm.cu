@@ -14,8 +14,6 @@
 // Barriers: full[s] (leader; count 1 + 64 KB of transactions from both CTAs), empty[s] (both CTAs;
 // released by a multicast tcgen05.commit), tfull[a] (both CTAs; multicast commit), tempty[a] (leader;
 // 8 arrivals: 4 epilogue warps of each CTA, the peer's arrive remotely).
-#include <cooperative_groups.h>
-
 #include "tcgen05_util.cuh"
 
 namespace care {
@@ -267,7 +265,8 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
 template <typename OutT>
 static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, void* C, int64_t ldc,
                   int M, int N, int n_store, int K, int act, cudaStream_t stream) {
-  static bool configured = false;
+  static bool configured_all[64] = {false};   // per device: function attributes are per device
+  bool& configured = configured_all[ctx->device & 63];
   auto kern = gemm_bf16_2sm_kernel<OutT>;
   if (!configured) {
     CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

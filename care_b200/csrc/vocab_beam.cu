@@ -276,7 +276,8 @@ template <int KB>
 static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, float* partials, int nseg, int R, int V,
                   int d, cudaStream_t stream) {
   using cfg = Cfg<BN>;
-  static bool configured = false;
+  static bool configured_all[64] = {false};   // per device: function attributes are per device
+  bool& configured = configured_all[ctx->device & 63];
   auto kern = vocab_beam_tcgen05_kernel<KB>;
   if (!configured) {
     CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
