@@ -220,8 +220,11 @@ attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   uint8_t* aux_gen = smem_raw + (aux - raw);
   uint32_t* mw = reinterpret_cast<uint32_t*>(aux_gen + 16);                 // [8 beams][8 words] key masks
   float* stat = reinterpret_cast<float*>(aux_gen + 16 + 256);               // [WARPS][8][2] (max, sum)
-  // [WARPS][8][COMB_LD] partial O: reuses the K tile, which is dead once every warp has its scores
-  float* comb = reinterpret_cast<float*>(smem_raw + (k_s - raw));
+  // [WARPS][8][COMB_LD] partial O: reuses the K tile (dead once every warp has its scores) when it is large
+  // enough, else it sits behind the auxiliary block (short key sets, e.g. the 30 concept embeddings)
+  constexpr uint32_t kCombBytes = WARPS * 8 * COMB_LD * 4;
+  float* comb = tile_bytes >= kCombBytes ? reinterpret_cast<float*>(smem_raw + (k_s - raw))
+                                         : reinterpret_cast<float*>(aux_gen + 16 + 256 + 256);
 
   // V rows [n_keys, rows_pad) are multiplied by P == 0: they must hold finite values
   {
@@ -275,9 +278,10 @@ attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
 template <int KKW, bool SELF, int WARPS>
 static int launch(care_ctx* ctx, const CUtensorMap& tmap, const Params& p, cudaStream_t stream) {
   auto kern = attn_mma_kernel<KKW, SELF, WARPS>;
-  const size_t tiles = (size_t)2 * p.rows_pad * 128;
-  const size_t comb_bytes = WARPS > 1 ? (size_t)WARPS * 8 * COMB_LD * 4 : 0;   // aliases the K tile
-  const size_t smem = std::max(tiles, comb_bytes) + 1024 + 16 + 256 + 256;
+  const size_t tile = (size_t)p.rows_pad * 128;
+  const size_t comb_bytes = WARPS > 1 ? (size_t)WARPS * 8 * COMB_LD * 4 : 0;
+  // the merge buffer aliases the K tile when that is large enough, else it gets its own space
+  const size_t smem = 2 * tile + 1024 + 16 + 256 + 256 + (tile >= comb_bytes ? 0 : comb_bytes);
   static size_t configured_all[64] = {0};   // per device: function attributes are per device
   size_t& configured = configured_all[ctx->device & 63];
   if (smem > configured) {
@@ -525,6 +529,8 @@ int cross_step(care_ctx* ctx, const void* q, int64_t ldq, const void* kv, int Lm
   p.done = done;
   p.out = static_cast<__nv_bfloat16*>(ctx_out);
   p.n_items = B * H;
+  if (Lm <= 32) return launch<2, false, 1>(ctx, tmap, p, stream);   // e.g. the 30 concept embeddings (attr_attention)
+  if (Lm <= 64) return launch<2, false, 2>(ctx, tmap, p, stream);
   return launch<2, false, 4>(ctx, tmap, p, stream);   // Lm <= 128: 8 steps of 16 keys over 4 warps
 }
 

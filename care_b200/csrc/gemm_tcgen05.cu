@@ -325,9 +325,12 @@ int gemm_bf16(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t 
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
         choice = (ok2 && best_ms[1] < best_ms[0]) ? 1 : 0;
-        std::lock_guard<std::mutex> g(ctx->mu);
-        ctx->gemm_choice[key] = choice;
-        return 0;   // C already holds the result (both variants compute the same GEMM)
+        {
+          std::lock_guard<std::mutex> g(ctx->mu);
+          ctx->gemm_choice[key] = choice;
+        }
+        // C holds the result of the variant timed last; fall through so that THIS call, like every later
+        // one, returns the chosen kernel's output (the two variants may differ in the last bit)
       }
     }
     use_2sm = choice;

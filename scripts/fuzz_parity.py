@@ -19,6 +19,7 @@ from oracle.weights import SHARP, make_state_dict  # noqa: E402
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 tot = exact = ties = bad = 0
+worst_bf16 = 0.0
 t0 = time.time()
 for case in range(n_cases):
     cfg = rng.choice(["cfg1", "cfg2", "cfg2", "cab", "cfg5"])
@@ -67,6 +68,48 @@ for case in range(n_cases):
             bad += 1
             print("MISMATCH case %d cfg %s over %s video %d margin %g" % (case, cfg, over, v, margins[v]))
     del model
+    # bf16 leg: every step's logits of the KV-cached path (attention MMA kernels for this K, small-M or tile
+    # GEMMs for this batch) within 1e-2 relative of the oracle run on bf16-rounded weights; graph replay stable
+    if cfg != "cfg5":
+        m16 = care_b200.get_framework(dict(opt, care_precision="bf16"))
+        m16.load_state_dict(sd)
+        m16 = m16.eval().cuda()
+        dev_feats = [f.cuda() for f in feats]
+        first = tr.translate_batch([m16], {"feats": dev_feats})
+        second = tr.translate_batch([m16], {"feats": dev_feats})
+        if first != second:
+            third = tr.translate_batch([m16], {"feats": dev_feats})
+            nd = [v for v in range(B) if first[0][v] != second[0][v]]
+            print("BF16 REPLAY case %d cfg %s over %s B=%d sharp=%s: videos %s differ; replay==replay2: %s" % (
+                case, cfg, over, B, sharp, nd, second == third))
+            for v in nd[:2]:
+                print("   first ", first[0][v][0], first[1][v][0])
+                print("   second", second[0][v][0], second[1][v][0])
+            bad += 1
+        eng = m16.engine()
+        enc = m16.encoding_phase(dev_feats)
+        K = opt["beam_size"]
+        trace = []
+        eng.ar_decode(enc, B, beam_size=K, topk=opt["topk"], trace=trace, trace_logits=True, early_exit_every=0)
+        sd16 = {k: (v.bfloat16().float() if v.dim() == 2 and "embeddings" not in k else v) for k, v in sd.items()}
+        inputs = {k: co.repeat_rows(enc[k].float().cpu(), K) for k in co.decoder_input_keys(opt)}
+        for rec in trace[::3]:
+            t = rec["step"]
+            anc, hist = rec["pre"]["anc"], rec["pre"]["tok_hist"]
+            rows = [[int(hist[v, p, int(anc[v, b, p])]) for p in range(t - 1)] + [int(hist[v, t - 1, b])]
+                    for v in range(B) for b in range(K)]
+            ref = co.decoding_phase(sd16, opt, torch.tensor(rows, dtype=torch.long), inputs, last_time_step_logits=True)
+            live = (rec["pre"]["done"] == 0).repeat_interleave(K)
+            if t == 1:
+                live = live & (torch.arange(B * K) % K == 0)
+            if live.any():
+                rel = (rec["logits"][live] - ref[live]).abs().max().item() / ref[live].abs().max().item()
+                worst_bf16 = max(worst_bf16, rel)
+                if rel >= 1e-2:
+                    bad += 1
+                    print("BF16 LOGITS case %d cfg %s over %s step %d rel err %g" % (case, cfg, over, t, rel))
+        del m16
+print("fuzz bf16: worst per-step logit error %.2e relative (tolerance 1e-2)" % worst_bf16)
 print("fuzz: %d cases, %d videos: %d identical, %d differ at an oracle near-tie, %d unexplained; %.0f s" % (
     n_cases, tot, exact, ties, bad, time.time() - t0))
 sys.exit(1 if bad else 0)

@@ -247,10 +247,11 @@ def test_embed_ln_and_add_ln(env, dt, T):
 
 
 @pytest.mark.parametrize("dt,T", [(F32, torch.float32), (BF16, torch.bfloat16)])
-@pytest.mark.parametrize("K,H", [(5, 8), (1, 8), (3, 12), (5, 16)])
-def test_cross_attention(env, dt, T, K, H):
+@pytest.mark.parametrize("K,H,Lm", [(5, 8, 114), (1, 8, 114), (3, 12, 84), (5, 16, 114), (5, 8, 30), (8, 8, 30),
+                                    (5, 16, 56), (2, 8, 17), (8, 16, 128)])
+def test_cross_attention(env, dt, T, K, H, Lm):
     lib, h, L = env
-    B, Lm, d = 6, 114, H * 64
+    B, d = 6, H * 64
     R = B * K
     q = torch.randn(R, d, device="cuda").to(T)
     kv = torch.randn(B, Lm, 2 * d, device="cuda").to(T)
