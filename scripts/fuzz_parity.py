@@ -109,6 +109,33 @@ for case in range(n_cases):
                     bad += 1
                     print("BF16 LOGITS case %d cfg %s over %s step %d rel err %g" % (case, cfg, over, t, rel))
         del m16
+    else:
+        # mask-predict family, bf16: the full-sequence path (group attention, fused / plain vocabulary GEMM)
+        m16 = care_b200.get_framework(dict(opt, care_precision="bf16"))
+        m16.load_state_dict(sd)
+        m16 = m16.eval().cuda()
+        dev_feats = [f.cuda() for f in feats]
+        h1 = tr.translate_batch([m16], {"feats": dev_feats})
+        h2 = tr.translate_batch([m16], {"feats": dev_feats})
+        if h1 != h2:
+            bad += 1
+            print("BF16 NAR case %d: two identical calls returned different outputs" % case)
+        enc = m16.encoding_phase(dev_feats)
+        inputs = m16.prepare_inputs_for_decoder(enc, {})
+        L = rng.randint(4, 30)
+        gen = torch.Generator().manual_seed(case)
+        ids = torch.randint(4, opt["vocab_size"], (B * 2, L), generator=gen)
+        ids[0, L - 1] = 0
+        sd16 = {k: (v.bfloat16().float() if v.dim() == 2 and "embeddings" not in k else v) for k, v in sd.items()}
+        o_inputs = {k: co.repeat_rows(v.float().cpu(), 2) for k, v in inputs.items()}
+        ref = co.decoding_phase(sd16, opt, ids, o_inputs)
+        got = m16.decoding_phase(ids.cuda(), inputs)["logits"].float().cpu()
+        rel = (got - ref).abs().max().item() / ref.abs().max().item()
+        worst_bf16 = max(worst_bf16, rel)
+        if rel >= 1e-2:
+            bad += 1
+            print("BF16 NAR LOGITS case %d L=%d rel err %g" % (case, L, rel))
+        del m16
 print("fuzz bf16: worst per-step logit error %.2e relative (tolerance 1e-2)" % worst_bf16)
 print("fuzz: %d cases, %d videos: %d identical, %d differ at an oracle near-tie, %d unexplained; %.0f s" % (
     n_cases, tot, exact, ties, bad, time.time() - t0))
