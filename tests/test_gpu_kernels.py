@@ -111,6 +111,37 @@ def test_gemm_small_m_matches_tile_kernel(env, M, N, K, out_dtype):
         assert (C1[:, N:].float() == 0).all()
 
 
+@pytest.mark.parametrize("M,N,K", [(20480, 1024, 1024), (4096, 14745, 1024), (5001, 3072, 768), (20480, 1024, 4096),
+                                   (9999, 2049, 512)])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_gemm_cta_pair_matches_single_cta(env, M, N, K, out_dtype):
+    """The CTA-pair (cta_group::2) GEMM and the single-CTA GEMM, each forced, against the fp32 product:
+    row / column tails, K not a multiple of the stage depth, both output types, bias + ReLU."""
+    lib, h, L = env
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    act = 1 if out_dtype == torch.bfloat16 else 0
+    ref = A.float() @ W.float().t() + b
+    if act:
+        ref = ref.relu()
+    tol = 2e-3 if out_dtype == torch.float32 else 2e-2
+    outs = []
+    try:
+        for mode in (1, 0):
+            lib.care_ctx_set_option(h, b"gemm_2sm", mode)
+            C = _gemm(env, BF16, A, W, b, out_dtype, act)
+            assert torch.isfinite(C.float()).all()
+            assert (C[:, :N].float() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item()), mode
+            if C.shape[1] > N:
+                assert (C[:, N:].float() == 0).all()
+            outs.append(C)
+    finally:
+        lib.care_ctx_set_option(h, b"gemm_2sm", 2)
+    assert (outs[0].float() - outs[1].float()).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+
+
 def test_gemm_bf16_strided_output(env):
     """QKV GEMM writes straight into a [T, R, 3d] cache slice and reads strided A."""
     lib, h, L = env

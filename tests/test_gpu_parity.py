@@ -389,3 +389,39 @@ def test_randomised_differential_fp32():
                          capture_output=True, text=True, timeout=600)
     print(out.stdout[-400:])
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_full_size_batch_properties():
+    """BASELINE.json's full size (cfg4, 4096 videos = 20480 beam rows per GPU), where no CPU oracle run is
+    affordable for every video: size-independent properties.  (1) bf16: the second half of the batch is a
+    copy of the first, so both halves must decode to identical captions (rows are independent; this
+    exercises every kernel's addressing at the high row indices, the multi-segment vocabulary records and
+    the CTA-pair GEMM tiles).  (2) fp32: eight videos spread over the batch match the CPU oracle and the
+    same videos decoded alone."""
+    import care_b200
+    from oracle.shapes import CONFIGS, make_feats, make_opt
+    from oracle.weights import SHARP, make_state_dict
+    opt = make_opt(**CONFIGS["cfg4"])
+    sd = make_state_dict(opt, seed=5, perturb=True, sharpen=SHARP)
+    half = make_feats(opt, 2048, seed=77)
+    feats = [torch.cat([f, f]).cuda() for f in half]
+    tr = care_b200.get_translator(opt)
+    m16 = _gpu_model(opt, sd, "bf16")
+    hyps, scores = tr.translate_batch([m16], {"feats": feats})
+    assert len(hyps) == 4096 and all(len(h) == 1 and 1 <= len(h[0]) <= 29 for h in hyps)
+    assert hyps[:2048] == hyps[2048:] and scores[:2048] == scores[2048:]
+    assert len({tuple(h[0]) for h in hyps}) > 100      # not a degenerate decode
+    del m16
+    m32 = _gpu_model(opt, sd, "fp32")
+    h32, s32 = tr.translate_batch([m32], {"feats": feats})
+    assert h32[:2048] == h32[2048:]
+    pick = [0, 1, 511, 1024, 2047, 2048 + 3, 3000, 4095]
+    sub = [f[pick].contiguous() for f in feats]
+    h_sub, s_sub = tr.translate_batch([m32], {"feats": sub})
+    assert h_sub == [h32[i] for i in pick]
+    o_h, o_s, margins, _ = _oracle_margins(sd, opt, [f.cpu() for f in sub])
+    for j, i in enumerate(pick):
+        if h32[i] != o_h[j]:
+            assert margins[j] < 1e-4, "video %d differs although the oracle margin is %g" % (i, margins[j])
+        else:
+            assert abs(s32[i][0] - o_s[j][0]) < 1e-4 * max(1.0, abs(o_s[j][0]))
