@@ -29,10 +29,12 @@ for case in range(n_cases):
         over = dict(beam_size=K, topk=rng.randint(1, K), max_len=rng.choice([6, 12, 20, 30]),
                     beam_alpha=rng.choice([0.0, 0.7, 1.0]))
     over["vocab_size"] = rng.choice([517, 1203, 4099, 9468])
+    over["arch"] = rng.choice(["base", "base", "base", "median", "large"])
     opt = make_opt(**{**CONFIGS[cfg], **over})
     sharp = rng.random() < 0.7
     sd = make_state_dict(opt, seed=100 + case, perturb=True, sharpen=SHARP if sharp else None)
-    B = rng.randint(1, 9)
+    B = rng.randint(1, 9) if over["arch"] == "base" and rng.random() < 0.85 else rng.randint(1, 24) // (
+        1 if over["arch"] == "base" else 4) + 1
     feats = make_feats(opt, B, seed=200 + case)
     model = care_b200.get_framework(dict(opt, care_precision="fp32"))
     model.load_state_dict(sd)
@@ -58,20 +60,31 @@ for case in range(n_cases):
         srt = otr["enc"]["preds_attr"].sort(dim=1, descending=True)[0]
         k = opt["use_attr_topk"]
         concept_gap = (srt[:, :k] - srt[:, 1:k + 1]).min(dim=1)[0].tolist()
+    earlier_tie = False
     for v in range(B):
         tot += 1
+        n_common = min(len(hyps[v]), len(o_h[v]))
         if hyps[v] == o_h[v]:
             exact += 1
         elif margins[v] < 1e-4 or concept_gap[v] < 1e-6:
             ties += 1
+            earlier_tie = True
+        elif earlier_tie and n_common >= 1 and hyps[v][:n_common] == o_h[v][:n_common]:
+            # the reference carries `n_best = min(n_best, #finished)` over to LATER videos (Translator.py:215):
+            # an earlier video that legitimately differs at a tie can change how many hypotheses this one returns
+            ties += 1
         else:
             bad += 1
             print("MISMATCH case %d cfg %s over %s video %d margin %g" % (case, cfg, over, v, margins[v]))
+            print("   gpu", hyps[v], scores[v])
+            print("   ref", o_h[v], o_s[v])
+            if cfg != "cfg5":
+                print("   ref finished (score/len^alpha, t, k):", otr["beams"][v].finished)
     del model
     # bf16 leg: every step's logits of the KV-cached path (attention MMA kernels for this K, small-M or tile
     # GEMMs for this batch) within 1e-2 relative of the oracle run on bf16-rounded weights; graph replay stable
     if cfg != "cfg5":
-        m16 = care_b200.get_framework(dict(opt, care_precision="bf16"))
+        m16 = care_b200.get_framework(dict(opt, care_precision="bf16", care_self_compact=rng.random() < 0.3))
         m16.load_state_dict(sd)
         m16 = m16.eval().cuda()
         dev_feats = [f.cuda() for f in feats]
