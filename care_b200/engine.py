@@ -452,19 +452,20 @@ class CareEngine:
         return logits
 
     def ar_decode(self, enc, B, beam_size=5, topk=1, beam_alpha=1.0, early_exit_every=4, trace=None,
-                  trace_logits=False):
+                  trace_logits=False, bos=None):
         """Runs the whole beam search on device; returns padded int32 ids, lengths, raw scores, steps
         (device tensors).  `trace` (a list, tests only) receives per-step snapshots of the beam state."""
         K = beam_size
         need = max(K, topk)
         lib, ctx = self.lib, self.ctx
+        bos = BOS if bos is None else int(bos)
         if trace is None and self.use_graphs and B * K <= self.graph_max_rows:
-            return self._ar_decode_graph(enc, B, K, topk, float(beam_alpha))
+            return self._ar_decode_graph(enc, B, K, topk, float(beam_alpha), bos)
         st = self._stream()
         kv = self.cross_kv(enc["encoder_hidden_states"])
         akv = self.attr_kv(enc)
         bufs, bst = self._beam_buffers(B, K, need)
-        check(lib.care_beam_init(ctx, ctypes.byref(bst), BOS, st), "care_beam_init")
+        check(lib.care_beam_init(ctx, ctypes.byref(bst), bos, st), "care_beam_init")
         lib.care_ctx_set_early_exit(ctx, ptr(bufs["n_done"]), B)
         try:
             for t in range(1, self.max_len):
@@ -491,7 +492,7 @@ class CareEngine:
                                      ptr(out_score), ptr(out_t), st), "care_beam_finalize")
         return out_tok, out_len, out_score, out_t
 
-    def _ar_decode_graph(self, enc, B, K, topk, beam_alpha):
+    def _ar_decode_graph(self, enc, B, K, topk, beam_alpha, bos=BOS):
         """The whole decode (cross K/V projection, beam init, max_len-1 steps, finalisation) as ONE CUDA
         graph per (B, K, topk, alpha): a fixed launch sequence over fixed workspaces with no host
         sync inside, so small batches are not bound by per-launch host overhead.  Inputs are copied
@@ -519,7 +520,7 @@ class CareEngine:
             kv = self.cross_kv(memory, static=True)
             akv = self.attr_kv(static_enc, static=True)
             bufs, bst = self._beam_buffers(B, K, need)
-            check(lib.care_beam_init(ctx, ctypes.byref(bst), BOS, st), "care_beam_init")
+            check(lib.care_beam_init(ctx, ctypes.byref(bst), bos, st), "care_beam_init")
             lib.care_ctx_set_early_exit(ctx, ptr(bufs["n_done"]), B)
             try:
                 for t in range(1, self.max_len):
@@ -529,7 +530,7 @@ class CareEngine:
             check(lib.care_beam_finalize(ctx, ctypes.byref(bst), beam_alpha, topk, ptr(outs[0]), ptr(outs[1]),
                                          ptr(outs[2]), ptr(outs[3]), st), "care_beam_finalize")
 
-        key = (B, K, topk, beam_alpha)
+        key = (B, K, topk, beam_alpha, bos)
         entry = self._graphs.get(key)
         if entry is None:
             before = int(lib.care_ctx_launch_count(ctx))

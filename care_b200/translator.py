@@ -35,9 +35,7 @@ class Translator_ARFormer(object):
         self.beam_alpha = opt.get("beam_alpha", 1.0)
         self.topk = opt.get("topk", 1)
         self.max_len = opt.get("max_len", 30)
-        self.ar_token_id = opt.get("ar_token_id", None)
-        if self.ar_token_id is not None:
-            raise NotImplementedError("ar_token_id is outside the accelerated hot path")
+        self.ar_token_id = opt.get("ar_token_id", None)   # alternative <bos> id (Translator.py:33,61)
 
     # host-resident batches larger than this are decoded in chunks whose host->device copies overlap
     # the previous chunk's decode (the copy of 4096 videos' fp32 features is 1.4 GB)
@@ -160,7 +158,8 @@ class Translator_ARFormer(object):
         enc = model.encoding_phase(feats)
         B = enc["encoder_hidden_states"].shape[0]
         return eng.ar_decode(enc, B, beam_size=self.beam_size, topk=self.topk, beam_alpha=self.beam_alpha,
-                             trace=trace, early_exit_every=early_exit_every)
+                             trace=trace, early_exit_every=early_exit_every,
+                             bos=self.ar_token_id if self.ar_token_id is not None else None)
 
 
 class Translator_NARFormer(object):

@@ -312,7 +312,8 @@ def ar_translate(sd, opt, feats, return_trace=False):
         enc = encoding_phase(sd, opt, feats)
         B = feats[0].shape[0]
         inputs = {k: repeat_rows(enc[k], K) for k in decoder_input_keys(opt)}
-        beams = [VideoBeam(K, max_len, n_best, audit=return_trace) for _ in range(B)]
+        bos = opt.get("ar_token_id") if opt.get("ar_token_id") is not None else BOS   # Translator.py:61
+        beams = [VideoBeam(K, max_len, n_best, bos=bos, audit=return_trace) for _ in range(B)]
         active = list(range(B))
         for t in range(1, max_len):
             ids = torch.stack([beams[i].prefixes() for i in active]).view(-1, t)

@@ -425,3 +425,18 @@ def test_full_size_batch_properties():
             assert margins[j] < 1e-4, "video %d differs although the oracle margin is %g" % (i, margins[j])
         else:
             assert abs(s32[i][0] - o_s[j][0]) < 1e-4 * max(1.0, abs(o_s[j][0]))
+
+
+def test_alternative_bos_token():
+    """`ar_token_id` (Translator.py:33,61): the beams start from another token id than <bos>."""
+    import care_b200
+    rec = load_golden("cfg2_sharp")
+    opt, sd, feats = rebuild_case(rec, batch=5)
+    opt = dict(opt, ar_token_id=7)
+    model = _gpu_model(opt, sd, "fp32")
+    tr = care_b200.get_translator(opt)
+    hyps, scores = tr.translate_batch([model], {"feats": [f.cuda() for f in feats]})
+    o_h, o_s, margins, _ = _oracle_margins(sd, opt, feats)
+    for v in range(5):
+        assert hyps[v] == o_h[v] or margins[v] < 1e-4
+    assert hyps != [h for h in rec["hyps"][:5]]     # really started from another token
