@@ -395,7 +395,7 @@ def run_care_arm(args):
             if tkey in tr_json:
                 r["traffic"] = tr_json[tkey]["traffic_bytes_per_launch"]
                 r["traffic_source"] = "%s (dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches " \
-                                      "of one decode step, t~12-15)" % os.path.relpath(tfiles[-1], ROOT)
+                                      "of one decode step, t~15)" % os.path.relpath(tfiles[-1], ROOT)
     use_bf16 = args.precision == "bf16"
     if rank != 0:
         if world > 1:

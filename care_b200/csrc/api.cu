@@ -1,5 +1,6 @@
 // ctx lifetime, error string, TMA descriptor cache.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -96,6 +97,10 @@ int care_ctx_create(care_ctx** out, int device) {
     return -4;
   }
   c->encode = (care_tmap_encode_fn)fn;
+  // reproducible kernel selection for profiling runs: CARE_B200_GEMM_2SM=0|1 pins the GEMM variant instead of the
+  // one-time timing (timings taken under a profiler are not representative); CARE_B200_DEBUG=1 logs the choices
+  if (const char* e = getenv("CARE_B200_GEMM_2SM")) c->gemm_2sm = atoi(e);
+  if (const char* e = getenv("CARE_B200_DEBUG")) c->debug = atoi(e);
   if (cudaMalloc(&c->self_attn_rows, sizeof(unsigned long long)) != cudaSuccess ||
       cudaMemset(c->self_attn_rows, 0, sizeof(unsigned long long)) != cudaSuccess) {
     care::set_error("care_ctx_create: cannot allocate the ctx counters");

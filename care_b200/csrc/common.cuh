@@ -87,6 +87,7 @@ struct care_ctx {
   // 0: single-CTA tiles only, 1: CTA-pair (cta_group::2) tiles whenever the shape allows, 2 (default): pick per
   // (M, N, K, out dtype) by timing both once on the first call with that shape (skipped while capturing)
   int gemm_2sm = 2;
+  int debug = 0;
   std::unordered_map<uint64_t, int> gemm_choice;
   // device-side early exit: kernels without a per-video `done` predicate return at once when
   // *skip_counter >= skip_target (all videos of the batch have finished); NULL disables

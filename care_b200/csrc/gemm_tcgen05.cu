@@ -11,6 +11,8 @@
 // overlaps the MMAs of tiles i+1 and i+2.
 // Edges: TMA zero-fills out-of-bounds rows/columns of A and W; stores are predicated.
 #include <cstdint>
+#include <cstdio>
+#include <string>
 #include <initializer_list>
 
 #include "tcgen05_util.cuh"
@@ -325,6 +327,10 @@ int gemm_bf16(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t 
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
         choice = (ok2 && best_ms[1] < best_ms[0]) ? 1 : 0;
+        if (ctx->debug)
+          fprintf(stderr, "[care_b200] gemm M=%d N=%d K=%d out=%s: single-CTA %.3f ms, CTA-pair %s -> %s\n", M, N, K,
+                  out_dtype == CARE_F32 ? "f32" : "bf16", best_ms[0] / 3.0f,
+                  ok2 ? (std::to_string(best_ms[1] / 3.0f) + " ms").c_str() : "n/a", choice ? "CTA-pair" : "single-CTA");
         {
           std::lock_guard<std::mutex> g(ctx->mu);
           ctx->gemm_choice[key] = choice;
