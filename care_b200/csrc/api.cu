@@ -157,6 +157,10 @@ int care_ctx_set_option(care_ctx* ctx, const char* name, int value) {
     }
     return 0;
   }
+  if (strcmp(name, "vocab_2sm") == 0) {
+    ctx->vocab_2sm = value;
+    return 0;
+  }
   if (strcmp(name, "gemm_smallm") == 0) {
     ctx->gemm_smallm = value;
     return 0;

@@ -285,6 +285,7 @@ struct SegLayout {
   const float* partials;   // NULL: st.scratch already holds one record per row (beam_row_kernel)
   int nseg, n_tiles;
   int64_t T, G;
+  int row_shift;   // log2(rows per row block of the kernel that wrote the records: 7 single-CTA, 8 CTA pair)
 };
 
 template <int KB>
@@ -311,7 +312,7 @@ beam_update_kernel(const care_beam_state st, const SegLayout sl, int step, int m
       // large batches: a few segments per row -> one lane per row, no cross-lane traffic
       if (lane < K) {
         const int r = v * K + lane;
-        const int m_blk = r >> 7;
+        const int m_blk = r >> sl.row_shift;
         const int c0 = (int)((((int64_t)m_blk * sl.n_tiles + 1) * sl.G - 1) / sl.T);
         const int c1 = (int)((((int64_t)m_blk * sl.n_tiles + sl.n_tiles) * sl.G - 1) / sl.T);
         const float* base = sl.partials + (int64_t)r * sl.nseg * (2 + 2 * KB);
@@ -351,7 +352,7 @@ beam_update_kernel(const care_beam_state st, const SegLayout sl, int step, int m
       // one row at a time
       for (int b = 0; b < K; ++b) {
         const int r = v * K + b;
-        const int m_blk = r >> 7;
+        const int m_blk = r >> sl.row_shift;
         const int c0 = (int)((((int64_t)m_blk * sl.n_tiles + 1) * sl.G - 1) / sl.T);
         const int c1 = (int)((((int64_t)m_blk * sl.n_tiles + sl.n_tiles) * sl.G - 1) / sl.T);
         const float* base = sl.partials + (int64_t)r * sl.nseg * (2 + 2 * KB);
@@ -569,7 +570,7 @@ static int check_state(const care_beam_state* st, const char* who) {
 }  // namespace beam
 
 namespace vb {  // vocab_beam.cu
-void seg_layout(const care_ctx* ctx, int R, int V, int* n_tiles, int64_t* T, int64_t* G);
+void seg_layout(const care_ctx* ctx, int R, int V, int* n_tiles, int64_t* T, int64_t* G, int* row_shift);
 }
 }  // namespace care
 
@@ -629,7 +630,7 @@ int care_beam_step_partials(care_ctx* ctx, const care_beam_state* st, const floa
   beam::SegLayout sl{};
   sl.partials = partials;
   sl.nseg = nseg;
-  vb::seg_layout(ctx, st->B * K, st->V, &sl.n_tiles, &sl.T, &sl.G);
+  vb::seg_layout(ctx, st->B * K, st->V, &sl.n_tiles, &sl.T, &sl.G, &sl.row_shift);
   const int ugrid = (st->B + beam::UPD_WARPS - 1) / beam::UPD_WARPS, uthreads = beam::UPD_WARPS * 32;
   if (K <= 1) beam::beam_update_kernel<2><<<ugrid, uthreads, 0, s>>>(*st, sl, step, max_len, cand_val, cand_idx);
   else if (K <= 3) beam::beam_update_kernel<4><<<ugrid, uthreads, 0, s>>>(*st, sl, step, max_len, cand_val, cand_idx);

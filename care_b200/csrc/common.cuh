@@ -88,6 +88,7 @@ struct care_ctx {
   // (M, N, K, out dtype) by timing both once on the first call with that shape (skipped while capturing)
   int gemm_2sm = 2;
   int debug = 0;
+  int vocab_2sm = 1;   // fused vocabulary kernel on CTA pairs when the shape has >= two waves of pair tiles
   std::unordered_map<uint64_t, int> gemm_choice;
   // device-side early exit: kernels without a per-video `done` predicate return at once when
   // *skip_counter >= skip_target (all videos of the batch have finished); NULL disables

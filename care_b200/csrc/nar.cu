@@ -109,11 +109,11 @@ __global__ void __launch_bounds__(256) best_logits_kernel(const float* __restric
 
 // same from the fused vocabulary kernel's records (KB = 2); segment existence as in beam.cu
 __global__ void best_partials_kernel(const float* __restrict__ partials, int nseg, int n_tiles, int64_t T, int64_t G,
-                                     int rows, int32_t* __restrict__ idx, float* __restrict__ prob) {
+                                     int row_shift, int rows, int32_t* __restrict__ idx, float* __restrict__ prob) {
   constexpr int KB = 2, W = 2 + 2 * KB;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
-  const int m_blk = r >> 7;
+  const int m_blk = r >> row_shift;
   const int c0 = (int)((((int64_t)m_blk * n_tiles + 1) * G - 1) / T);
   const int c1 = (int)((((int64_t)m_blk * n_tiles + n_tiles) * G - 1) / T);
   const int64_t mlo = (int64_t)m_blk * n_tiles, mhi = mlo + n_tiles;
@@ -231,7 +231,7 @@ __global__ void select_kernel(const int32_t* __restrict__ tokens, const float* _
 }  // namespace nar
 
 namespace vb {  // vocab_beam.cu
-void seg_layout(const care_ctx* ctx, int R, int V, int* n_tiles, int64_t* T, int64_t* G);
+void seg_layout(const care_ctx* ctx, int R, int V, int* n_tiles, int64_t* T, int64_t* G, int* row_shift);
 }
 }  // namespace care
 
@@ -296,11 +296,11 @@ int care_nar_best_logits(care_ctx* ctx, const float* logits, int64_t ldv, int ro
 int care_nar_best_partials(care_ctx* ctx, const float* partials, int nseg, int rows, int V, int32_t* idx,
                            float* prob, void* stream) {
   CARE_CHECK_ARG(ctx && partials && idx && prob && rows > 0 && V > 0, "care_nar_best_partials: bad args");
-  int n_tiles;
+  int n_tiles, row_shift;
   int64_t T, G;
-  vb::seg_layout(ctx, rows, V, &n_tiles, &T, &G);
-  nar::best_partials_kernel<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, nseg, n_tiles, T, G, rows,
-                                                                                  idx, prob);
+  vb::seg_layout(ctx, rows, V, &n_tiles, &T, &G, &row_shift);
+  nar::best_partials_kernel<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, nseg, n_tiles, T, G,
+                                                                                  row_shift, rows, idx, prob);
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

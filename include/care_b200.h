@@ -63,7 +63,9 @@ int care_ctx_set_early_exit(care_ctx* ctx, const int32_t* counter, int target);
  * (M, N, K, out dtype) by timing both variants ONCE, on the first care_gemm call with that shape - the
  * only place the library waits on the stream (never while the stream is being captured). */
 int care_ctx_set_option(care_ctx* ctx, const char* name, int value);
-/* "gemm_smallm": 1 (default) = GEMMs with M <= 16 rows (batch-1 / latency mode) use a weight-streaming
+/* "vocab_2sm": 1 (default) = the fused vocabulary kernel runs on CTA pairs when the shape has at least two
+ * waves of 256 x 256 tiles, 0 = single-CTA tiles only.
+ * "gemm_smallm": 1 (default) = GEMMs with M <= 16 rows (batch-1 / latency mode) use a weight-streaming
  * warp-MMA kernel with one CTA per 8 output columns, 0 = always the tcgen05 tile kernels.
  * "self_compact" (option above): 1 = the bf16 self-attention kernel gathers only the KV-cache slots some
  * beam still references (experimental: less traffic, more latency), 0 (default) = it streams all K slots
