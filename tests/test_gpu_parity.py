@@ -380,12 +380,12 @@ def test_empty_batch():
 
 
 def test_randomised_differential_fp32():
-    """scripts/fuzz_parity.py: random beam widths / n_best / max_len / vocab sizes / batch sizes / model
+    """tests/fuzz_parity.py: random beam widths / n_best / max_len / vocab sizes / batch sizes / model
     families against the oracle; every mismatch must sit on an oracle near-tie."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_parity.py"), "24", "3"],
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "fuzz_parity.py"), "24", "3"],
                          capture_output=True, text=True, timeout=600)
     print(out.stdout[-400:])
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
