@@ -92,7 +92,7 @@ constexpr int ROW_CAP = 64;                             // candidate list capaci
 
 template <int KB>
 __global__ void __launch_bounds__(ROW_THREADS)
-beam_row_kernel(const care_beam_state st, const float* __restrict__ logits, int64_t ldv, int step) {
+beam_row_kernel(const care_beam_state st, const float* __restrict__ logits, int64_t ldv, int step, int normalized) {
   __shared__ float wl_v[ROW_WARPS][KB];
   __shared__ int wl_i[ROW_WARPS][KB];
   __shared__ float sm_red[ROW_WARPS];
@@ -262,8 +262,9 @@ beam_row_kernel(const care_beam_state st, const float* __restrict__ logits, int6
   }
   if (tid == 0) {
     float* rec = st.scratch + (int64_t)r * (2 + 2 * KB);
-    rec[0] = run_M;
-    rec[1] = run_S;
+    // `normalized`: the row already holds log-probabilities (ensemble mean): candidate value = x itself
+    rec[0] = normalized ? 0.f : run_M;
+    rec[1] = normalized ? 1.f : run_S;
 #pragma unroll
     for (int q = 0; q < KB; ++q) {
       rec[2 + q] = keep_v[q];
@@ -555,6 +556,45 @@ __global__ void beam_finalize_kernel(const care_beam_state st, double alpha, int
   }
 }
 
+// Model ensembling (Translator.py:111-133): out[r, :] = mean_i log_softmax(logits_i[r, :]), one CTA per row.
+constexpr int MAX_MODELS = 8;
+struct ModelLogits {
+  const float* p[MAX_MODELS];
+};
+__global__ void __launch_bounds__(256) ensemble_logprob_kernel(const ModelLogits ml, int n, int64_t ldv, int V,
+                                                               float* __restrict__ out) {
+  __shared__ float red[8];
+  __shared__ float lse[MAX_MODELS];
+  const int r = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = 0; i < n; ++i) {
+    const float* x = ml.p[i] + (int64_t)r * ldv;
+    float m = -INFINITY;
+    for (int c = tid; c < V; c += 256) m = fmaxf(m, x[c]);
+    m = warp_max(m);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float s = 0.f;
+    for (int c = tid; c < V; c += 256) s += expf(x[c] - m);
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += red[w];
+      lse[i] = m + logf(t);   // log_softmax(x) = (x - m) - log(sum) = x - lse
+    }
+    __syncthreads();
+  }
+  for (int c = tid; c < V; c += 256) {
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) acc += ml.p[i][(int64_t)r * ldv + c] - lse[i];
+    out[(int64_t)r * ldv + c] = acc / (float)n;
+  }
+}
+
 static int check_state(const care_beam_state* st, const char* who) {
   CARE_CHECK_ARG(st != nullptr, "%s: state is NULL", who);
   CARE_CHECK_ARG(st->B > 0 && st->K >= 1 && st->K <= 8, "%s: K=%d must be in [1,8]", who, st->K);
@@ -588,8 +628,8 @@ int care_beam_init(care_ctx* ctx, const care_beam_state* st, int bos, void* stre
   return 0;
 }
 
-int care_beam_step(care_ctx* ctx, const care_beam_state* st, const float* logits, int64_t ldv, int step, int max_len,
-                   float* cand_val, int32_t* cand_idx, void* stream) {
+static int beam_step_impl(care_ctx* ctx, const care_beam_state* st, const float* logits, int64_t ldv, int step,
+                          int max_len, float* cand_val, int32_t* cand_idx, void* stream, int normalized) {
   CARE_CHECK_ARG(ctx && logits, "care_beam_step: bad args");
   if (beam::check_state(st, "care_beam_step")) return -1;
   CARE_CHECK_ARG(step >= 1 && step <= st->T_max, "care_beam_step: step=%d outside [1,%d]", step, st->T_max);
@@ -603,7 +643,7 @@ int care_beam_step(care_ctx* ctx, const care_beam_state* st, const float* logits
   const int ugrid = (st->B + beam::UPD_WARPS - 1) / beam::UPD_WARPS, uthreads = beam::UPD_WARPS * 32;
 #define CARE_BEAM_GO(KB_)                                                                                  \
   do {                                                                                                     \
-    beam::beam_row_kernel<KB_><<<R, beam::ROW_THREADS, 0, s>>>(*st, logits, ldv, step);                    \
+    beam::beam_row_kernel<KB_><<<R, beam::ROW_THREADS, 0, s>>>(*st, logits, ldv, step, normalized);        \
     CARE_LAUNCH_CHECK(ctx);                                                                                \
     beam::beam_update_kernel<KB_><<<ugrid, uthreads, 0, s>>>(*st, beam::SegLayout{}, step, max_len, cand_val, \
                                                               cand_idx);                                   \
@@ -613,6 +653,30 @@ int care_beam_step(care_ctx* ctx, const care_beam_state* st, const float* logits
   else if (K <= 5) CARE_BEAM_GO(6);
   else CARE_BEAM_GO(9);
 #undef CARE_BEAM_GO
+  CARE_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int care_beam_step(care_ctx* ctx, const care_beam_state* st, const float* logits, int64_t ldv, int step, int max_len,
+                   float* cand_val, int32_t* cand_idx, void* stream) {
+  return beam_step_impl(ctx, st, logits, ldv, step, max_len, cand_val, cand_idx, stream, 0);
+}
+
+int care_beam_step_logprobs(care_ctx* ctx, const care_beam_state* st, const float* logprobs, int64_t ldv, int step,
+                            int max_len, float* cand_val, int32_t* cand_idx, void* stream) {
+  return beam_step_impl(ctx, st, logprobs, ldv, step, max_len, cand_val, cand_idx, stream, 1);
+}
+
+int care_ensemble_logprobs(care_ctx* ctx, const float* const* logits, int n, int64_t ldv, int R, int V, float* out,
+                           void* stream) {
+  CARE_CHECK_ARG(ctx && logits && out && n >= 1 && n <= beam::MAX_MODELS && R > 0 && V > 0,
+                 "care_ensemble_logprobs: bad args (n=%d, at most %d models)", n, beam::MAX_MODELS);
+  beam::ModelLogits ml{};
+  for (int i = 0; i < n; ++i) {
+    CARE_CHECK_ARG(logits[i] != nullptr, "care_ensemble_logprobs: logits[%d] is NULL", i);
+    ml.p[i] = logits[i];
+  }
+  beam::ensemble_logprob_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(ml, n, ldv, V, out);
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

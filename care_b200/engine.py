@@ -389,8 +389,9 @@ class CareEngine:
         st = BeamState(B=B, K=K, T_max=Tm, V=self.V, need=need, **{k: ptr(v) for k, v in bufs.items()})
         return bufs, st
 
-    def decode_step(self, t, B, K, enc, kv, bufs, bst, audit=None, want_logits=False, akv=None):
-        """One beam step (len_input_ids == t) for every video; 14 kernel launches (15 unfused)."""
+    def step_hidden(self, t, B, K, enc, kv, bufs, akv=None):
+        """Decoder layer for the newest position of every beam row (13 launches); returns the hidden states
+        [R, d] the vocabulary projection consumes.  `bufs` holds the shared beam state (tokens, ancestry)."""
         lib, ctx, dt, w, d, T = self.lib, self.ctx, self.dt, self.w, self.d, self.tdtype
         st = self._stream()
         R = B * K
@@ -401,8 +402,6 @@ class CareEngine:
         cx = self._buf("ctx", (R, d), T); qc = self._buf("qc", (R, d), T)
         y32 = self._buf("y32", (R, d), torch.float32)
         hb = self._buf("ffn_h", (R, self.F), T)
-        fused = self.fused_vocab and not want_logits
-        logits = None if fused else self._buf("logits", (R, self.ldv), torch.float32)
         gsg = enc.get("semantic_hidden_states")
         done = ptr(bufs["done"])
         check(lib.care_embed_ln(ctx, dt, ptr(bufs["cur_tok"]), None, t - 1, ptr(w["word"]), ptr(w["pos"]), None,
@@ -432,6 +431,16 @@ class CareEngine:
         self.gemm(hb, w["W2"], w["b2"], y32, R, d, self.F)
         check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x2), ptr(w["ln3_g"]), ptr(w["ln3_b"]), self.eps, R, d, ptr(x3),
                               st), "care_add_ln")
+        return x3
+
+    def decode_step(self, t, B, K, enc, kv, bufs, bst, audit=None, want_logits=False, akv=None):
+        """One beam step (len_input_ids == t) for every video; 14 kernel launches (15 unfused)."""
+        lib, ctx, w, d = self.lib, self.ctx, self.w, self.d
+        st = self._stream()
+        R = B * K
+        x3 = self.step_hidden(t, B, K, enc, kv, bufs, akv)
+        fused = self.fused_vocab and not want_logits
+        logits = None if fused else self._buf("logits", (R, self.ldv), torch.float32)
         cv = ci = None
         if audit is not None:
             cv, ci = audit
@@ -731,6 +740,45 @@ class CareEngine:
         if trace is not None:
             trace.append(dict(lengths=lengths.cpu().clone(), best=best.cpu().clone()))
         return out_tok, out_lp
+
+
+def ensemble_ar_decode(engines, encs, B, beam_size=5, topk=1, beam_alpha=1.0, bos=None):
+    """Beam search over the mean of the models' log-probabilities (reference: models/Translator.py:39-52,
+    111-133).  Every model keeps its own KV cache and cross K/V; the beam state (tokens, ancestry, scores)
+    is shared.  Logits are materialised per model (no fused vocabulary kernel on this path)."""
+    e0 = engines[0]
+    K = beam_size
+    need = max(K, topk)
+    lib = e0.lib
+    st = e0._stream()
+    for e in engines[1:]:
+        if (e.V, e.max_len, e.device) != (e0.V, e0.max_len, e0.device):
+            raise ValueError("ensembled models must share the vocabulary, max_len and device")
+    bos = BOS if bos is None else int(bos)
+    kvs = [e.cross_kv(enc["encoder_hidden_states"]) for e, enc in zip(engines, encs)]
+    akvs = [e.attr_kv(enc) for e, enc in zip(engines, encs)]
+    bufs, bst = e0._beam_buffers(B, K, need)
+    check(lib.care_beam_init(e0.ctx, ctypes.byref(bst), bos, st), "care_beam_init")
+    R = B * K
+    logits = [e._buf("ens_logits", (R, e.ldv), torch.float32) for e in engines]
+    mean_lp = e0._buf("ens_mean", (R, e0.ldv), torch.float32)
+    ptrs = (ctypes.c_void_p * len(engines))(*[ptr(x) for x in logits])
+    for t in range(1, e0.max_len):
+        for e, enc, kv, akv, lg in zip(engines, encs, kvs, akvs, logits):
+            x3 = e.step_hidden(t, B, K, enc, kv, bufs, akv)
+            e.gemm(x3, e.w["Wvocab"], None, lg, R, e.V, e.d)
+        check(lib.care_ensemble_logprobs(e0.ctx, ptrs, len(engines), e0.ldv, R, e0.V, ptr(mean_lp), st),
+              "care_ensemble_logprobs")
+        check(lib.care_beam_step_logprobs(e0.ctx, ctypes.byref(bst), ptr(mean_lp), e0.ldv, t, e0.max_len, None, None,
+                                          st), "care_beam_step_logprobs")
+    Tm = e0.max_len - 1
+    out_tok = torch.empty((B, topk, Tm), dtype=torch.int32, device=e0.device)
+    out_len = torch.empty((B, topk), dtype=torch.int32, device=e0.device)
+    out_score = torch.empty((B, topk), dtype=torch.float32, device=e0.device)
+    out_t = torch.empty((B, topk), dtype=torch.int32, device=e0.device)
+    check(lib.care_beam_finalize(e0.ctx, ctypes.byref(bst), float(beam_alpha), topk, ptr(out_tok), ptr(out_len),
+                                 ptr(out_score), ptr(out_t), st), "care_beam_finalize")
+    return out_tok, out_len, out_score, out_t
 
 
 def hyps_from_device(out_tok, out_len, out_score, out_t, beam_alpha, topk):

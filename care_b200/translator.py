@@ -6,7 +6,7 @@ on the device: beam state never visits the host until the final ids come back.
 """
 import torch
 
-from .engine import hyps_from_device
+from .engine import ensemble_ar_decode, hyps_from_device
 
 __all__ = ("Translator_ARFormer", "Translator_NARFormer", "get_translator")
 
@@ -22,7 +22,7 @@ def get_translator(opt: dict):
 def _single_model(models):
     if isinstance(models, (list, tuple)):
         if len(models) != 1:
-            raise NotImplementedError("model ensembling is outside the accelerated hot path (single model only)")
+            raise NotImplementedError("this entry point takes a single model (ensembles: Translator_ARFormer.translate_batch)")
         return models[0]
     return models
 
@@ -42,6 +42,8 @@ class Translator_ARFormer(object):
     pipeline_chunk = 2048
 
     def translate_batch(self, models, batch, *args, **kwargs):
+        if isinstance(models, (list, tuple)) and len(models) > 1:
+            return self._translate_ensemble(models, batch)
         model = _single_model(models)
         feats = batch["feats"]
         if feats[0].shape[0] == 0:
@@ -51,6 +53,20 @@ class Translator_ARFormer(object):
                 out = self.decode_pipelined(model, feats, self.pipeline_chunk)
             else:
                 out = self.decode_on_device(model, feats)
+        return hyps_from_device(*out, self.beam_alpha, self.topk)
+
+    def _translate_ensemble(self, models, batch):
+        """Model ensembling (reference: models/Translator.py:39-52,111-133): the beams follow the mean of the
+        models' log-probabilities.  `batch['feats']` may hold one feature list per model (ModelEnsemble)."""
+        feats = batch["feats"]
+        per_model = isinstance(feats[0], (list, tuple))
+        B = (feats[0][0] if per_model else feats[0]).shape[0]
+        if B == 0:
+            return [], []
+        with torch.no_grad():
+            encs = [m.encoding_phase(feats[i] if per_model else feats) for i, m in enumerate(models)]
+            out = ensemble_ar_decode([m.engine() for m in models], encs, B, beam_size=self.beam_size, topk=self.topk,
+                                     beam_alpha=self.beam_alpha, bos=self.ar_token_id)
         return hyps_from_device(*out, self.beam_alpha, self.topk)
 
     def translate_stream(self, models, batches, device_hook=None, **kwargs):

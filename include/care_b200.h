@@ -232,6 +232,15 @@ int care_beam_init(care_ctx* ctx, const care_beam_state* st, int bos, void* stre
 int care_beam_step(care_ctx* ctx, const care_beam_state* st, const float* logits, int64_t ldv,
                    int step, int max_len, float* cand_val, int32_t* cand_idx, void* stream);
 
+/* Model ensembling (Translator.py:111-133, predict_word): out[r, :] = mean over the n models of
+ * log_softmax(logits_i[r, :]).  `logits` is a HOST array of n <= 8 device pointers, each fp32 [R, ldv];
+ * out fp32 [R, ldv].  care_beam_step_logprobs is care_beam_step for rows that already hold log-probabilities
+ * (no second normalisation). */
+int care_ensemble_logprobs(care_ctx* ctx, const float* const* logits, int n, int64_t ldv, int R, int V,
+                           float* out, void* stream);
+int care_beam_step_logprobs(care_ctx* ctx, const care_beam_state* st, const float* logprobs, int64_t ldv,
+                            int step, int max_len, float* cand_val, int32_t* cand_idx, void* stream);
+
 /* Fused vocabulary projection + beam partials, bf16 only (Head.py:26-32 + Translator.py:127 + the
  * top-k half of Beam.py:45-60): the fp32 logits never reach HBM.  x bf16 [R, ldx] (decoder output of
  * the newest position), W bf16 [V, ldw] (cls_head.tgt_word_prj.weight).  Each row's vocabulary is

@@ -294,6 +294,41 @@ class VideoBeam:
         return [s for s, _, _ in self.finished], [(t, k) for _, t, k in self.finished]
 
 
+def _ar_translate_ensemble(sds, opt, feats):
+    K = opt.get("beam_size", 5)
+    alpha = opt.get("beam_alpha", 1.0)
+    n_best = opt.get("topk", 1)
+    max_len = opt.get("max_len", 30)
+    with torch.no_grad():
+        B = feats[0].shape[0]
+        all_inputs = []
+        for sd in sds:
+            enc = encoding_phase(sd, opt, feats)
+            all_inputs.append({k: repeat_rows(enc[k], K) for k in decoder_input_keys(opt)})
+        bos = opt.get("ar_token_id") if opt.get("ar_token_id") is not None else BOS
+        beams = [VideoBeam(K, max_len, n_best, bos=bos) for _ in range(B)]
+        active = list(range(B))
+        for t in range(1, max_len):
+            ids = torch.stack([beams[i].prefixes() for i in active]).view(-1, t)
+            lps = [torch.log_softmax(decoding_phase(sd, opt, ids, inp, last_time_step_logits=True), dim=1)
+                   for sd, inp in zip(sds, all_inputs)]
+            logp = torch.stack(lps, dim=0).mean(0).view(len(active), K, -1)      # Translator.py:131
+            still = [i for pos, i in enumerate(active) if not beams[i].advance(logp[pos])]
+            if not still:
+                break
+            pos_of = {i: p for p, i in enumerate(active)}
+            keep = torch.LongTensor([pos_of[i] for i in still])
+            all_inputs = [{k: _select_rows(v, keep, len(active), K) for k, v in inp.items()} for inp in all_inputs]
+            active = still
+    hyps, scores = [], []
+    for b in beams:
+        sc, tk = b.ranked(alpha)
+        n_best = min(n_best, len(sc))
+        scores.append(sc[:n_best])
+        hyps.append([b.backtrack(k, t) for t, k in tk[:n_best]])
+    return hyps, scores
+
+
 def _select_rows(x, keep, n_prev, k):
     # Translator.collect_active_part (models/Translator.py:191-209)
     rest = x.shape[1:]
@@ -303,7 +338,10 @@ def _select_rows(x, keep, n_prev, k):
 def ar_translate(sd, opt, feats, return_trace=False):
     """Translator_ARFormer.translate_batch (models/Translator.py:35-85) with beam_decode_step
     (:91-109), predict_word (:111-133), collect_active_* (:135-209) and
-    collect_hypothesis_and_scores (:211-220), single model."""
+    collect_hypothesis_and_scores (:211-220).  `sd` may be a list of state dicts: model ensembling,
+    the beams follow the mean of the models' log-probabilities (:39-52,127-131)."""
+    if isinstance(sd, (list, tuple)):
+        return _ar_translate_ensemble(list(sd), opt, feats)
     K = opt.get("beam_size", 5)
     alpha = opt.get("beam_alpha", 1.0)
     n_best = opt.get("topk", 1)

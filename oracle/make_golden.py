@@ -63,10 +63,41 @@ def run_case(name, cfg, over, bsz, wkw, feat_seed=11):
     return rec
 
 
+def run_ensemble_case(name, cfg, over, bsz, weight_list, feat_seed=11):
+    """Model ensembling through the reference's own Translator (models/Translator.py:39-52,111-133)."""
+    opt = make_opt(**{**CONFIGS[cfg], **over})
+    models = []
+    for wkw in weight_list:
+        m = rh.build_reference_model(opt)
+        m.load_state_dict(make_state_dict(opt, **wkw), strict=True)
+        models.append(m)
+    feats = make_feats(opt, bsz, seed=feat_seed)
+    _, get_translator, _ = rh.load_reference()
+    with torch.no_grad():
+        hyps, scores = get_translator(dict(opt)).translate_batch(models, {"feats": feats},
+                                                                 vocab={i: str(i) for i in range(opt["vocab_size"])})
+    return dict(name=name, config=cfg, overrides=over, batch=bsz, weights_list=weight_list, feat_seed=feat_seed,
+                hyps=hyps, scores=scores)
+
+
+ENSEMBLE_CASES = [
+    ("ens2_cfg2_sharp", "cfg2", {}, 6, [dict(seed=1, perturb=True, sharpen=SHARP), dict(seed=12, perturb=True, sharpen=SHARP)]),
+    ("ens3_cfg2_k3", "cfg2", dict(beam_size=3, topk=2), 5,
+     [dict(seed=13, perturb=True, sharpen=SHARP), dict(seed=14, perturb=True, sharpen=SHARP), dict(seed=15, perturb=True)]),
+]
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     assert rh.reference_available(), "needs /root/reference"
     only = set(sys.argv[1:])
+    for case in ENSEMBLE_CASES:
+        if only and case[0] not in only:
+            continue
+        rec = run_ensemble_case(*case)
+        with open(os.path.join(OUT, rec["name"] + ".json"), "w") as f:
+            json.dump(rec, f)
+        print(rec["name"], "lens", [len(h[0]) for h in rec["hyps"]])
     for case in CASES:
         if only and case[0] not in only:
             continue

@@ -10,7 +10,19 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-5] for p in glob.glob(os.path.join(GOLDEN, "cfg*.json")))
+    return sorted(os.path.basename(p)[:-5] for p in glob.glob(os.path.join(GOLDEN, "*.json"))
+                  if os.path.basename(p).startswith(("cfg", "cab")))
+
+
+def ensemble_golden_names():
+    return sorted(os.path.basename(p)[:-5] for p in glob.glob(os.path.join(GOLDEN, "ens*.json")))
+
+
+def rebuild_ensemble_case(rec):
+    opt = make_opt(**{**CONFIGS[rec["config"]], **rec["overrides"]})
+    sds = [make_state_dict(opt, **w) for w in rec["weights_list"]]
+    feats = make_feats(opt, rec["batch"], seed=rec["feat_seed"])
+    return opt, sds, feats
 
 
 def load_golden(name):

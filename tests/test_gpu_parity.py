@@ -440,3 +440,25 @@ def test_alternative_bos_token():
     for v in range(5):
         assert hyps[v] == o_h[v] or margins[v] < 1e-4
     assert hyps != [h for h in rec["hyps"][:5]]     # really started from another token
+
+
+@pytest.mark.parametrize("name", ["ens2_cfg2_sharp", "ens3_cfg2_k3"])
+def test_model_ensembling_matches_reference_golden(name):
+    """`translate_batch(models=[m1, m2, ...])`: beams follow the mean of the models' log-probabilities
+    (models/Translator.py:39-52,111-133); fp32 mode against the unmodified reference's output."""
+    import care_b200
+    from tests.helpers import rebuild_ensemble_case
+    rec = load_golden(name)
+    opt, sds, feats = rebuild_ensemble_case(rec)
+    models = [_gpu_model(opt, sd, "fp32") for sd in sds]
+    tr = care_b200.get_translator(opt)
+    hyps, scores = tr.translate_batch(models, {"feats": [f.cuda() for f in feats]})
+    exact = sum(int(a == b) for a, b in zip(hyps, rec["hyps"]))
+    assert exact == len(hyps), (hyps, rec["hyps"])
+    for a, b in zip(scores, rec["scores"]):
+        for x, y in zip(a, b):
+            assert abs(x - y) < 1e-4 * max(1.0, abs(y))
+    # bf16 engines: same driver, well-formed output
+    m16 = [_gpu_model(opt, sd, "bf16") for sd in sds]
+    h16, _ = tr.translate_batch(m16, {"feats": [f.cuda() for f in feats]})
+    assert len(h16) == len(hyps) and all(1 <= len(h[0]) <= opt["max_len"] - 1 for h in h16)
