@@ -786,14 +786,31 @@ def hyps_from_device(out_tok, out_len, out_score, out_t, beam_alpha, topk):
     scores are `float(score) / t ** alpha` in Python double precision (Beam.py:91-101), and the
     reference's n_best carry-over between videos (Translator.py:215) is reproduced."""
     tok = out_tok.cpu().tolist()
-    ln = out_len.cpu().tolist()
+    ln_t = out_len.cpu()
+    ln = ln_t.tolist()
     sc = out_score.cpu().tolist()
     tt = out_t.cpu().tolist()
+    # n_best[v] = min(topk, min over u <= v of the number of finished hypotheses of video u)
+    n_best = torch.cummin((ln_t > 0).sum(dim=1).clamp(max=topk), dim=0).values.tolist() if ln else []
+    if topk == 1 and (not n_best or n_best[-1] == 1):
+        hyps = [[t[0][:l[0]]] for t, l in zip(tok, ln)]
+        scores = [[s[0] / t[0] ** beam_alpha] for s, t in zip(sc, tt)]
+        return hyps, scores
     hyps, scores = [], []
+    for v, nb in enumerate(n_best):
+        hyps.append([tok[v][r][:ln[v][r]] for r in range(nb)])
+        scores.append([sc[v][r] / tt[v][r] ** beam_alpha for r in range(nb)])
+    return hyps, scores
+
+
+def carry_n_best(hyps, scores, topk):
+    """Re-applies the reference's running `n_best = min(n_best, finished hypotheses)` (Translator.py:215)
+    across lists that were built per chunk: a video with fewer than `topk` hypotheses truncates every
+    later video, also those of later chunks."""
     n_best = topk
-    for v in range(len(tok)):
-        avail = sum(1 for x in ln[v] if x > 0)
-        n_best = min(n_best, avail)
-        hyps.append([tok[v][r][:ln[v][r]] for r in range(n_best)])
-        scores.append([sc[v][r] / tt[v][r] ** beam_alpha for r in range(n_best)])
+    for v in range(len(hyps)):
+        if len(hyps[v]) < n_best:
+            n_best = len(hyps[v])
+        elif len(hyps[v]) > n_best:
+            hyps[v], scores[v] = hyps[v][:n_best], scores[v][:n_best]
     return hyps, scores

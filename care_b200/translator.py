@@ -6,7 +6,7 @@ on the device: beam state never visits the host until the final ids come back.
 """
 import torch
 
-from .engine import ensemble_ar_decode, hyps_from_device
+from .engine import carry_n_best, ensemble_ar_decode, hyps_from_device
 
 __all__ = ("Translator_ARFormer", "Translator_NARFormer", "get_translator")
 
@@ -50,10 +50,27 @@ class Translator_ARFormer(object):
             return [], []
         with torch.no_grad():
             if feats[0].device.type == "cpu" and feats[0].shape[0] > self.pipeline_chunk:
-                out = self.decode_pipelined(model, feats, self.pipeline_chunk)
-            else:
-                out = self.decode_on_device(model, feats)
+                return self._translate_chunked(model, feats, self.pipeline_chunk)
+            out = self.decode_on_device(model, feats)
         return hyps_from_device(*out, self.beam_alpha, self.topk)
+
+    def _translate_chunked(self, model, host_feats, chunk):
+        """One large host-resident batch as a stream of chunks: chunk i+1's host->device copy and chunk
+        i-1's read-back + list building overlap chunk i's decode.  Videos are independent, so the result
+        equals one big call; the reference's n_best carry-over (Translator.py:215) is re-applied across the
+        chunk boundaries."""
+        n_mod = len(model.engine().modality)
+        host_feats = list(host_feats[:n_mod])
+        B = host_feats[0].shape[0]
+        # a short first chunk keeps the one copy nothing can hide (the first) small
+        first = max(chunk // 4, 1)
+        bounds = [(0, first)] + [(a, min(a + chunk, B)) for a in range(first, B, chunk)]
+        chunks = ({"feats": [f[a:b] for f in host_feats]} for a, b in bounds)
+        hyps, scores = [], []
+        for h, s in self.translate_stream([model], chunks):
+            hyps += h
+            scores += s
+        return carry_n_best(hyps, scores, self.topk)
 
     def _translate_ensemble(self, models, batch):
         """Model ensembling (reference: models/Translator.py:39-52,111-133): the beams follow the mean of the
@@ -73,7 +90,8 @@ class Translator_ARFormer(object):
         """Throughput API for a stream of host-resident batches (the `for batch in loader` loop of
         translate.py:34-43): yields `(hyps, scores)` per batch, in order, with the same values as
         `translate_batch`.  While batch i decodes, the features of batch i+1 are copied host->device
-        on a side stream, and the ids of batch i-1 are read back and turned into Python lists.
+        on a side stream, and the ids of batch i-1 (read back to pinned host memory behind their own
+        decode) are turned into Python lists.
         `device_hook(out) -> out` (optional) runs on the device results before they are read back,
         e.g. the all-gather of care_b200.sharding for a video-sharded multi-GPU run."""
         model = _single_model(models)
@@ -83,6 +101,7 @@ class Translator_ARFormer(object):
         main = torch.cuda.current_stream(dev)
         side = eng.copy_stream()
         staging = [None, None]
+        landing = [None, None]      # pinned host copies of the results, two sets in flight
         freed = [torch.cuda.Event(), torch.cuda.Event()]
 
         def stage(i, batch):
@@ -91,9 +110,12 @@ class Translator_ARFormer(object):
                 return feats, None
             shapes = [tuple(f.shape) for f in feats]
             if staging[i % 2] is None or [tuple(t.shape) for t in staging[i % 2]] != shapes:
-                staging[i % 2] = [torch.empty(f.shape, dtype=f.dtype, device=dev) for f in feats]
+                # allocated in the copy stream's pool (a block recycled from the decode stream could still be
+                # read by an earlier decode when the copy starts) and marked as used by the decode stream
+                with torch.cuda.stream(side):
+                    staging[i % 2] = [torch.empty(f.shape, dtype=f.dtype, device=dev) for f in feats]
                 for t in staging[i % 2]:
-                    t.record_stream(side)
+                    t.record_stream(main)
             ev = torch.cuda.Event()
             with torch.cuda.stream(side):
                 if i >= 2:
@@ -123,12 +145,22 @@ class Translator_ARFormer(object):
                 freed[i % 2].record(main)
                 if device_hook is not None:
                     out = device_hook(out)
+                # the read-back of batch i is enqueued behind its decode and waited for one iteration
+                # later, so the host builds batch i-1's lists while the device decodes batch i
+                if landing[i % 2] is None or [tuple(t.shape) for t in landing[i % 2]] != [tuple(t.shape) for t in out]:
+                    landing[i % 2] = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in out]
+                for dst, src in zip(landing[i % 2], out):
+                    dst.copy_(src, non_blocking=True)
+                landed = torch.cuda.Event()
+                landed.record(main)
                 if pending is not None:
-                    yield hyps_from_device(*pending, self.beam_alpha, self.topk)
-                pending = out
+                    pending[1].synchronize()
+                    yield hyps_from_device(*pending[0], self.beam_alpha, self.topk)
+                pending = (landing[i % 2], landed)
                 i += 1
         if pending is not None:
-            yield hyps_from_device(*pending, self.beam_alpha, self.topk)
+            pending[1].synchronize()
+            yield hyps_from_device(*pending[0], self.beam_alpha, self.topk)
 
     def decode_pipelined(self, model, host_feats, chunk):
         """Chunked decode of a host-resident batch: chunk i+1's features are copied on a side stream into

@@ -303,6 +303,21 @@ def test_host_batches_chunked_and_streamed_match_single_call():
     assert list(tr.translate_stream([model], [])) == []
 
 
+def test_chunked_host_batch_nbest_and_pageable_memory():
+    """topk = 3 with a chunk size that splits the batch unevenly, from pageable (not pinned) host memory:
+    the chunked call equals the golden of the unmodified reference."""
+    import care_b200
+    rec = load_golden("cfg2_sharp_k3_nbest3_a07")
+    opt, sd, feats = rebuild_case(rec)
+    model = _gpu_model(opt, sd, "fp32")
+    tr = care_b200.get_translator(opt)
+    tr.pipeline_chunk = 7
+    h, s = tr.translate_batch([model], {"feats": [f.clone() for f in feats]})
+    assert h == rec["hyps"]
+    ref_h, ref_s = tr.translate_batch([model], {"feats": [f.cuda() for f in feats]})
+    assert h == ref_h and s == ref_s
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_cuda_graph_replay_matches_eager(precision):
     """Small batches replay the whole decode as one CUDA graph: first call (eager + capture), replays,

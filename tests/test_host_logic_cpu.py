@@ -5,7 +5,7 @@ import pytest
 import torch
 
 import care_b200
-from care_b200.engine import hyps_from_device
+from care_b200.engine import carry_n_best, hyps_from_device
 from oracle.shapes import CONFIGS, make_opt
 
 
@@ -44,6 +44,24 @@ def test_hyps_from_device_carries_n_best_over_like_the_reference():
     assert [len(h) for h in hyps] == [3, 1, 1]
     assert hyps[0][1] == [5, 6, 7] and hyps[2][0] == [24]
     assert scores[0][2] == pytest.approx(-3.0 / 4 ** 0.7)
+
+
+def test_chunked_lists_equal_one_call_after_carry_over():
+    g = torch.Generator().manual_seed(5)
+    for trial in range(20):
+        B, topk, T = 23, 3, 7
+        ln = torch.randint(0 if trial % 2 else 1, T, (B, topk), generator=g, dtype=torch.int32)
+        ln[:, 0].clamp_(min=1)
+        tok = torch.randint(4, 90, (B, topk, T), generator=g, dtype=torch.int32)
+        sc = -torch.rand(B, topk, generator=g)
+        tt = ln.clamp(min=1)
+        whole = hyps_from_device(tok, ln, sc, tt, 0.7, topk)
+        hyps, scores = [], []
+        for a in range(0, B, 5):
+            h, s = hyps_from_device(tok[a:a + 5], ln[a:a + 5], sc[a:a + 5], tt[a:a + 5], 0.7, topk)
+            hyps += h
+            scores += s
+        assert carry_n_best(hyps, scores, topk) == whole
 
 
 def test_registries_and_refusals():
