@@ -97,7 +97,7 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -438,13 +438,28 @@ def run_care_arm(args):
                                    for r in kernels[1:]],
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout."""
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
+_JSON_OUT = sys.stdout
+
+
 def main():
+    global _JSON_OUT
     args = parse()
+    # libraries that write to file descriptor 1 (NCCL prints its version banner there) must not end up in
+    # front of the JSON line: keep a private handle on the real stdout and point fd 1 at stderr
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
     else:
