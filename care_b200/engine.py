@@ -57,6 +57,11 @@ class CareEngine:
         # bf16: the vocabulary GEMM's epilogue feeds the beam kernel directly (no logits in HBM)
         self.fused_vocab = precision == "bf16" and bool(opt.get("care_fused_vocab", True))
         self._ws = {}
+        self._ws_epoch_of = {}
+        self._ws_bytes = 0
+        self._epoch = 0            # advanced once per encoded batch (encode())
+        limit = opt.get("care_workspace_limit_bytes")
+        self._ws_limit = int(limit) if limit is not None else torch.cuda.get_device_properties(index).total_memory // 2
         self._nseg = {}
         # launch-bound regime (few rows per step): replay the whole decode as one CUDA graph
         self.use_graphs = bool(opt.get("care_cuda_graph", True))
@@ -193,16 +198,39 @@ class CareEngine:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _buf(self, name, shape, dtype):
+        """Workspace keyed by (name, shape, dtype), kept across calls.  A service that sees many batch
+        sizes would otherwise accumulate one workspace set per size: once the sets exceed
+        `care_workspace_limit_bytes` (default: half of the device memory), the buffers the current
+        call has not touched are dropped (stream-ordered reuse makes that safe for launches in flight)."""
         key = (name, tuple(shape), dtype)
         t = self._ws.get(key)
         if t is None:
+            nbytes = torch.empty((), dtype=dtype).element_size()
+            for n in shape:
+                nbytes *= int(n)
+            if self._ws_bytes + nbytes > self._ws_limit:
+                self._evict_stale()
             t = torch.empty(shape, dtype=dtype, device=self.device)
             self._ws[key] = t
+            self._ws_bytes += nbytes
+        self._ws_epoch_of[key] = self._epoch
         return t
+
+    def _evict_stale(self):
+        stale = [k for k, e in self._ws_epoch_of.items() if e < self._epoch]
+        if not stale:
+            return
+        self._graphs.clear()   # graphs hold raw pointers into the workspaces
+        for k in stale:
+            t = self._ws.pop(k)
+            self._ws_bytes -= t.numel() * t.element_size()
+            del self._ws_epoch_of[k]
 
     def free_workspaces(self):
         self._graphs.clear()   # graphs hold raw pointers into the workspaces
         self._ws.clear()
+        self._ws_epoch_of.clear()
+        self._ws_bytes = 0
 
     def copy_stream(self):
         """Side stream for host->device feature copies that overlap the decode."""
@@ -227,6 +255,7 @@ class CareEngine:
         opt, d, T, w = self.opt, self.d, self.tdtype, self.w
         feats = feats[:len(self.modality)]
         B = feats[0].shape[0]
+        self._epoch += 1
         st = self._stream()
         lib, ctx, dt = self.lib, self.ctx, self.dt
         n_pred = len([c for c in self.modality if c in self.m_pred])
@@ -549,10 +578,14 @@ class CareEngine:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 body()
-            self._graphs[key] = (graph, n_launch)
+            # the workspaces the captured launches point into: kept fresh on every replay (see _buf)
+            used = [k for k, e in self._ws_epoch_of.items() if e == self._epoch]
+            self._graphs[key] = (graph, n_launch, used)
             self._graph_launches -= n_launch   # the capture pass went through the library's counter without running
             # the eager pass already produced this call's result
         else:
+            for k in entry[2]:
+                self._ws_epoch_of[k] = self._epoch
             entry[0].replay()
             self._graph_launches += entry[1]
         return tuple(o.clone() for o in outs)

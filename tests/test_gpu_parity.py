@@ -318,6 +318,28 @@ def test_chunked_host_batch_nbest_and_pageable_memory():
     assert h == ref_h and s == ref_s
 
 
+def test_workspace_limit_evicts_stale_sets_and_keeps_results():
+    """A tiny workspace budget: every new batch size drops the workspaces (and CUDA graphs) of the previous
+    sizes; results stay those of the reference and only the current call's buffers remain."""
+    import care_b200
+    rec = load_golden("cfg2_sharp")
+    opt, sd, feats = rebuild_case(rec)
+    model = _gpu_model(dict(opt, care_workspace_limit_bytes=1), sd, "fp32")
+    tr = care_b200.get_translator(opt)
+    dev = [f.cuda() for f in feats]
+    eng = model.engine()
+    for n in (12, 5, 12, 3, 3, 12, 5):
+        h, _ = tr.translate_batch([model], {"feats": [f[:n].contiguous() for f in dev]})
+        assert h == rec["hyps"][:n]
+        assert all(e == eng._epoch for e in eng._ws_epoch_of.values())
+        assert set(eng._ws) == set(eng._ws_epoch_of)
+        assert eng._ws_bytes == sum(t.numel() * t.element_size() for t in eng._ws.values())
+    roomy = _gpu_model(opt, sd, "fp32")
+    for n in (12, 5):
+        tr.translate_batch([roomy], {"feats": [f[:n].contiguous() for f in dev]})
+    assert len({k[1] for k in roomy.engine()._ws if k[0] == "bs_scores"}) == 2   # both sizes stay resident
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_cuda_graph_replay_matches_eager(precision):
     """Small batches replay the whole decode as one CUDA graph: first call (eager + capture), replays,
