@@ -38,7 +38,8 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=16, help="videos per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--self-compact", action="store_true", help="opt-in slot-compacting self-attention kernel")
+    ap.add_argument("--self-compact", type=int, default=0, choices=(0, 1, 2),
+                    help="self-attention over live cache slots only: 1 = per-CTA gather, 2 = gathered chunk stream")
     ap.add_argument("--no-latency", action="store_true", help="skip the small-batch latency section (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-fed e2e section (profiling runs)")
     return ap.parse_args()

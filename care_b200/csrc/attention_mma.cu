@@ -309,7 +309,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 
 // Per-video record consumed by attn_self_compact_kernel, built once per step instead of once per head:
 //   word 0: n_live;  words 1..64: key masks [8 beams][8 words] in the compacted index space;
-//   words 65..: uint16 rowsrc[row] = position * K + slot of the cache row gathered into tile row `row`.
+//   words 65..: uint16 rowsrc[row] = (position << 4) | slot of the cache row gathered into tile row `row`.
 constexpr int INFO_WORDS = 160;   // 1 + 64 + 80 (160 uint16) padded: 640 B per video
 
 __global__ void __launch_bounds__(128)
@@ -347,7 +347,7 @@ compact_info_kernel(const uint8_t* __restrict__ anc, int anc_stride, const int32
     const int off = carry + incl - cnt;
     if (pp < n_pos) {
       for (int sl = 0; sl < K; ++sl)
-        if ((bits >> sl) & 1u) rowsrc[off + __popc(bits & ((1u << sl) - 1u))] = (uint16_t)(pp * K + sl);
+        if ((bits >> sl) & 1u) rowsrc[off + __popc(bits & ((1u << sl) - 1u))] = (uint16_t)((pp << 4) | sl);
       for (int b = 0; b < K; ++b) {
         const uint32_t slot = (slots >> (4 * b)) & 15u;
         const int tok = tok_hist[(int64_t)v * tok_stride + pp * K + slot];
@@ -388,7 +388,7 @@ attn_self_compact_kernel(const Params p, const __nv_bfloat16* __restrict__ cache
   uint8_t* sa = aux_gen + 16 + 256 + 256 + WARPS * 8 * COMB_LD * 4;          // [8][MAX_POS] slot of (beam, pos)
   uint8_t* live = sa + 8 * MAX_POS;                                           // [MAX_POS] slot bitmask per position
   uint16_t* off = reinterpret_cast<uint16_t*>(live + MAX_POS);                // [MAX_POS + 1] first row of a position
-  uint16_t* rowsrc = off + MAX_POS + 2;                                       // [rows] cache row (pos * K + slot)
+  uint16_t* rowsrc = off + MAX_POS + 2;                                       // [rows] cache row (pos << 4 | slot)
   __shared__ int n_live_s;
 
   // Q fragments first: their latency overlaps the ancestry bookkeeping
@@ -447,7 +447,7 @@ attn_self_compact_kernel(const Params p, const __nv_bfloat16* __restrict__ cache
     for (int i = threadIdx.x; i < K * n_pos; i += 128) {
       const int s = i / n_pos, pp = i - s * n_pos;        // here: candidate slot s of position pp
       const uint32_t bits = live[pp];
-      if ((bits >> s) & 1u) rowsrc[off[pp] + __popc(bits & ((1u << s) - 1u))] = (uint16_t)(pp * K + s);
+      if ((bits >> s) & 1u) rowsrc[off[pp] + __popc(bits & ((1u << s) - 1u))] = (uint16_t)((pp << 4) | s);
       // beam b == s of this loop index: its key at position pp
       const int b = s;
       const int slot = sa[b * MAX_POS + pp];
@@ -467,7 +467,7 @@ attn_self_compact_kernel(const Params p, const __nv_bfloat16* __restrict__ cache
     for (int c = threadIdx.x; c < n_chunks; c += 128) {
       const int j = c >> 4, isv = (c >> 3) & 1, c16 = c & 7;
       const int src = rowsrc[j];
-      const int pp = src / K, sl = src - pp * K;
+      const int pp = src >> 4, sl = src & 15;
       const int64_t roff = ((int64_t)pp * R + sl) * (3LL * p.d) + c16 * 8;
       cp_async16((isv ? v_s : k_s) + sw128(j, c16), (isv ? vbase : kbase) + roff);
     }
@@ -504,6 +504,320 @@ static int launch_compact(care_ctx* ctx, const Params& p, const void* cache, int
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Self-attention as a stream of gathered key chunks (option self_compact = 2).
+//
+// The compacting kernel above keeps the one-CTA-per-(video, head) shape: shared memory is sized for the
+// worst case (every slot live), so halving the bytes per CTA halves the bytes in flight per SM, and the
+// per-video record adds a dependent read to every CTA's latency chain - it measured slower than the dense
+// TMA kernel.  Here every WARP walks its own strided list of (video, head) items and consumes their live
+// K/V rows as fixed 16-row chunks out of a private ring of stages:
+//   * rows are fetched by TMA row gathers (cp.async.bulk.tensor.2d.tile::gather4: four arbitrary rows of the
+//     [T*R, 3d] cache per instruction, 128 B each, SWIZZLE_128B), issued up to STAGES chunks ahead and
+//     across the boundary to the next item, whose record is prefetched two items ahead - bytes in flight
+//     no longer depend on the worst-case tile;
+//   * softmax is computed online across the chunks of an item (running max / sum / O in registers), so one
+//     warp owns an item end to end: no block barriers, no merge buffer; 16 such warps per SM hide each
+//     other's instruction latency.
+// MMA fragments, masks and the hi+lo split of P are those of attend() above.
+// ---------------------------------------------------------------------------------------------
+namespace gs {
+
+constexpr int CH = 16;                       // rows per chunk (one MMA k-step)
+constexpr int SLOTS = 3;                     // resident records: current item, next, the one after
+constexpr int WARPS = 4;                     // independent warps per CTA
+constexpr uint32_t CHUNK_BYTES = CH * 128;   // one K (or V) chunk
+constexpr uint32_t REC_BYTES = INFO_WORDS * 4;
+
+template <int STAGES>
+struct Cfg {
+  static constexpr uint32_t RING = STAGES * 2 * CHUNK_BYTES;
+  static constexpr uint32_t WARP_BYTES = (RING + SLOTS * REC_BYTES + 8 * (STAGES + SLOTS) + 1023u) & ~1023u;
+  static constexpr uint32_t SMEM_BYTES = WARPS * WARP_BYTES + 1024;
+};
+
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, uint32_t bar, int col, int r0, int r1,
+                                            int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(WARPS * 32, 4)
+attn_self_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Params p, int R, const uint32_t* __restrict__ info,
+                        unsigned long long* __restrict__ row_counter, const EarlyExit ee) {
+  if (all_done(ee)) return;
+  extern __shared__ uint8_t smem_raw[];
+  using C = Cfg<STAGES>;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int K = p.K, H = p.H;
+  const int stride = gridDim.x * WARPS;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = ((raw + 1023u) & ~1023u) + warp * C::WARP_BYTES;   // this warp's private region
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t kv_s = base;                                   // stage s: K chunk, then V chunk
+  const uint32_t rec_s = base + C::RING;                        // SLOTS records
+  const uint32_t bar_kv = rec_s + SLOTS * REC_BYTES;            // STAGES barriers
+  const uint32_t bar_item = bar_kv + 8 * STAGES;                // SLOTS barriers
+  const uint32_t* rec_gen = reinterpret_cast<const uint32_t*>(gen + C::RING);
+
+  auto next_valid = [&](int n) {
+    while (n < p.n_items && p.done != nullptr && p.done[n / H]) n += stride;
+    return n;
+  };
+  int it = next_valid(blockIdx.x * WARPS + warp);
+  if (it >= p.n_items) return;
+
+  // V rows behind the last gathered group are multiplied by P == 0: every stage starts out finite
+  for (uint32_t i = lane; i < C::RING / 16; i += 32)
+    *reinterpret_cast<uint4*>(gen + (size_t)i * 16) = make_uint4(0u, 0u, 0u, 0u);
+  if (lane == 0) {
+    for (int i = 0; i < STAGES + SLOTS; ++i) mbar_init(bar_kv + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zero fill precedes the TMA writes
+  __syncwarp();
+
+  const int g = lane >> 2, tig = lane & 3, m = lane >> 3, rr = lane & 7;
+  auto prefetch_record = [&](int item, int slot) {
+    if (lane == 0) {
+      const uint32_t bar = bar_item + 8 * slot;
+      mbar_expect_tx(bar, REC_BYTES);
+      bulk_load(rec_s + slot * REC_BYTES, info + (int64_t)(item / H) * INFO_WORDS, REC_BYTES, bar);
+    }
+  };
+  // q fragments of beam g for (video, head) `item`, straight from the cache rows of the newest position
+  auto load_q = [&](int item, uint32_t (&qa)[4][2]) {
+    const int v = item / H, h = item - v * H;
+    const uint32_t* qrow = reinterpret_cast<const uint32_t*>(
+        p.q + (int64_t)(v * K + (g < K ? g : 0)) * p.q_ld + h * DH);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      qa[ks][0] = g < K ? __ldg(qrow + 8 * ks + tig) : 0u;
+      qa[ks][1] = g < K ? __ldg(qrow + 8 * ks + tig + 4) : 0u;
+    }
+  };
+  // chunk c of `item` (its record sits in `slot`) into ring stage `stage`: lane gq gathers rows 4gq .. 4gq+3
+  auto issue_chunk = [&](int item, int slot, int c, int stage) {
+    const int v = item / H, h = item - v * H;
+    const uint32_t* rec = rec_gen + slot * INFO_WORDS;
+    const int n_live = (int)rec[0];
+    const int groups = (min(CH, n_live - c * CH) + 3) >> 2;
+    const uint16_t* rowsrc = reinterpret_cast<const uint16_t*>(rec + 65);
+    const int src = rowsrc[min(c * CH + (lane & 15), n_live - 1)];
+    const int row = (src >> 4) * R + v * K + (src & 15);
+    const int r0 = __shfl_sync(0xffffffffu, row, (lane & 3) * 4), r1 = __shfl_sync(0xffffffffu, row, (lane & 3) * 4 + 1);
+    const int r2 = __shfl_sync(0xffffffffu, row, (lane & 3) * 4 + 2), r3 = __shfl_sync(0xffffffffu, row, (lane & 3) * 4 + 3);
+    const uint32_t bar = bar_kv + 8 * stage;
+    const uint32_t k_dst = kv_s + stage * 2 * CHUNK_BYTES, v_dst = k_dst + CHUNK_BYTES;
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)groups * 1024u);
+    __syncwarp();
+    if (lane < groups) {
+      tma_gather4(k_dst + lane * 512, &tmap, bar, p.k_col + h * DH, r0, r1, r2, r3);
+      tma_gather4(v_dst + lane * 512, &tmap, bar, p.v_col + h * DH, r0, r1, r2, r3);
+    }
+  };
+
+  uint32_t item_seq = 0, issued = 0, consumed = 0;
+  bool p_on_next = false;   // the producer has moved on to the next item
+  int p_chunk = 0;          // next chunk the producer issues (of the current or of the next item)
+  int nc_next = 0;
+  prefetch_record(it, 0);
+  int nxt = next_valid(it + stride);
+  if (nxt < p.n_items) prefetch_record(nxt, 1);
+  uint32_t qa[4][2], qn[4][2];
+  load_q(it, qa);
+
+  while (true) {
+    const int slot = item_seq % SLOTS, slot1 = (item_seq + 1) % SLOTS;
+    const bool has_next = nxt < p.n_items;
+    // the record of the item after next is requested a whole item ahead of the producer needing it
+    const int nxt2 = has_next ? next_valid(nxt + stride) : p.n_items;
+    if (nxt2 < p.n_items) prefetch_record(nxt2, (item_seq + 2) % SLOTS);
+    if (has_next) load_q(nxt, qn);
+    mbar_wait(bar_item + 8 * slot, (item_seq / SLOTS) & 1);
+    const uint32_t* rec = rec_gen + slot * INFO_WORDS;
+    const int n_live = (int)rec[0];
+    const int nc = (n_live + CH - 1) / CH;
+    const int v = it / H, h = it - v * H;
+    if (lane == 0 && h == 0 && row_counter != nullptr) atomicAdd(row_counter, (unsigned long long)n_live);
+
+    auto issue_more = [&]() {
+      while (issued - consumed < (uint32_t)STAGES) {
+        if (!p_on_next) {
+          if (p_chunk < nc) {
+            issue_chunk(it, slot, p_chunk, issued % STAGES);
+            ++issued;
+            ++p_chunk;
+            continue;
+          }
+          if (!has_next) break;
+          mbar_wait(bar_item + 8 * slot1, ((item_seq + 1) / SLOTS) & 1);
+          p_on_next = true;
+          p_chunk = 0;
+          nc_next = ((int)rec_gen[slot1 * INFO_WORDS] + CH - 1) / CH;
+        }
+        if (p_chunk >= nc_next) break;
+        issue_chunk(nxt, slot1, p_chunk, issued % STAGES);
+        ++issued;
+        ++p_chunk;
+      }
+    };
+    issue_more();
+
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[8][4];
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[dn][e] = 0.f;
+
+    for (int c = 0; c < nc; ++c) {
+      const int stage = consumed % STAGES;
+      const uint32_t k_s = kv_s + stage * 2 * CHUNK_BYTES, v_s = k_s + CHUNK_BYTES;
+      mbar_wait(bar_kv + 8 * stage, (consumed / STAGES) & 1);
+      // ---- S = Q K^T over the chunk's 16 keys ----
+      float s[2][2];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float cc[4] = {0.f, 0.f, 0.f, 0.f};
+        const int r = half * 8 + rr;
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+          uint32_t b[4];
+          ldsm_x4(b, k_s + sw128(r, 4 * kp + m));
+          mma_bf16(cc, qa[2 * kp][0], qa[2 * kp][1], b[0], b[1]);
+          mma_bf16(cc, qa[2 * kp + 1][0], qa[2 * kp + 1][1], b[2], b[3]);
+        }
+        s[half][0] = cc[0];
+        s[half][1] = cc[1];
+      }
+      // ---- mask (bit j of beam g: compacted key j is on g's prefix and not <pad>), online softmax ----
+      const uint32_t bits = rec[1 + (g & 7) * 8 + (c >> 1)] >> ((c & 1) * 16);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int jl = half * 8 + 2 * tig + e;
+          const float x = ((bits >> jl) & 1u) ? s[half][e] * 0.125f : -INFINITY;
+          s[half][e] = x;
+          mx = fmaxf(mx, x);
+        }
+      }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float m_new = fmaxf(m_run, mx);
+      const float mref = m_new == -INFINITY ? 0.f : m_new;
+      const float scale = __expf(m_run - mref);   // 0 for the first chunk with a visible key
+      const float p0 = __expf(s[0][0] - mref), p1 = __expf(s[0][1] - mref);
+      const float p2 = __expf(s[1][0] - mref), p3 = __expf(s[1][1] - mref);
+      float sum = (p0 + p1) + (p2 + p3);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      l_run = l_run * scale + sum;
+      m_run = m_new;
+#pragma unroll
+      for (int dn = 0; dn < 8; ++dn) {
+        o[dn][0] *= scale;
+        o[dn][1] *= scale;
+      }
+      // ---- O += P V ----
+      {
+        const uint32_t a0h = pack_bf16(p0, p1), a2h = pack_bf16(p2, p3);
+        const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&a0h);
+        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&a2h);
+        const uint32_t a0l = pack_bf16(p0 - __low2float(h0), p1 - __high2float(h0));
+        const uint32_t a2l = pack_bf16(p2 - __low2float(h2), p3 - __high2float(h2));
+        const int r = 8 * (m & 1) + rr;
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t b[4];
+          ldsm_x4_trans(b, v_s + sw128(r, 2 * dp + (m >> 1)));
+          mma_bf16(o[2 * dp], a0h, a2h, b[0], b[1]);
+          mma_bf16(o[2 * dp], a0l, a2l, b[0], b[1]);
+          mma_bf16(o[2 * dp + 1], a0h, a2h, b[2], b[3]);
+          mma_bf16(o[2 * dp + 1], a0l, a2l, b[2], b[3]);
+        }
+      }
+      ++consumed;
+      __syncwarp();   // every lane is done with the stage before it is refilled
+      issue_more();
+    }
+    if (g < K) {
+      const float inv = 1.0f / l_run;
+      __nv_bfloat16* orow = p.out + (int64_t)(v * K + g) * p.d + h * DH + 2 * tig;
+#pragma unroll
+      for (int dn = 0; dn < 8; ++dn)
+        *reinterpret_cast<__nv_bfloat162*>(orow + 8 * dn) = __floats2bfloat162_rn(o[dn][0] * inv, o[dn][1] * inv);
+    }
+    if (!has_next) break;
+    __syncwarp();   // the record slot of this item is free for the item three ahead
+    ++item_seq;
+    it = nxt;
+    nxt = nxt2;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      qa[ks][0] = qn[ks][0];
+      qa[ks][1] = qn[ks][1];
+    }
+    if (p_on_next) {
+      p_on_next = false;   // the chunks issued ahead now belong to the current item
+    } else {
+      p_chunk = 0;
+    }
+  }
+}
+
+template <int STAGES>
+static int launch_stream_t(care_ctx* ctx, const CUtensorMap& tmap, const Params& p, int64_t R, cudaStream_t stream) {
+  auto kern = attn_self_stream_kernel<STAGES>;
+  static int ctas_per_sm_all[64] = {0};   // per device
+  int& ctas_per_sm = ctas_per_sm_all[ctx->device & 63];
+  if (ctas_per_sm == 0) {
+    CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<STAGES>::SMEM_BYTES));
+    int n = 0;
+    CARE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, WARPS * 32, Cfg<STAGES>::SMEM_BYTES));
+    ctas_per_sm = std::max(n, 1);
+  }
+  const int grid = std::min((p.n_items + WARPS - 1) / WARPS, ctx->sm_count * ctas_per_sm);
+  kern<<<grid, WARPS * 32, Cfg<STAGES>::SMEM_BYTES, stream>>>(tmap, p, (int)R, ctx->compact_info, ctx->self_attn_rows,
+                                                              early_exit_of(ctx));
+  CARE_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+static int launch_stream(care_ctx* ctx, const Params& p, const void* cache, int64_t R, int T_rows, cudaStream_t stream) {
+  const int B = p.n_items / p.H;
+  CUtensorMap tmap;
+  const uint64_t gdim[2] = {(uint64_t)3 * p.d, (uint64_t)T_rows * (uint64_t)R};
+  const uint64_t gstr[1] = {(uint64_t)3 * p.d * 2};
+  const uint32_t box[2] = {(uint32_t)DH, 1u};
+  int rc = get_tmap_bf16(ctx, cache, 2, gdim, gstr, box, &tmap);
+  if (rc) return rc;
+  compact_info_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p.anc, p.anc_stride, p.tok_hist, p.tok_stride, p.done, B, p.K,
+                                                       p.n_pos, ctx->compact_info);
+  CARE_LAUNCH_CHECK(ctx);
+  static const int stages = [] {
+    const char* e = getenv("CARE_B200_STREAM_STAGES");
+    return e != nullptr ? atoi(e) : 2;
+  }();
+  if (stages == 3) return launch_stream_t<3>(ctx, tmap, p, R, stream);
+  if (stages == 4) return launch_stream_t<4>(ctx, tmap, p, R, stream);
+  return launch_stream_t<2>(ctx, tmap, p, R, stream);
+}
+
+}  // namespace gs
 
 // returns 1 if the shape is not covered (caller falls back to the SIMT kernel), 0 on launch, else error
 int cross_step(care_ctx* ctx, const void* q, int64_t ldq, const void* kv, int Lm, int B, int K, int H, int d,
@@ -563,7 +877,11 @@ int self_step(care_ctx* ctx, const void* cache, int n_pos, int B, int K, int H, 
   p.done = done;
   p.out = static_cast<__nv_bfloat16*>(ctx_out);
   p.n_items = B * H;
-  if (ctx->self_compact && n_pos >= 8 && n_pos <= MAX_POS) {
+  // short prefixes: nearly every slot is still live and the dense TMA tile is cheaper than the per-item bookkeeping
+  if (ctx->self_compact == 2 && n_pos >= 6 && ctx->compact_info != nullptr && B <= ctx->compact_info_videos &&
+      (int64_t)anc_stride * R < (1LL << 31))
+    return gs::launch_stream(ctx, p, cache, R, anc_stride, stream);   // rows of the cache as a 2D [T * R, 3d] tensor
+  if (ctx->self_compact == 1 && n_pos >= 8 && n_pos <= MAX_POS) {
     // long enough prefixes: gather only the cache slots some beam still references
     if (n_keys <= 128) return launch_compact<2>(ctx, p, cache, R, stream);
     return launch_compact<3>(ctx, p, cache, R, stream);

@@ -43,7 +43,8 @@ class CareEngine:
         check(self.lib.care_ctx_create(ctypes.byref(handle), index), "care_ctx_create")
         self.ctx = handle
         if opt.get("care_self_compact"):
-            check(self.lib.care_ctx_set_option(self.ctx, b"self_compact", 1), "care_ctx_set_option")
+            check(self.lib.care_ctx_set_option(self.ctx, b"self_compact", int(opt["care_self_compact"])),
+                  "care_ctx_set_option")
         self.d = opt["dim_hidden"]
         self.H = opt["num_attention_heads"]
         self.F = opt["intermediate_size"]

@@ -1,5 +1,5 @@
 """Per-kernel timing at the cfg4 shapes (CUDA events, L2 flushed by working sets >> 126 MB).
-Usage: python scripts/bench_kernels.py [attn] [beam] [gemm]   (runs on the GPU box)"""
+Usage: python scripts/bench_kernels.py [attn] [selfc] [beam] [gemm]   (runs on the GPU box)"""
 import ctypes
 import json
 import os
@@ -67,6 +67,32 @@ def main():
                 nbytes = R * n_pos * 2 * d * 2 + 2 * R * d * 2
                 print("self attn n_pos=%2d impl=%d: %.3f ms  %.0f GB/s (%.1f%%)" % (
                     n_pos, impl, ms, nbytes / ms / 1e6, 100 * nbytes / ms / 1e6 / PEAK))
+        del cache
+    if "selfc" in what:
+        # self-attention over live slots only, with an ancestry table from simulated beam parents
+        # (uniform parent choice: ~2.6 of 5 slots per position stay referenced, like the benchmark weights)
+        cache = torch.randn(Tm, R, 3 * d, device="cuda").bfloat16()
+        tok = torch.randint(4, 100, (B, Tm + 1, K), device="cuda", dtype=torch.int32)
+        done = torch.zeros(B, device="cuda", dtype=torch.int32)
+        out = torch.zeros(R, d, device="cuda", dtype=torch.bfloat16)
+        g = torch.Generator().manual_seed(0)
+        for n_pos in (4, 8, 15, 22, 29):
+            anc = torch.zeros(B, K, Tm, dtype=torch.int64)
+            for t in range(1, n_pos):      # beam b at step t continues beam parent[b] of step t - 1
+                parent = torch.randint(0, K, (B, K), generator=g)
+                anc[:, :, :t - 1] = torch.gather(anc[:, :, :t - 1], 1, parent[:, :, None].expand(B, K, t - 1))
+                anc[:, :, t - 1] = parent
+            live = sum(len(set(anc[v, :, pp].tolist())) for v in range(64) for pp in range(n_pos - 1)) / 64.0 + K
+            d_anc = anc.to(torch.uint8).cuda()
+            for compact in (0, 1, 2):
+                lib.care_ctx_set_option(h, b"self_compact", compact)
+                ms = timed(lambda: _lib.check(lib.care_self_attn_step(
+                    h, BF16, cache.data_ptr(), n_pos, B, K, H, d, d_anc.data_ptr(), Tm, tok.data_ptr(),
+                    done.data_ptr(), out.data_ptr(), st), "s"))
+                dense = R * n_pos * 2 * d * 2 + 2 * R * d * 2
+                print("self attn n_pos=%2d live rows %.1f of %d, compact=%d: %.3f ms  (dense bytes at %.0f GB/s)" % (
+                    n_pos, live, n_pos * K, compact, ms, dense / ms / 1e6))
+            lib.care_ctx_set_option(h, b"self_compact", 0)
         del cache
     if "gemm" in what:
       for two in (0, 1, 2):
