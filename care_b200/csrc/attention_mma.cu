@@ -571,12 +571,37 @@ attn_self_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
   const uint32_t bar_item = bar_kv + 8 * STAGES;                // SLOTS barriers
   const uint32_t* rec_gen = reinterpret_cast<const uint32_t*>(gen + C::RING);
 
-  auto next_valid = [&](int n) {
-    while (n < p.n_items && p.done != nullptr && p.done[n / H]) n += stride;
-    return n;
+  // items of this warp: id, id + stride, ... ; (video, head) advance without divisions
+  struct Item {
+    int id, v, h;
   };
-  int it = next_valid(blockIdx.x * WARPS + warp);
-  if (it >= p.n_items) return;
+  const int dv = stride / H, dh = stride - dv * H;
+  auto skip_done = [&](Item& x) {
+    while (x.id < p.n_items && p.done != nullptr && p.done[x.v]) {
+      x.id += stride;
+      x.v += dv;
+      x.h += dh;
+      if (x.h >= H) {
+        x.h -= H;
+        ++x.v;
+      }
+    }
+  };
+  auto following = [&](const Item& x) {
+    Item y{x.id + stride, x.v + dv, x.h + dh};
+    if (y.h >= H) {
+      y.h -= H;
+      ++y.v;
+    }
+    skip_done(y);
+    return y;
+  };
+  Item it;
+  it.id = blockIdx.x * WARPS + warp;
+  it.v = it.id / H;
+  it.h = it.id - it.v * H;
+  skip_done(it);
+  if (it.id >= p.n_items) return;
 
   // V rows behind the last gathered group are multiplied by P == 0: every stage starts out finite
   for (uint32_t i = lane; i < C::RING / 16; i += 32)
@@ -589,42 +614,44 @@ attn_self_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
   __syncwarp();
 
   const int g = lane >> 2, tig = lane & 3, m = lane >> 3, rr = lane & 7;
-  auto prefetch_record = [&](int item, int slot) {
+  // ldmatrix addresses inside a chunk (SWIZZLE_128B): K row (half * 8 + rr), 16-byte column (4 kp + m);
+  // V row (8 (m & 1) + rr), column (2 dp + (m >> 1)).  kp / half / dp only flip address bits.
+  const uint32_t k_lane = (uint32_t)(rr * 128 + ((m ^ rr) << 4));
+  const uint32_t v_lane = (uint32_t)((8 * (m & 1) + rr) * 128 + (((m >> 1) ^ rr) << 4));
+  auto prefetch_record = [&](const Item& x, int slot) {
     if (lane == 0) {
       const uint32_t bar = bar_item + 8 * slot;
       mbar_expect_tx(bar, REC_BYTES);
-      bulk_load(rec_s + slot * REC_BYTES, info + (int64_t)(item / H) * INFO_WORDS, REC_BYTES, bar);
+      bulk_load(rec_s + slot * REC_BYTES, info + (int64_t)x.v * INFO_WORDS, REC_BYTES, bar);
     }
   };
-  // q fragments of beam g for (video, head) `item`, straight from the cache rows of the newest position
-  auto load_q = [&](int item, uint32_t (&qa)[4][2]) {
-    const int v = item / H, h = item - v * H;
-    const uint32_t* qrow = reinterpret_cast<const uint32_t*>(
-        p.q + (int64_t)(v * K + (g < K ? g : 0)) * p.q_ld + h * DH);
+  // q fragments of beam g for the item, straight from the cache rows of the newest position
+  auto load_q = [&](const Item& x, uint32_t (&qf)[4][2]) {
+    const uint32_t* qrow =
+        reinterpret_cast<const uint32_t*>(p.q + (int64_t)(x.v * K + (g < K ? g : 0)) * p.q_ld + x.h * DH) + tig;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      qa[ks][0] = g < K ? __ldg(qrow + 8 * ks + tig) : 0u;
-      qa[ks][1] = g < K ? __ldg(qrow + 8 * ks + tig + 4) : 0u;
+      qf[ks][0] = g < K ? __ldg(qrow + 8 * ks) : 0u;
+      qf[ks][1] = g < K ? __ldg(qrow + 8 * ks + 4) : 0u;
     }
   };
-  // chunk c of `item` (its record sits in `slot`) into ring stage `stage`: lane gq gathers rows 4gq .. 4gq+3
-  auto issue_chunk = [&](int item, int slot, int c, int stage) {
-    const int v = item / H, h = item - v * H;
+  // chunk c of the item (its record sits in `slot`) into ring stage `stage`: lane gq gathers rows 4gq .. 4gq+3
+  auto issue_chunk = [&](const Item& x, int slot, int c, int stage) {
     const uint32_t* rec = rec_gen + slot * INFO_WORDS;
     const int n_live = (int)rec[0];
     const int groups = (min(CH, n_live - c * CH) + 3) >> 2;
     const uint16_t* rowsrc = reinterpret_cast<const uint16_t*>(rec + 65);
     const int src = rowsrc[min(c * CH + (lane & 15), n_live - 1)];
-    const int row = (src >> 4) * R + v * K + (src & 15);
-    const int r0 = __shfl_sync(0xffffffffu, row, (lane & 3) * 4), r1 = __shfl_sync(0xffffffffu, row, (lane & 3) * 4 + 1);
-    const int r2 = __shfl_sync(0xffffffffu, row, (lane & 3) * 4 + 2), r3 = __shfl_sync(0xffffffffu, row, (lane & 3) * 4 + 3);
+    const int row = (src >> 4) * R + x.v * K + (src & 15);
+    const int r0 = __shfl_sync(0xffffffffu, row, tig * 4), r1 = __shfl_sync(0xffffffffu, row, tig * 4 + 1);
+    const int r2 = __shfl_sync(0xffffffffu, row, tig * 4 + 2), r3 = __shfl_sync(0xffffffffu, row, tig * 4 + 3);
     const uint32_t bar = bar_kv + 8 * stage;
-    const uint32_t k_dst = kv_s + stage * 2 * CHUNK_BYTES, v_dst = k_dst + CHUNK_BYTES;
+    const uint32_t k_dst = kv_s + stage * 2 * CHUNK_BYTES + lane * 512;
     if (lane == 0) mbar_expect_tx(bar, (uint32_t)groups * 1024u);
     __syncwarp();
     if (lane < groups) {
-      tma_gather4(k_dst + lane * 512, &tmap, bar, p.k_col + h * DH, r0, r1, r2, r3);
-      tma_gather4(v_dst + lane * 512, &tmap, bar, p.v_col + h * DH, r0, r1, r2, r3);
+      tma_gather4(k_dst, &tmap, bar, p.k_col + x.h * DH, r0, r1, r2, r3);
+      tma_gather4(k_dst + CHUNK_BYTES, &tmap, bar, p.v_col + x.h * DH, r0, r1, r2, r3);
     }
   };
 
@@ -633,24 +660,26 @@ attn_self_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
   int p_chunk = 0;          // next chunk the producer issues (of the current or of the next item)
   int nc_next = 0;
   prefetch_record(it, 0);
-  int nxt = next_valid(it + stride);
-  if (nxt < p.n_items) prefetch_record(nxt, 1);
+  Item nxt = following(it);
+  if (nxt.id < p.n_items) prefetch_record(nxt, 1);
   uint32_t qa[4][2], qn[4][2];
   load_q(it, qa);
 
   while (true) {
     const int slot = item_seq % SLOTS, slot1 = (item_seq + 1) % SLOTS;
-    const bool has_next = nxt < p.n_items;
+    const bool has_next = nxt.id < p.n_items;
     // the record of the item after next is requested a whole item ahead of the producer needing it
-    const int nxt2 = has_next ? next_valid(nxt + stride) : p.n_items;
-    if (nxt2 < p.n_items) prefetch_record(nxt2, (item_seq + 2) % SLOTS);
-    if (has_next) load_q(nxt, qn);
+    Item nxt2 = nxt;
+    if (has_next) {
+      nxt2 = following(nxt);
+      if (nxt2.id < p.n_items) prefetch_record(nxt2, (item_seq + 2) % SLOTS);
+      load_q(nxt, qn);
+    }
     mbar_wait(bar_item + 8 * slot, (item_seq / SLOTS) & 1);
     const uint32_t* rec = rec_gen + slot * INFO_WORDS;
     const int n_live = (int)rec[0];
     const int nc = (n_live + CH - 1) / CH;
-    const int v = it / H, h = it - v * H;
-    if (lane == 0 && h == 0 && row_counter != nullptr) atomicAdd(row_counter, (unsigned long long)n_live);
+    if (lane == 0 && it.h == 0 && row_counter != nullptr) atomicAdd(row_counter, (unsigned long long)n_live);
 
     auto issue_more = [&]() {
       while (issued - consumed < (uint32_t)STAGES) {
@@ -681,21 +710,22 @@ attn_self_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
     for (int dn = 0; dn < 8; ++dn)
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[dn][e] = 0.f;
+    const uint32_t* mask_words = rec + 1 + (g & 7) * 8;
 
     for (int c = 0; c < nc; ++c) {
       const int stage = consumed % STAGES;
-      const uint32_t k_s = kv_s + stage * 2 * CHUNK_BYTES, v_s = k_s + CHUNK_BYTES;
+      const uint32_t k_s = kv_s + stage * 2 * CHUNK_BYTES + k_lane;
+      const uint32_t v_s = kv_s + stage * 2 * CHUNK_BYTES + CHUNK_BYTES + v_lane;
       mbar_wait(bar_kv + 8 * stage, (consumed / STAGES) & 1);
       // ---- S = Q K^T over the chunk's 16 keys ----
       float s[2][2];
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         float cc[4] = {0.f, 0.f, 0.f, 0.f};
-        const int r = half * 8 + rr;
 #pragma unroll
         for (int kp = 0; kp < 2; ++kp) {
           uint32_t b[4];
-          ldsm_x4(b, k_s + sw128(r, 4 * kp + m));
+          ldsm_x4(b, (k_s + half * 1024) ^ (kp << 6));
           mma_bf16(cc, qa[2 * kp][0], qa[2 * kp][1], b[0], b[1]);
           mma_bf16(cc, qa[2 * kp + 1][0], qa[2 * kp + 1][1], b[2], b[3]);
         }
@@ -703,25 +733,18 @@ attn_self_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
         s[half][1] = cc[1];
       }
       // ---- mask (bit j of beam g: compacted key j is on g's prefix and not <pad>), online softmax ----
-      const uint32_t bits = rec[1 + (g & 7) * 8 + (c >> 1)] >> ((c & 1) * 16);
-      float mx = -INFINITY;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int jl = half * 8 + 2 * tig + e;
-          const float x = ((bits >> jl) & 1u) ? s[half][e] * 0.125f : -INFINITY;
-          s[half][e] = x;
-          mx = fmaxf(mx, x);
-        }
-      }
+      const uint32_t bits = mask_words[c >> 1] >> ((c & 1) * 16 + 2 * tig);
+      const float x0 = (bits & 1u) ? s[0][0] * 0.125f : -INFINITY, x1 = (bits & 2u) ? s[0][1] * 0.125f : -INFINITY;
+      const float x2 = (bits & 0x100u) ? s[1][0] * 0.125f : -INFINITY;
+      const float x3 = (bits & 0x200u) ? s[1][1] * 0.125f : -INFINITY;
+      float mx = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
       const float m_new = fmaxf(m_run, mx);
       const float mref = m_new == -INFINITY ? 0.f : m_new;
       const float scale = __expf(m_run - mref);   // 0 for the first chunk with a visible key
-      const float p0 = __expf(s[0][0] - mref), p1 = __expf(s[0][1] - mref);
-      const float p2 = __expf(s[1][0] - mref), p3 = __expf(s[1][1] - mref);
+      const float p0 = __expf(x0 - mref), p1 = __expf(x1 - mref);
+      const float p2 = __expf(x2 - mref), p3 = __expf(x3 - mref);
       float sum = (p0 + p1) + (p2 + p3);
       sum += __shfl_xor_sync(0xffffffffu, sum, 1);
       sum += __shfl_xor_sync(0xffffffffu, sum, 2);
@@ -739,11 +762,10 @@ attn_self_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
         const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&a2h);
         const uint32_t a0l = pack_bf16(p0 - __low2float(h0), p1 - __high2float(h0));
         const uint32_t a2l = pack_bf16(p2 - __low2float(h2), p3 - __high2float(h2));
-        const int r = 8 * (m & 1) + rr;
 #pragma unroll
         for (int dp = 0; dp < 4; ++dp) {
           uint32_t b[4];
-          ldsm_x4_trans(b, v_s + sw128(r, 2 * dp + (m >> 1)));
+          ldsm_x4_trans(b, v_s ^ (dp << 5));
           mma_bf16(o[2 * dp], a0h, a2h, b[0], b[1]);
           mma_bf16(o[2 * dp], a0l, a2l, b[0], b[1]);
           mma_bf16(o[2 * dp + 1], a0h, a2h, b[2], b[3]);
@@ -756,7 +778,7 @@ attn_self_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
     }
     if (g < K) {
       const float inv = 1.0f / l_run;
-      __nv_bfloat16* orow = p.out + (int64_t)(v * K + g) * p.d + h * DH + 2 * tig;
+      __nv_bfloat16* orow = p.out + (int64_t)(it.v * K + g) * p.d + it.h * DH + 2 * tig;
 #pragma unroll
       for (int dn = 0; dn < 8; ++dn)
         *reinterpret_cast<__nv_bfloat162*>(orow + 8 * dn) = __floats2bfloat162_rn(o[dn][0] * inv, o[dn][1] * inv);
