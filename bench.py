@@ -38,8 +38,9 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=16, help="videos per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--self-compact", type=int, default=0, choices=(0, 1, 2),
-                    help="self-attention over live cache slots only: 1 = per-CTA gather, 2 = gathered chunk stream")
+    ap.add_argument("--self-compact", type=int, default=None, choices=(0, 1, 2, 3),
+                    help="bf16 self-attention: 0 = dense tiles, 1 = per-CTA gather of the live cache slots, "
+                         "2 = gathered chunk stream (the library default)")
     ap.add_argument("--no-latency", action="store_true", help="skip the small-batch latency section (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-fed e2e section (profiling runs)")
     return ap.parse_args()
@@ -178,14 +179,19 @@ def kernel_work_table(esz):
         "care_cross_attn_step": lambda a: ("attn_mma_kernel<cross>", "hbm",
                                            (a[6] * a[5] * 2.0 * a[9] + 2.0 * a[6] * a[7] * a[9]) * esz),
         # self at step t: the K*t cached keys/values of every video once + q in + ctx out
-        "care_self_attn_step": lambda a: ("attn_mma_kernel<self>", "hbm",
+        # (all K slots of every position; run_care_arm replaces the K/V part by the rows the kernels actually
+        # read, counted on the device, when the live-slot stream kernel is in use)
+        "care_self_attn_step": lambda a: (SELF_LABEL, "hbm",
                                           (a[4] * a[5] * a[3] * 2.0 * a[7] + 2.0 * a[4] * a[5] * a[7]) * esz),
         "care_add_ln": lambda a: ("add_ln_kernel", "hbm", a[7] * a[8] * (4.0 + 2 * esz)),
         "care_beam_step": lambda a: ("beam_row_kernel", "hbm", 0.0),
     }
 
 
-def summarise_kernels(records, peaks):
+SELF_LABEL = "attn_self_stream_kernel / attn_mma_kernel<self>"
+
+
+def summarise_kernels(records, peaks, units_override=None):
     import collections
     agg = collections.OrderedDict()
     for name, (label, bound, units), e0, e1 in records:
@@ -194,6 +200,9 @@ def summarise_kernels(records, peaks):
         d["ms"] += ms
         d["units"] += units
         d["n"] += 1
+    for label, total in (units_override or {}).items():
+        if label in agg:
+            agg[label]["units"] = total
     hbm = peaks.get("hbm_gbs") or 6650.0
     tens = peaks.get("bf16_tflops_sustained") or 1400.0
     src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
@@ -213,6 +222,13 @@ def summarise_kernels(records, peaks):
                     "algorithmic_units_per_launch": d["units"] / d["n"], "peak_source": psrc})
     out.sort(key=lambda r: -r["total_ms"])
     return out
+
+
+def read_counter(eng, name):
+    import ctypes
+    v = ctypes.c_int64(0)
+    rc = eng.lib.care_ctx_counter(eng.ctx, name.encode(), ctypes.byref(v))
+    return int(v.value) if rc == 0 else 0
 
 
 # ------------------------------------------------------------------------------------------------
@@ -236,6 +252,7 @@ def run_care_arm(args):
     opt = make_opt(**CONFIGS[args.config])
     sd = make_state_dict(opt, seed=0)
     model = care_b200.get_framework(dict(opt, care_precision=args.precision, care_self_compact=args.self_compact))
+    # (care_self_compact None keeps the library default)
     model.load_state_dict(sd)
     model = model.eval().to(dev)
     del sd
@@ -297,6 +314,7 @@ def run_care_arm(args):
         sampler.start()
     timed.on = True
     launches0 = eng.launch_count()
+    rows0 = read_counter(eng, "self_attn_rows")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -305,6 +323,7 @@ def run_care_arm(args):
     sync_all()
     timed.on = False
     launches = eng.launch_count() - launches0
+    self_rows = read_counter(eng, "self_attn_rows") - rows0   # K/V cache rows the bf16 self-attention kernels read
     elapsed_ms = ev0.elapsed_time(ev1)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -386,7 +405,11 @@ def run_care_arm(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    kernels = summarise_kernels(timed.records, peaks)
+    override = {}
+    if self_rows > 0:   # algorithmic bytes of the self-attention = the rows actually read + q in + ctx out
+        n_self = sum(1 for r in timed.records if r[0] == "care_self_attn_step")
+        override[SELF_LABEL] = (self_rows * 2.0 * eng.d + n_self * 2.0 * B * opt["beam_size"] * eng.d) * esz
+    kernels = summarise_kernels(timed.records, peaks, override)
     # DRAM traffic per launch from the committed `ncu --set full` capture of one decode step (profiles/)
     import glob
     tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic_*.json")))

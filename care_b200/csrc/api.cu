@@ -107,6 +107,8 @@ int care_ctx_create(care_ctx** out, int device) {
     delete c;
     return -5;
   }
+  if (const char* e = getenv("CARE_B200_SELF_COMPACT")) c->self_compact = atoi(e);
+  if (c->self_compact && care_ctx_set_option(c, "self_compact", c->self_compact) != 0) c->self_compact = 0;
   *out = c;
   return 0;
 }
@@ -151,8 +153,9 @@ int care_ctx_set_option(care_ctx* ctx, const char* name, int value) {
     if (value && ctx->compact_info == nullptr) {   // scratch for the per-video records (16384 videos x 640 B)
       ctx->compact_info_videos = 16384;
       if (cudaMalloc(&ctx->compact_info, (size_t)ctx->compact_info_videos * 160 * sizeof(uint32_t)) != cudaSuccess) {
+        (void)cudaGetLastError();
         ctx->compact_info = nullptr;
-        ctx->compact_info_videos = 0;
+        ctx->compact_info_videos = 0;   // the self-attention dispatch falls back to the dense tiles
       }
     }
     return 0;

@@ -41,6 +41,7 @@ struct Params {
   const int32_t* tok_hist;  // self: [B, T_max+1, K]
   int tok_stride;
   const int32_t* done;
+  unsigned long long* row_counter;   // self: statistics, K/V cache rows read per video (head 0 counts)
   __nv_bfloat16* out;       // [R, d]
   int n_items;              // B * H
 };
@@ -210,6 +211,7 @@ attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   const int v = blockIdx.x / p.H, h = blockIdx.x - v * p.H;
   if (p.done != nullptr && p.done[v]) return;   // uniform for the CTA
   const int K = p.K, n_keys = p.n_keys;
+  if (SELF && h == 0 && threadIdx.x == 0 && p.row_counter != nullptr) atomicAdd(p.row_counter, (unsigned long long)n_keys);
 
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -897,10 +899,14 @@ int self_step(care_ctx* ctx, const void* cache, int n_pos, int B, int K, int H, 
   p.tok_hist = tok_hist;
   p.tok_stride = (anc_stride + 1) * K;
   p.done = done;
+  p.row_counter = ctx->self_attn_rows;
   p.out = static_cast<__nv_bfloat16*>(ctx_out);
   p.n_items = B * H;
   // short prefixes: nearly every slot is still live and the dense TMA tile is cheaper than the per-item bookkeeping
-  if (ctx->self_compact == 2 && n_pos >= 6 && ctx->compact_info != nullptr && B <= ctx->compact_info_videos &&
+  // (and few (video, head) items - latency mode - leave most of the stream kernel's warps without work)
+  // (3 = the stream kernel for every shape: tests)
+  if ((ctx->self_compact == 3 || (ctx->self_compact == 2 && n_pos >= 6 && p.n_items >= 1024)) &&
+      ctx->compact_info != nullptr && B <= ctx->compact_info_videos &&
       (int64_t)anc_stride * R < (1LL << 31))
     return gs::launch_stream(ctx, p, cache, R, anc_stride, stream);   // rows of the cache as a 2D [T * R, 3d] tensor
   if (ctx->self_compact == 1 && n_pos >= 8 && n_pos <= MAX_POS) {

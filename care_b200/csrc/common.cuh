@@ -77,13 +77,13 @@ struct care_ctx {
   int sm_count = 0;
   int64_t launches = 0;
   int attn_impl = 1;   // 1: TMA + mma.sync attention for bf16 (default), 0: SIMT kernel everywhere
-  // 1: the bf16 self-attention gathers only the cache slots still referenced by a beam (less HBM traffic, but
-  // measured slower than the dense TMA tiles on the benchmark model: profiles/), 0 (default): dense tiles
-  int self_compact = 0;
+  // bf16 self-attention: 2 (default) = gathered chunk stream over the cache slots still referenced by a beam,
+  // 1 = per-CTA gather of those slots (slower than the dense tile, kept for A/B runs), 0 = dense TMA tiles
+  int self_compact = 2;
   int gemm_smallm = 1;   // M <= 16: weight-streaming mma.sync kernel instead of 128-row tensor-core tiles
   uint32_t* compact_info = nullptr;   // [compact_info_videos][160] per-video records of the compacting kernel
   int compact_info_videos = 0;
-  unsigned long long* self_attn_rows = nullptr;   // device counter: K/V rows gathered per (video) by head 0
+  unsigned long long* self_attn_rows = nullptr;   // device counter: K/V cache rows read per video (counted by head 0)
   // 0: single-CTA tiles only, 1: CTA-pair (cta_group::2) tiles whenever the shape allows, 2 (default): pick per
   // (M, N, K, out dtype) by timing both once on the first call with that shape (skipped while capturing)
   int gemm_2sm = 2;

@@ -42,7 +42,7 @@ class CareEngine:
         handle = ctypes.c_void_p()
         check(self.lib.care_ctx_create(ctypes.byref(handle), index), "care_ctx_create")
         self.ctx = handle
-        if opt.get("care_self_compact"):
+        if opt.get("care_self_compact") is not None:   # 0 / 1 / 2, see include/care_b200.h (library default: 2)
             check(self.lib.care_ctx_set_option(self.ctx, b"self_compact", int(opt["care_self_compact"])),
                   "care_ctx_set_option")
         self.d = opt["dim_hidden"]

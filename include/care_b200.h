@@ -67,11 +67,14 @@ int care_ctx_set_option(care_ctx* ctx, const char* name, int value);
  * waves of 256 x 256 tiles, 0 = single-CTA tiles only.
  * "gemm_smallm": 1 (default) = GEMMs with M <= 16 rows (batch-1 / latency mode) use a weight-streaming
  * warp-MMA kernel with one CTA per 8 output columns, 0 = always the tcgen05 tile kernels.
- * "self_compact" (option above): 1 = the bf16 self-attention kernel gathers only the KV-cache slots some
- * beam still references (experimental: less traffic, more latency), 0 (default) = it streams all K slots
- * of every position with one TMA tensor copy.
+ * "self_compact" (option above), bf16 self-attention over the KV cache: 2 (default) = only the cache slots
+ * some beam of the video still references are read, as a stream of 16-row chunks fetched by TMA row gathers
+ * (prefixes of at least 6 positions, 1024 .. 16384 x H (video, head) pairs per call; otherwise the dense tile);
+ * 3 = the chunk stream for every shape (tests); 1 = the earlier per-CTA gather of the live slots (slower,
+ * kept for A/B runs); 0 = all K slots of every
+ * position with one TMA tensor copy.  The environment variable CARE_B200_SELF_COMPACT sets the default.
  * Statistics kept on the device (reading one synchronises): "self_attn_rows" = K/V cache rows per
- * head gathered so far by the compacting self-attention kernel, summed over videos and steps. */
+ * head read so far by the bf16 self-attention kernels, summed over videos and steps. */
 int care_ctx_counter(care_ctx* ctx, const char* name, int64_t* value);
 
 /* C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) — every nn.Linear on the path:

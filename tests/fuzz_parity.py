@@ -84,7 +84,7 @@ for case in range(n_cases):
     # bf16 leg: every step's logits of the KV-cached path (attention MMA kernels for this K, small-M or tile
     # GEMMs for this batch) within 1e-2 relative of the oracle run on bf16-rounded weights; graph replay stable
     if cfg != "cfg5":
-        m16 = care_b200.get_framework(dict(opt, care_precision="bf16", care_self_compact=rng.choice([0, 0, 1, 2, 2])))
+        m16 = care_b200.get_framework(dict(opt, care_precision="bf16", care_self_compact=rng.choice([0, 1, 2, 3, 3])))
         m16.load_state_dict(sd)
         m16 = m16.eval().cuda()
         dev_feats = [f.cuda() for f in feats]

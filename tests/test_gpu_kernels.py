@@ -301,7 +301,7 @@ def test_cross_attention(env, dt, T, K, H, Lm):
     assert (out.float() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("compact", [0, 1, 2])
+@pytest.mark.parametrize("compact", [0, 1, 3])
 @pytest.mark.parametrize("dt,T", [(F32, torch.float32), (BF16, torch.bfloat16)])
 @pytest.mark.parametrize("K,H,n_pos", [(5, 8, 1), (5, 8, 13), (5, 16, 29), (1, 8, 9), (3, 12, 20), (8, 4, 20), (2, 16, 3)])
 def test_self_attention(env, dt, T, K, H, n_pos, compact):

@@ -97,14 +97,17 @@ def _prefixes_from_trace(step_rec, B, K):
     return torch.tensor(rows, dtype=torch.long)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16-stream"])
 @pytest.mark.parametrize("name", ["cfg2_sharp", "cfg1_sharp", "cfg4_sharp", "cab_sharp"])
 def test_teacher_forced_step_logits(name, precision):
     """Every step's logits from the KV-cached, ancestry-indirected CUDA path against the oracle's
-    full-prefix recompute on exactly the prefixes the GPU beam holds at that step."""
+    full-prefix recompute on exactly the prefixes the GPU beam holds at that step.  "bf16-stream" forces the
+    live-slot chunk-stream self-attention kernel, which small batches would not select by themselves."""
     import care_b200
     rec = load_golden(name)
     opt, sd, feats = rebuild_case(rec, batch=3)
+    if precision == "bf16-stream":
+        opt, precision = dict(opt, care_self_compact=3), "bf16"
     if precision == "bf16":
         sd_o = {k: (v.bfloat16().float() if v.dim() == 2 and "embeddings" not in k else v) for k, v in sd.items()}
     else:
