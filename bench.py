@@ -35,7 +35,8 @@ def parse():
     ap.add_argument("--impl", default="care", choices=["care", "reference"])
     ap.add_argument("--config", default="cfg4")
     ap.add_argument("--batch", type=int, default=4096, help="videos per GPU per step")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"],
+                    help="fp16 (default) / bf16: 16-bit tensor-core operands, fp32 accumulation; fp32: the bit-exact parity mode")
     ap.add_argument("--cpu-batch", type=int, default=16, help="videos per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--self-compact", type=int, default=None, choices=(0, 1, 2, 3),
@@ -302,7 +303,7 @@ def run_care_arm(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    esz = 2 if args.precision == "bf16" else 4
+    esz = 4 if args.precision == "fp32" else 2
     timed = TimedLib(eng.lib, kernel_work_table(esz))
     eng.lib = timed
 
@@ -413,7 +414,7 @@ def run_care_arm(args):
     # DRAM traffic per launch from the committed `ncu --set full` capture of one decode step (profiles/)
     import glob
     tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic_*.json")))
-    if tfiles and args.config == "cfg4" and B == 4096 and args.precision == "bf16":
+    if tfiles and args.config == "cfg4" and B == 4096 and args.precision != "fp32":
         tr_json = json.load(open(tfiles[-1]))
         for r in kernels:
             tkey = r["kernel"].split(" / ")[0]
@@ -421,7 +422,6 @@ def run_care_arm(args):
                 r["traffic"] = tr_json[tkey]["traffic_bytes_per_launch"]
                 r["traffic_source"] = "%s (dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches " \
                                       "of one decode step, t~15)" % os.path.relpath(tfiles[-1], ROOT)
-    use_bf16 = args.precision == "bf16"
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -440,7 +440,7 @@ def run_care_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if use_bf16 else "f32", "data": "synthetic",
+        "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
         "config": {"workload": workload_name(args.config, B, args.precision), "beam_size": opt["beam_size"],
                    "per_gpu_batch": B, "global_batch": B * world, "parallelism": "video-sharded x%d" % world,
                    "decode_ms_per_beam_step": step_ms / Tm,

@@ -8,9 +8,10 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcare_b200.so")
+LIB_PATH = os.path.join(_HERE, "lib", "libcare_b200.so")            # 16-bit operand type: IEEE fp16
+LIB_PATH_BF16 = os.path.join(_HERE, "lib", "libcare_b200_bf16.so")  # same sources built with -DCARE_USE_BF16
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_RELU = 0, 1
 
 
@@ -26,6 +27,7 @@ class BeamState(Structure):
 
 _SIGNATURES = {
     "care_version": (c_int, []),
+    "care_h16_dtype": (c_int, []),
     "care_last_error": (c_char_p, []),
     "care_ctx_create": (c_int, [POINTER(c_void_p), c_int]),
     "care_ctx_destroy": (None, [c_void_p]),
@@ -36,7 +38,7 @@ _SIGNATURES = {
     "care_ctx_set_option": (c_int, [c_void_p, c_char_p, c_int]),
     "care_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                           c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "care_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "care_split_f32_h16": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
     "care_encoder_ln_mean": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int,
                                      c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_void_p]),
     "care_encoder_highway_bn_mean": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -86,30 +88,40 @@ _SIGNATURES = {
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())
 
-_lib = None
+_libs = {}
 
 
-def load():
-    """Loads the shared library (once).  Raises if it has not been built."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.isfile(LIB_PATH):
+def load(h16="fp16"):
+    """Loads the shared library whose 16-bit operand type is `h16` ("fp16": libcare_b200.so, "bf16":
+    libcare_b200_bf16.so), once.  Raises if it has not been built."""
+    lib = _libs.get(h16)
+    if lib is not None:
+        return lib
+    if h16 not in ("fp16", "bf16"):
+        raise ValueError("h16 must be 'fp16' or 'bf16'")
+    path = LIB_PATH if h16 == "fp16" else LIB_PATH_BF16
+    if not os.path.isfile(path):
         raise RuntimeError(
             "care_b200: %s is missing - build it with `python -m care_b200.build` "
-            "(there is no CPU or PyTorch fallback)" % LIB_PATH)
-    lib = ctypes.CDLL(LIB_PATH)
+            "(there is no CPU or PyTorch fallback)" % path)
+    lib = ctypes.CDLL(path)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
+    if lib.care_h16_dtype() != (F16 if h16 == "fp16" else BF16):
+        raise RuntimeError("care_b200: %s was built for another 16-bit type" % path)
+    _libs[h16] = lib
     return lib
 
 
-def check(rc, what=""):
+def check(rc, what="", lib=None):
     if rc != 0:
-        msg = load().care_last_error()
+        msg = None
+        for l in ([lib] if lib is not None else list(_libs.values())):
+            msg = l.care_last_error()
+            if msg:
+                break
         raise RuntimeError("care_b200 %s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else "?"))
 
 

@@ -1,4 +1,6 @@
-"""Builds care_b200/lib/libcare_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Builds the C-ABI libraries in-tree with nvcc for sm_100a (cross-compiles without a GPU):
+care_b200/lib/libcare_b200.so (16-bit operand type = IEEE fp16, the default throughput mode) and
+care_b200/lib/libcare_b200_bf16.so (same sources with -DCARE_USE_BF16)."""
 import glob
 import hashlib
 import os
@@ -9,6 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libcare_b200.so")
+LIB_BF16 = os.path.join(LIB_DIR, "libcare_b200_bf16.so")
+VARIANTS = (("fp16", LIB, []), ("bf16", LIB_BF16, ["-DCARE_USE_BF16"]))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -33,20 +37,25 @@ def build(force=False, verbose=False):
     os.makedirs(LIB_DIR, exist_ok=True)
     stamp = os.path.join(LIB_DIR, "build.sha256")
     dig = _digest()
-    if not force and os.path.isfile(LIB) and os.path.isfile(stamp) and open(stamp).read().strip() == dig:
+    if (not force and all(os.path.isfile(v[1]) for v in VARIANTS) and os.path.isfile(stamp)
+            and open(stamp).read().strip() == dig):
         return LIB
-    objs = []
     procs = []
-    for src in _sources():
-        obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + ".o")
-        objs.append(obj)
-        cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs = {}
+    for name, lib, defs in VARIANTS:
+        odir = os.path.join(LIB_DIR, "obj_" + name)
+        os.makedirs(odir, exist_ok=True)
+        objs[name] = []
+        for src in _sources():
+            obj = os.path.join(odir, os.path.basename(src)[:-3] + ".o")
+            objs[name].append(obj)
+            cmd = [NVCC] + FLAGS + defs + ["-c", src, "-o", obj]
+            procs.append((name, src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     failed = False
-    for src, p in procs:
+    for name, src, p in procs:
         out, _ = p.communicate()
-        log.append("== %s\n%s" % (os.path.basename(src), out))
+        log.append("== [%s] %s\n%s" % (name, os.path.basename(src), out))
         if p.returncode != 0:
             failed = True
     with open(os.path.join(LIB_DIR, "build.log"), "w") as f:
@@ -55,7 +64,8 @@ def build(force=False, verbose=False):
         sys.stderr.write("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed; see %s" % os.path.join(LIB_DIR, "build.log"))
-    subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    for name, lib, _ in VARIANTS:
+        subprocess.check_call([NVCC, "-shared", "-o", lib] + objs[name] + ["-gencode", "arch=compute_100a,code=sm_100a"])
     with open(stamp, "w") as f:
         f.write(dig)
     return LIB

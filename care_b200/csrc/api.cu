@@ -42,7 +42,7 @@ int get_tmap_bf16(care_ctx* ctx, const void* ptr, int rank, const uint64_t* gdim
     bx[i] = box[i];
     if (i > 0) gs[i - 1] = gstride_bytes[i - 1];
   }
-  CUresult r = ctx->encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
+  CUresult r = ctx->encode(&m, CARE_TMAP_H16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -63,7 +63,9 @@ int get_tmap_bf16(care_ctx* ctx, const void* ptr, int rank, const uint64_t* gdim
 
 extern "C" {
 
-int care_version(void) { return 100; }
+int care_version(void) { return 200; }
+
+int care_h16_dtype(void) { return CARE_H16; }
 
 const char* care_last_error(void) { return care::g_err; }
 

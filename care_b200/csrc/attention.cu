@@ -221,9 +221,10 @@ extern "C" {
 int care_self_attn_step(care_ctx* ctx, int dtype, const void* cache, int n_pos, int B, int K, int H, int d,
                         const uint8_t* anc, int anc_stride, const int32_t* tok_hist, const int32_t* done,
                         void* ctx_out, void* stream) {
+  CARE_CHECK_DTYPE(dtype, "care_self_attn_step");
   CARE_CHECK_ARG(ctx && cache && anc && tok_hist && ctx_out && n_pos >= 1, "care_self_attn_step: bad args");
   if (attn::common_checks("care_self_attn_step", B, K, H, d)) return -1;
-  if (dtype == CARE_BF16 && ctx->attn_impl == 1) {
+  if (dtype == CARE_H16 && ctx->attn_impl == 1) {
     const int rc = attn_mma::self_step(ctx, cache, n_pos, B, K, H, d, anc, anc_stride, tok_hist, done, ctx_out,
                                        (cudaStream_t)stream);
     if (rc != 1) return rc;
@@ -251,17 +252,18 @@ int care_self_attn_step(care_ctx* ctx, int dtype, const void* cache, int n_pos, 
   p.sc_ld = (p.n_keys + 3) & ~3;
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == CARE_F32) return attn::launch<float, true>(ctx, p, B, s);
-  if (dtype == CARE_BF16) return attn::launch<__nv_bfloat16, true>(ctx, p, B, s);
+  if (dtype == CARE_H16) return attn::launch<h16, true>(ctx, p, B, s);
   care::set_error("care_self_attn_step: bad dtype %d", dtype);
   return -1;
 }
 
 int care_cross_attn_step(care_ctx* ctx, int dtype, const void* q, int64_t ldq, const void* kv, int Lm, int B, int K,
                          int H, int d, const float* hybrid_bias, const int32_t* done, void* ctx_out, void* stream) {
+  CARE_CHECK_DTYPE(dtype, "care_cross_attn_step");
   CARE_CHECK_ARG(ctx && q && kv && ctx_out && Lm >= 1, "care_cross_attn_step: bad args");
   if (attn::common_checks("care_cross_attn_step", B, K, H, d)) return -1;
   CARE_CHECK_ARG(ldq % 8 == 0, "care_cross_attn_step: ldq must be a multiple of 8");
-  if (dtype == CARE_BF16 && ctx->attn_impl == 1) {
+  if (dtype == CARE_H16 && ctx->attn_impl == 1) {
     const int rc = attn_mma::cross_step(ctx, q, ldq, kv, Lm, B, K, H, d, hybrid_bias, done, ctx_out,
                                         (cudaStream_t)stream);
     if (rc != 1) return rc;
@@ -284,7 +286,7 @@ int care_cross_attn_step(care_ctx* ctx, int dtype, const void* q, int64_t ldq, c
   p.sc_ld = (Lm + 3) & ~3;
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == CARE_F32) return attn::launch<float, false>(ctx, p, B, s);
-  if (dtype == CARE_BF16) return attn::launch<__nv_bfloat16, false>(ctx, p, B, s);
+  if (dtype == CARE_H16) return attn::launch<h16, false>(ctx, p, B, s);
   care::set_error("care_cross_attn_step: bad dtype %d", dtype);
   return -1;
 }

@@ -80,14 +80,14 @@ __global__ void __launch_bounds__(32) group_attn_mma_kernel(const __grid_constan
   __syncwarp();
   mbar_wait(bar, 0);
 
-  const __nv_bfloat16* qbase = static_cast<const __nv_bfloat16*>(p.q) + h * DH;
-  __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.out) + h * DH;
+  const h16* qbase = static_cast<const h16*>(p.q) + h * DH;
+  h16* obase = static_cast<h16*>(p.out) + h * DH;
   const int m = lane >> 3, rr = lane & 7;
   for (int qb = 0; qb * 16 < nq; ++qb) {
     const int i0 = qb * 16 + g, i1 = i0 + 8;   // this thread's two query rows (within the group)
     const bool ok0 = i0 < nq, ok1 = i1 < nq;
-    const __nv_bfloat16* q0 = qbase + ((int64_t)grp * nq + (ok0 ? i0 : 0)) * p.q_ld;
-    const __nv_bfloat16* q1 = qbase + ((int64_t)grp * nq + (ok1 ? i1 : 0)) * p.q_ld;
+    const h16* q0 = qbase + ((int64_t)grp * nq + (ok0 ? i0 : 0)) * p.q_ld;
+    const h16* q1 = qbase + ((int64_t)grp * nq + (ok1 ? i1 : 0)) * p.q_ld;
     uint32_t qa[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
@@ -171,14 +171,14 @@ __global__ void __launch_bounds__(32) group_attn_mma_kernel(const __grid_constan
     for (int kk = 0; kk < NT / 2; ++kk) {
       if (kk * 16 < nk) {
         uint32_t ah[4], al[4];
-        ah[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-        ah[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-        ah[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-        ah[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-        al[0] = pack_bf16(s[2 * kk][0] - bf16_lo(ah[0]), s[2 * kk][1] - bf16_hi(ah[0]));
-        al[1] = pack_bf16(s[2 * kk][2] - bf16_lo(ah[1]), s[2 * kk][3] - bf16_hi(ah[1]));
-        al[2] = pack_bf16(s[2 * kk + 1][0] - bf16_lo(ah[2]), s[2 * kk + 1][1] - bf16_hi(ah[2]));
-        al[3] = pack_bf16(s[2 * kk + 1][2] - bf16_lo(ah[3]), s[2 * kk + 1][3] - bf16_hi(ah[3]));
+        ah[0] = pack_h16(s[2 * kk][0], s[2 * kk][1]);
+        ah[1] = pack_h16(s[2 * kk][2], s[2 * kk][3]);
+        ah[2] = pack_h16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        ah[3] = pack_h16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        al[0] = pack_h16(s[2 * kk][0] - h16_lo(ah[0]), s[2 * kk][1] - h16_hi(ah[0]));
+        al[1] = pack_h16(s[2 * kk][2] - h16_lo(ah[1]), s[2 * kk][3] - h16_hi(ah[1]));
+        al[2] = pack_h16(s[2 * kk + 1][0] - h16_lo(ah[2]), s[2 * kk + 1][1] - h16_hi(ah[2]));
+        al[3] = pack_h16(s[2 * kk + 1][2] - h16_lo(ah[3]), s[2 * kk + 1][3] - h16_hi(ah[3]));
         const int r = kk * 16 + 8 * (m & 1) + rr;
 #pragma unroll
         for (int dp = 0; dp < 4; ++dp) {
@@ -193,16 +193,16 @@ __global__ void __launch_bounds__(32) group_attn_mma_kernel(const __grid_constan
     }
     const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
     if (ok0) {
-      __nv_bfloat16* orow = obase + ((int64_t)grp * nq + i0) * p.d + 2 * tig;
+      h16* orow = obase + ((int64_t)grp * nq + i0) * p.d + 2 * tig;
 #pragma unroll
       for (int dn = 0; dn < 8; ++dn)
-        *reinterpret_cast<__nv_bfloat162*>(orow + 8 * dn) = __floats2bfloat162_rn(o[dn][0] * inv0, o[dn][1] * inv0);
+        *reinterpret_cast<h162*>(orow + 8 * dn) = floats_to_h162(o[dn][0] * inv0, o[dn][1] * inv0);
     }
     if (ok1) {
-      __nv_bfloat16* orow = obase + ((int64_t)grp * nq + i1) * p.d + 2 * tig;
+      h16* orow = obase + ((int64_t)grp * nq + i1) * p.d + 2 * tig;
 #pragma unroll
       for (int dn = 0; dn < 8; ++dn)
-        *reinterpret_cast<__nv_bfloat162*>(orow + 8 * dn) = __floats2bfloat162_rn(o[dn][2] * inv1, o[dn][3] * inv1);
+        *reinterpret_cast<h162*>(orow + 8 * dn) = floats_to_h162(o[dn][2] * inv1, o[dn][3] * inv1);
     }
   }
 }
@@ -295,6 +295,7 @@ extern "C" {
 int care_group_attn(care_ctx* ctx, int dtype, const void* q, int64_t ldq, const void* kv, int64_t ldkv, int k_col,
                     int v_col, int n_groups, int nq, int nk, int H, int d, const int32_t* key_tokens, int causal,
                     const float* bias, void* out, void* stream) {
+  CARE_CHECK_DTYPE(dtype, "care_group_attn");
   CARE_CHECK_ARG(ctx && q && kv && out && n_groups > 0 && nq > 0 && nk > 0, "care_group_attn: bad args");
   CARE_CHECK_ARG(H > 0 && d == H * attn_group::DH, "care_group_attn: head size must be 64 (d=%d, H=%d)", d, H);
   CARE_CHECK_ARG(!causal || nq == nk, "care_group_attn: causal needs nq == nk");
@@ -306,7 +307,7 @@ int care_group_attn(care_ctx* ctx, int dtype, const void* q, int64_t ldq, const 
   p.rows_pad = (nk + 15) & ~15;
   p.key_tokens = key_tokens; p.causal = causal; p.bias = bias; p.out = out;
   cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == CARE_BF16 && ctx->attn_impl == 1 && nk <= 128 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0) {
+  if (dtype == CARE_H16 && ctx->attn_impl == 1 && nk <= 128 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0) {
     CUtensorMap tmap;
     const uint64_t gdim[2] = {(uint64_t)ldkv, (uint64_t)n_groups * nk};
     const uint64_t gstr[1] = {(uint64_t)ldkv * 2};
@@ -320,7 +321,7 @@ int care_group_attn(care_ctx* ctx, int dtype, const void* q, int64_t ldq, const 
   const int64_t items = (int64_t)n_groups * H * nq;
   const int grid = (int)((items + 3) / 4);
   if (dtype == CARE_F32) attn_group::group_attn_simt_kernel<float><<<grid, 128, 0, s>>>(p);
-  else if (dtype == CARE_BF16) attn_group::group_attn_simt_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(p);
+  else if (dtype == CARE_H16) attn_group::group_attn_simt_kernel<h16><<<grid, 128, 0, s>>>(p);
   else {
     care::set_error("care_group_attn: bad dtype %d", dtype);
     return -1;

@@ -27,7 +27,7 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a2
 }
 
 struct Params {
-  const __nv_bfloat16* q;   // q of (row 0, head 0)
+  const h16* q;   // q of (row 0, head 0)
   int64_t q_ld;
   int k_col, v_col;         // element column of K / V (head 0) in the tensor map's row
   int n_keys;               // Lm (cross) or n_pos * K (self)
@@ -42,7 +42,7 @@ struct Params {
   int tok_stride;
   const int32_t* done;
   unsigned long long* row_counter;   // self: statistics, K/V cache rows read per video (head 0 counts)
-  __nv_bfloat16* out;       // [R, d]
+  h16* out;       // [R, d]
   int n_items;              // B * H
 };
 
@@ -140,11 +140,11 @@ __device__ __forceinline__ void attend(const Params& p, int v, int h, int warp, 
     const int kk = kk0 + i;
     if (kk < kk1) {
       const float p0 = s[2 * i][0], p1 = s[2 * i][1], p2 = s[2 * i + 1][0], p3 = s[2 * i + 1][1];
-      const uint32_t a0h = pack_bf16(p0, p1), a2h = pack_bf16(p2, p3);
-      const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&a0h);
-      const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&a2h);
-      const uint32_t a0l = pack_bf16(p0 - __low2float(h0), p1 - __high2float(h0));
-      const uint32_t a2l = pack_bf16(p2 - __low2float(h2), p3 - __high2float(h2));
+      const uint32_t a0h = pack_h16(p0, p1), a2h = pack_h16(p2, p3);
+      const h162 h0 = *reinterpret_cast<const h162*>(&a0h);
+      const h162 h2 = *reinterpret_cast<const h162*>(&a2h);
+      const uint32_t a0l = pack_h16(p0 - __low2float(h0), p1 - __high2float(h0));
+      const uint32_t a2l = pack_h16(p2 - __low2float(h2), p3 - __high2float(h2));
       const int r = kk * 16 + 8 * (m & 1) + rr;
 #pragma unroll
       for (int dp = 0; dp < 4; ++dp) {
@@ -160,10 +160,10 @@ __device__ __forceinline__ void attend(const Params& p, int v, int h, int warp, 
   if (WARPS == 1) {   // short key sets: one warp saw every key, no merge
     if (g < K) {
       const float inv = 1.0f / sum;
-      __nv_bfloat16* orow = p.out + (int64_t)(v * K + g) * p.d + h * DH + 2 * tig;
+      h16* orow = p.out + (int64_t)(v * K + g) * p.d + h * DH + 2 * tig;
 #pragma unroll
       for (int dn = 0; dn < 8; ++dn)
-        *reinterpret_cast<__nv_bfloat162*>(orow + 8 * dn) = __floats2bfloat162_rn(o[dn][0] * inv, o[dn][1] * inv);
+        *reinterpret_cast<h162*>(orow + 8 * dn) = floats_to_h162(o[dn][0] * inv, o[dn][1] * inv);
     }
     return;
   }
@@ -193,7 +193,7 @@ __device__ __forceinline__ void attend(const Params& p, int v, int h, int warp, 
         den += stat[(w * 8 + b) * 2 + 1] * sc;
         num += comb[((size_t)w * 8 + b) * COMB_LD + col] * sc;
       }
-      p.out[(int64_t)(v * K + b) * p.d + h * DH + col] = __float2bfloat16_rn(num / den);
+      p.out[(int64_t)(v * K + b) * p.d + h * DH + col] = float_to_h16(num / den);
     }
   }
 }
@@ -252,7 +252,7 @@ attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   // Q fragments: A[beam g][dims 16ks + 2tig, +1] and [.. + 8, + 9]
   uint32_t qa[4][2];
   {
-    const __nv_bfloat16* qrow = p.q + (int64_t)(v * K + (g < K ? g : 0)) * p.q_ld + h * DH;
+    const h16* qrow = p.q + (int64_t)(v * K + (g < K ? g : 0)) * p.q_ld + h * DH;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       qa[ks][0] = *reinterpret_cast<const uint32_t*>(qrow + 16 * ks + 2 * tig);
@@ -369,7 +369,7 @@ compact_info_kernel(const uint8_t* __restrict__ anc, int anc_stride, const int32
 
 template <int KKW>
 __global__ void __launch_bounds__(128)
-attn_self_compact_kernel(const Params p, const __nv_bfloat16* __restrict__ cache, int64_t R,
+attn_self_compact_kernel(const Params p, const h16* __restrict__ cache, int64_t R,
                          unsigned long long* __restrict__ row_counter, const uint32_t* __restrict__ info) {
   constexpr int WARPS = 4;
   extern __shared__ uint8_t smem_raw[];
@@ -397,7 +397,7 @@ attn_self_compact_kernel(const Params p, const __nv_bfloat16* __restrict__ cache
   const int g = lane >> 2, tig = lane & 3;
   uint32_t qa[4][2];
   {
-    const __nv_bfloat16* qrow = p.q + (int64_t)(v * K + (g < K ? g : 0)) * p.q_ld + h * DH;
+    const h16* qrow = p.q + (int64_t)(v * K + (g < K ? g : 0)) * p.q_ld + h * DH;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       qa[ks][0] = *reinterpret_cast<const uint32_t*>(qrow + 16 * ks + 2 * tig);
@@ -463,8 +463,8 @@ attn_self_compact_kernel(const Params p, const __nv_bfloat16* __restrict__ cache
   }
   // gather: 16 chunks of 16 B per live row (8 of K, 8 of V)
   {
-    const __nv_bfloat16* kbase = cache + (int64_t)v * K * (3LL * p.d) + p.k_col + h * DH;
-    const __nv_bfloat16* vbase = cache + (int64_t)v * K * (3LL * p.d) + p.v_col + h * DH;
+    const h16* kbase = cache + (int64_t)v * K * (3LL * p.d) + p.k_col + h * DH;
+    const h16* vbase = cache + (int64_t)v * K * (3LL * p.d) + p.v_col + h * DH;
     const int n_chunks = n_live * 16;
     for (int c = threadIdx.x; c < n_chunks; c += 128) {
       const int j = c >> 4, isv = (c >> 3) & 1, c16 = c & 7;
@@ -502,7 +502,7 @@ static int launch_compact(care_ctx* ctx, const Params& p, const void* cache, int
     CARE_LAUNCH_CHECK(ctx);
     info = ctx->compact_info;
   }
-  kern<<<p.n_items, 128, smem, stream>>>(p, static_cast<const __nv_bfloat16*>(cache), R, ctx->self_attn_rows, info);
+  kern<<<p.n_items, 128, smem, stream>>>(p, static_cast<const h16*>(cache), R, ctx->self_attn_rows, info);
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -759,11 +759,11 @@ attn_self_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
       }
       // ---- O += P V ----
       {
-        const uint32_t a0h = pack_bf16(p0, p1), a2h = pack_bf16(p2, p3);
-        const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&a0h);
-        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&a2h);
-        const uint32_t a0l = pack_bf16(p0 - __low2float(h0), p1 - __high2float(h0));
-        const uint32_t a2l = pack_bf16(p2 - __low2float(h2), p3 - __high2float(h2));
+        const uint32_t a0h = pack_h16(p0, p1), a2h = pack_h16(p2, p3);
+        const h162 h0 = *reinterpret_cast<const h162*>(&a0h);
+        const h162 h2 = *reinterpret_cast<const h162*>(&a2h);
+        const uint32_t a0l = pack_h16(p0 - __low2float(h0), p1 - __high2float(h0));
+        const uint32_t a2l = pack_h16(p2 - __low2float(h2), p3 - __high2float(h2));
 #pragma unroll
         for (int dp = 0; dp < 4; ++dp) {
           uint32_t b[4];
@@ -780,10 +780,10 @@ attn_self_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
     }
     if (g < K) {
       const float inv = 1.0f / l_run;
-      __nv_bfloat16* orow = p.out + (int64_t)(it.v * K + g) * p.d + it.h * DH + 2 * tig;
+      h16* orow = p.out + (int64_t)(it.v * K + g) * p.d + it.h * DH + 2 * tig;
 #pragma unroll
       for (int dn = 0; dn < 8; ++dn)
-        *reinterpret_cast<__nv_bfloat162*>(orow + 8 * dn) = __floats2bfloat162_rn(o[dn][0] * inv, o[dn][1] * inv);
+        *reinterpret_cast<h162*>(orow + 8 * dn) = floats_to_h162(o[dn][0] * inv, o[dn][1] * inv);
     }
     if (!has_next) break;
     __syncwarp();   // the record slot of this item is free for the item three ahead
@@ -856,7 +856,7 @@ int cross_step(care_ctx* ctx, const void* q, int64_t ldq, const void* kv, int Lm
   int rc = get_tmap_bf16(ctx, kv, 2, gdim, gstr, box, &tmap);
   if (rc) return rc;
   Params p{};
-  p.q = static_cast<const __nv_bfloat16*>(q);
+  p.q = static_cast<const h16*>(q);
   p.q_ld = ldq;
   p.k_col = 0;
   p.v_col = d;
@@ -865,7 +865,7 @@ int cross_step(care_ctx* ctx, const void* q, int64_t ldq, const void* kv, int Lm
   p.K = K; p.H = H; p.d = d; p.Lm = Lm;
   p.bias = hybrid_bias;
   p.done = done;
-  p.out = static_cast<__nv_bfloat16*>(ctx_out);
+  p.out = static_cast<h16*>(ctx_out);
   p.n_items = B * H;
   if (Lm <= 32) return launch<2, false, 1>(ctx, tmap, p, stream);   // e.g. the 30 concept embeddings (attr_attention)
   if (Lm <= 64) return launch<2, false, 2>(ctx, tmap, p, stream);
@@ -886,7 +886,7 @@ int self_step(care_ctx* ctx, const void* cache, int n_pos, int B, int K, int H, 
   int rc = get_tmap_bf16(ctx, cache, 3, gdim, gstr, box, &tmap);
   if (rc) return rc;
   Params p{};
-  p.q = static_cast<const __nv_bfloat16*>(cache) + (int64_t)(n_pos - 1) * R * 3 * d;
+  p.q = static_cast<const h16*>(cache) + (int64_t)(n_pos - 1) * R * 3 * d;
   p.q_ld = 3LL * d;
   p.k_col = d;
   p.v_col = 2 * d;
@@ -900,7 +900,7 @@ int self_step(care_ctx* ctx, const void* cache, int n_pos, int B, int K, int H, 
   p.tok_stride = (anc_stride + 1) * K;
   p.done = done;
   p.row_counter = ctx->self_attn_rows;
-  p.out = static_cast<__nv_bfloat16*>(ctx_out);
+  p.out = static_cast<h16*>(ctx_out);
   p.n_items = B * H;
   // short prefixes: nearly every slot is still live and the dense TMA tile is cheaper than the per-item bookkeeping
   // (and few (video, head) items - latency mode - leave most of the stream kernel's warps without work)

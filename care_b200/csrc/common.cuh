@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -11,6 +12,38 @@
 #include <unordered_map>
 
 #include "../../include/care_b200.h"
+
+// The 16-bit operand type of this build of the library.  Default: IEEE fp16 (10 mantissa bits - activations
+// of this model are O(1) after every LayerNorm, so fp16's range is ample and its rounding error is 8x below
+// bf16's; bf16-stored weights are exactly representable).  -DCARE_USE_BF16 builds the same kernels over bf16
+// (libcare_b200_bf16.so).  Tensor-core throughput is identical for both (tcgen05 kind::f16, mma.sync m16n8k16).
+#ifdef CARE_USE_BF16
+typedef __nv_bfloat16 h16;
+typedef __nv_bfloat162 h162;
+#define CARE_H16 CARE_BF16
+#define CARE_H16_NAME "bf16"
+#define CARE_TMAP_H16 CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#define CARE_MMA_H16 "bf16"
+#define CARE_UMMA_FMT 1u   // cute::UMMA::F16F32Format: F16 = 0, BF16 = 1
+__device__ __forceinline__ h162 floats_to_h162(float a, float b) { return __floats2bfloat162_rn(a, b); }
+__device__ __forceinline__ h16 float_to_h16(float a) { return __float2bfloat16_rn(a); }
+__device__ __forceinline__ float2 h162_to_float2(h162 a) { return __bfloat1622float2(a); }
+__device__ __forceinline__ float h16_to_float(h16 a) { return __bfloat162float(a); }
+#else
+typedef __half h16;
+typedef __half2 h162;
+#define CARE_H16 CARE_F16
+#define CARE_H16_NAME "fp16"
+#define CARE_TMAP_H16 CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#define CARE_MMA_H16 "f16"
+#define CARE_UMMA_FMT 0u
+// saturating: a value beyond fp16's range becomes +-65504 instead of inf (inf - inf = NaN inside a softmax)
+__device__ __forceinline__ float sat16(float a) { return fminf(fmaxf(a, -65504.f), 65504.f); }
+__device__ __forceinline__ h162 floats_to_h162(float a, float b) { return __floats2half2_rn(sat16(a), sat16(b)); }
+__device__ __forceinline__ h16 float_to_h16(float a) { return __float2half_rn(sat16(a)); }
+__device__ __forceinline__ float2 h162_to_float2(h162 a) { return __half22float2(a); }
+__device__ __forceinline__ float h16_to_float(h16 a) { return __half2float(a); }
+#endif
 
 namespace care {
 
@@ -23,6 +56,11 @@ void set_error(const char* fmt, ...);
       return -1;                           \
     }                                      \
   } while (0)
+
+#define CARE_CHECK_DTYPE(dtype, who)                                                                 \
+  CARE_CHECK_ARG((dtype) == CARE_F32 || (dtype) == CARE_H16,                                         \
+                 "%s: dtype code %d - this build of the library computes in fp32 (0) or " CARE_H16_NAME " (%d)", who, \
+                 (int)(dtype), (int)CARE_H16)
 
 #define CARE_CUDA(expr)                                                                   \
   do {                                                                                    \
@@ -156,40 +194,40 @@ struct Act<float> {
   static __device__ __forceinline__ float from_float(float x) { return x; }
 };
 template <>
-struct Act<__nv_bfloat16> {
-  static constexpr int kDtype = CARE_BF16;
-  static __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+struct Act<h16> {
+  static constexpr int kDtype = CARE_H16;
+  static __device__ __forceinline__ void load8(const h16* p, float (&v)[8]) {
     uint4 raw = *reinterpret_cast<const uint4*>(p);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    const h162* h = reinterpret_cast<const h162*>(&raw);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float2 f = __bfloat1622float2(h[i]);
+      float2 f = h162_to_float2(h[i]);
       v[2 * i] = f.x;
       v[2 * i + 1] = f.y;
     }
   }
-  static __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  static __device__ __forceinline__ void store8(h16* p, const float (&v)[8]) {
     uint4 raw;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+    h162* h = reinterpret_cast<h162*>(&raw);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    for (int i = 0; i < 4; ++i) h[i] = floats_to_h162(v[2 * i], v[2 * i + 1]);
     *reinterpret_cast<uint4*>(p) = raw;
   }
-  static __device__ __forceinline__ void load4(const __nv_bfloat16* p, float (&v)[4]) {
+  static __device__ __forceinline__ void load4(const h16* p, float (&v)[4]) {
     uint2 raw = *reinterpret_cast<const uint2*>(p);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
-    float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    const h162* h = reinterpret_cast<const h162*>(&raw);
+    float2 a = h162_to_float2(h[0]), b = h162_to_float2(h[1]);
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
   }
-  static __device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&v)[4]) {
+  static __device__ __forceinline__ void store4(h16* p, const float (&v)[4]) {
     uint2 raw;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
-    h[0] = __floats2bfloat162_rn(v[0], v[1]);
-    h[1] = __floats2bfloat162_rn(v[2], v[3]);
+    h162* h = reinterpret_cast<h162*>(&raw);
+    h[0] = floats_to_h162(v[0], v[1]);
+    h[1] = floats_to_h162(v[2], v[3]);
     *reinterpret_cast<uint2*>(p) = raw;
   }
-  static __device__ __forceinline__ float to_float(__nv_bfloat16 x) { return __bfloat162float(x); }
-  static __device__ __forceinline__ __nv_bfloat16 from_float(float x) { return __float2bfloat16_rn(x); }
+  static __device__ __forceinline__ float to_float(h16 x) { return h16_to_float(x); }
+  static __device__ __forceinline__ h16 from_float(float x) { return float_to_h16(x); }
 };
 
 }  // namespace care

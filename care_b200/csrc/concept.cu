@@ -144,10 +144,10 @@ extern "C" int care_concept_head(care_ctx* ctx, int dtype, const float* scores, 
     concept_head::concept_head_kernel<float><<<B, concept_head::THREADS, 0, s>>>(
         scores, ld_scores, n_attr, topk, attr_word, attr_pos, gamma, beta, eps, d, preds_f32, (float*)preds_T,
         ld_preds_T, labels, (float*)memory, mem_rows, mem_row0);
-  else if (dtype == CARE_BF16)
-    concept_head::concept_head_kernel<__nv_bfloat16><<<B, concept_head::THREADS, 0, s>>>(
-        scores, ld_scores, n_attr, topk, attr_word, attr_pos, gamma, beta, eps, d, preds_f32, (__nv_bfloat16*)preds_T,
-        ld_preds_T, labels, (__nv_bfloat16*)memory, mem_rows, mem_row0);
+  else if (dtype == CARE_H16)
+    concept_head::concept_head_kernel<h16><<<B, concept_head::THREADS, 0, s>>>(
+        scores, ld_scores, n_attr, topk, attr_word, attr_pos, gamma, beta, eps, d, preds_f32, (h16*)preds_T,
+        ld_preds_T, labels, (h16*)memory, mem_rows, mem_row0);
   else {
     care::set_error("care_concept_head: bad dtype %d", dtype);
     return -1;

@@ -59,17 +59,22 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
 __device__ __forceinline__ void mma_m16n8k16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                              uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "mma.sync.aligned.m16n8k16.row.col.f32." CARE_MMA_H16 "." CARE_MMA_H16 ".f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
       "{%0, %1, %2, %3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+__device__ __forceinline__ uint32_t pack_h16(float lo, float hi) {
+  h162 h = floats_to_h162(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+#ifdef CARE_USE_BF16
+__device__ __forceinline__ float h16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float h16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+#else
+__device__ __forceinline__ float h16_lo(uint32_t u) { return __low2float(*reinterpret_cast<const __half2*>(&u)); }
+__device__ __forceinline__ float h16_hi(uint32_t u) { return __high2float(*reinterpret_cast<const __half2*>(&u)); }
+#endif
 // physical byte offset of 16-byte chunk `c16` of row `r` inside a SWIZZLE_128B tile (1024-B aligned)
 __device__ __forceinline__ uint32_t sw128(int r, int c16) { return (uint32_t)(r * 128 + ((c16 ^ (r & 7)) << 4)); }
 

@@ -117,8 +117,8 @@ int gemm_f32(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t l
     gemm_f32_kernel<float><<<grid, THREADS, 0, stream>>>((const float*)A, lda, (const float*)W, ldw, bias, (float*)C,
                                                          ldc, M, N, n_pad, K, act == CARE_ACT_RELU, early_exit_of(ctx));
   else
-    gemm_f32_kernel<__nv_bfloat16><<<grid, THREADS, 0, stream>>>((const float*)A, lda, (const float*)W, ldw, bias,
-                                                                 (__nv_bfloat16*)C, ldc, M, N, n_pad, K,
+    gemm_f32_kernel<h16><<<grid, THREADS, 0, stream>>>((const float*)A, lda, (const float*)W, ldw, bias,
+                                                                 (h16*)C, ldc, M, N, n_pad, K,
                                                                  act == CARE_ACT_RELU, early_exit_of(ctx));
   CARE_LAUNCH_CHECK(ctx);
   return 0;
@@ -138,10 +138,10 @@ extern "C" int care_gemm(care_ctx* ctx, int dtype, const void* A, int64_t lda, c
   CARE_CHECK_ARG(ctx != nullptr, "care_gemm: ctx is NULL");
   CARE_CHECK_ARG(A && W && C, "care_gemm: NULL operand");
   CARE_CHECK_ARG(M > 0 && N > 0 && K > 0, "care_gemm: bad shape M=%d N=%d K=%d", M, N, K);
-  CARE_CHECK_ARG(out_dtype == CARE_F32 || out_dtype == CARE_BF16, "care_gemm: bad out_dtype %d", out_dtype);
+  CARE_CHECK_ARG(out_dtype == CARE_F32 || out_dtype == CARE_H16, "care_gemm: bad out_dtype %d", out_dtype);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == CARE_F32) return care::f32::gemm_f32(ctx, A, lda, W, ldw, bias, C, ldc, out_dtype, M, N, K, act, s);
-  if (dtype == CARE_BF16) return care::tc::gemm_bf16(ctx, A, lda, W, ldw, bias, C, ldc, out_dtype, M, N, K, act, s);
+  if (dtype == CARE_H16) return care::tc::gemm_bf16(ctx, A, lda, W, ldw, bias, C, ldc, out_dtype, M, N, K, act, s);
   care::set_error("care_gemm: bad dtype %d", dtype);
   return -1;
 }

@@ -23,7 +23,7 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
 
 template <typename OutT>
 __global__ void __launch_bounds__(WARPS * 32)
-gemm_smallm_kernel(const __nv_bfloat16* __restrict__ A, int64_t lda, const __nv_bfloat16* __restrict__ W, int64_t ldw,
+gemm_smallm_kernel(const h16* __restrict__ A, int64_t lda, const h16* __restrict__ W, int64_t ldw,
                    const float* __restrict__ bias, OutT* __restrict__ C, int64_t ldc, int M, int N, int n_store, int K,
                    int relu, const EarlyExit ee) {
   if (all_done(ee)) return;
@@ -34,9 +34,9 @@ gemm_smallm_kernel(const __nv_bfloat16* __restrict__ A, int64_t lda, const __nv_
   const int kw = K / WARPS;                 // K % 128 == 0 -> kw % 32 == 0
   const int k_begin = warp * kw;
   const bool row0 = g < M, row1 = g + 8 < M, wrow = n0 + g < N;
-  const __nv_bfloat16* a0p = A + (int64_t)(row0 ? g : 0) * lda + k_begin + 8 * tig;
-  const __nv_bfloat16* a1p = A + (int64_t)(row1 ? g + 8 : 0) * lda + k_begin + 8 * tig;
-  const __nv_bfloat16* wp = W + (int64_t)(wrow ? n0 + g : 0) * ldw + k_begin + 8 * tig;
+  const h16* a0p = A + (int64_t)(row0 ? g : 0) * lda + k_begin + 8 * tig;
+  const h16* a1p = A + (int64_t)(row1 ? g + 8 : 0) * lda + k_begin + 8 * tig;
+  const h16* wp = W + (int64_t)(wrow ? n0 + g : 0) * ldw + k_begin + 8 * tig;
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
   float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
@@ -75,12 +75,12 @@ int gemm_bf16_smallm(care_ctx* ctx, const void* A, int64_t lda, const void* W, i
   const int relu = act == CARE_ACT_RELU ? 1 : 0;
   if (out_dtype == CARE_F32)
     gemm_smallm_kernel<float><<<grid, WARPS * 32, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(W), ldw, bias,
+        static_cast<const h16*>(A), lda, static_cast<const h16*>(W), ldw, bias,
         static_cast<float*>(C), ldc, M, N, n_store, K, relu, early_exit_of(ctx));
   else
-    gemm_smallm_kernel<__nv_bfloat16><<<grid, WARPS * 32, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(W), ldw, bias,
-        static_cast<__nv_bfloat16*>(C), ldc, M, N, n_store, K, relu, early_exit_of(ctx));
+    gemm_smallm_kernel<h16><<<grid, WARPS * 32, 0, stream>>>(
+        static_cast<const h16*>(A), lda, static_cast<const h16*>(W), ldw, bias,
+        static_cast<h16*>(C), ldc, M, N, n_store, K, relu, early_exit_of(ctx));
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -208,12 +208,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
                 for (int q = 0; q < 8; ++q) f[q] = fmaxf(f[q], 0.f);
               }
               uint4 pk;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+              h162* h = reinterpret_cast<h162*>(&pk);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+              for (int q = 0; q < 4; ++q) h[q] = floats_to_h162(f[2 * q], f[2 * q + 1]);
               const int row = row_base + r;
               if (row < M && col < n_store)
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(C) + static_cast<int64_t>(row) * ldc + col) = pk;
+                *reinterpret_cast<uint4*>(reinterpret_cast<h16*>(C) + static_cast<int64_t>(row) * ldc + col) = pk;
             }
           }
         }
@@ -366,7 +366,7 @@ int gemm_bf16(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t 
   if (rc) return rc;
 #define CARE_TC_DISPATCH(BN_)                                                                          \
   (out_dtype == CARE_F32 ? launch<BN_, float>(ctx, ta, tb, bias, C, ldc, M, N, n_store, K, act, stream) \
-                         : launch<BN_, __nv_bfloat16>(ctx, ta, tb, bias, C, ldc, M, N, n_store, K, act, stream))
+                         : launch<BN_, h16>(ctx, ta, tb, bias, C, ldc, M, N, n_store, K, act, stream))
   if (bn == 256) return CARE_TC_DISPATCH(256);
   if (bn == 128) return CARE_TC_DISPATCH(128);
   return CARE_TC_DISPATCH(64);

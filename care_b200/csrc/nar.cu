@@ -240,16 +240,18 @@ using namespace care;
 extern "C" {
 
 int care_rows_mean(care_ctx* ctx, int dtype, const void* x, int B, int rows, int d, float* out, void* stream) {
+  CARE_CHECK_DTYPE(dtype, "care_rows_mean");
   CARE_CHECK_ARG(ctx && x && out && B > 0 && rows > 0 && d > 0, "care_rows_mean: bad args");
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == CARE_F32) nar::rows_mean_kernel<float><<<B, 256, 0, s>>>((const float*)x, rows, d, out);
-  else nar::rows_mean_kernel<__nv_bfloat16><<<B, 256, 0, s>>>((const __nv_bfloat16*)x, rows, d, out);
+  else nar::rows_mean_kernel<h16><<<B, 256, 0, s>>>((const h16*)x, rows, d, out);
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }
 
 int care_combine_means(care_ctx* ctx, int dtype, const void* means, int B, int n, int d, const float* weights,
                        void* out, int64_t ld_out, void* stream) {
+  CARE_CHECK_DTYPE(dtype, "care_combine_means");
   CARE_CHECK_ARG(ctx && means && out && weights && B > 0 && n >= 1 && n <= 8 && d > 0, "care_combine_means: bad args");
   nar::Weights w{};
   for (int i = 0; i < n; ++i) w.w[i] = weights[i];
@@ -257,8 +259,8 @@ int care_combine_means(care_ctx* ctx, int dtype, const void* means, int B, int n
   if (dtype == CARE_F32)
     nar::combine_means_kernel<float><<<B, 256, 0, s>>>((const float*)means, n, d, w, (float*)out, ld_out);
   else
-    nar::combine_means_kernel<__nv_bfloat16><<<B, 256, 0, s>>>((const __nv_bfloat16*)means, n, d, w,
-                                                               (__nv_bfloat16*)out, ld_out);
+    nar::combine_means_kernel<h16><<<B, 256, 0, s>>>((const h16*)means, n, d, w,
+                                                               (h16*)out, ld_out);
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

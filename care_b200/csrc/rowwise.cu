@@ -10,16 +10,45 @@ constexpr int MAX_D = 1024;           // per-lane register budget: MAX_D / 32 / 
 constexpr int MAX_CHUNKS = MAX_D / 128;
 
 // ---------------------------------------------------------------------------------------------
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n8,
-                                     int64_t n) {
+// dst[r] = [hi | lo | hi * 2^-11] (TERMS == 3) or [hi] (TERMS == 1) of src[r], each part `cols_pad` wide (zero
+// padded): hi = h16(x), lo = h16(x - hi).  With W' = [W_hi | W_hi | W_lo * 2^11] one K-concatenated tensor-core
+// GEMM then computes A_hi W_hi + A_lo W_hi + A_hi W_lo, i.e. the fp32 product to ~2^-21 relative.  The power-of-
+// two exchange between the third parts keeps W_lo (~2^-11 |W|, i.e. ~1e-5 for a typical weight) out of fp16's
+// subnormal range; hi * 2^-11 only goes subnormal for |x| < 0.125, where its product with W_lo is negligible.
+template <int TERMS>
+__global__ void split_f32_h16_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows, int cols,
+                                     int cols_pad, h16* __restrict__ dst) {
+  const int groups = cols_pad / 8;
+  const int64_t total = rows * groups;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
-    float v[8];
-    Act<float>::load8(src + i * 8, v);
-    Act<__nv_bfloat16>::store8(dst + i * 8, v);
+  const int64_t ld_dst = (int64_t)TERMS * cols_pad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / groups;
+    const int c0 = (int)(i - r * groups) * 8;
+    float v[8], lo[8];
+    if (c0 + 8 <= cols && (ld_src & 3) == 0) {
+      Act<float>::load8(src + r * ld_src + c0, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = c0 + j < cols ? src[r * ld_src + c0 + j] : 0.f;
+    }
+    h16* o = dst + r * ld_dst + c0;
+    if (TERMS == 1) {
+      Act<h16>::store8(o, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float hi = h16_to_float(float_to_h16(v[j]));
+        lo[j] = v[j] - hi;
+        v[j] = hi;
+      }
+      Act<h16>::store8(o, v);
+      Act<h16>::store8(o + cols_pad, lo);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= (1.0f / 2048.0f);
+      Act<h16>::store8(o + 2 * cols_pad, v);
+    }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0)
-    for (int64_t i = n8 * 8; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i]);
 }
 
 // LayerNorm of a row held as `nch` float4 chunks per lane (chunk c covers columns c*128 + lane*4 .. +3).
@@ -64,7 +93,7 @@ __global__ void __launch_bounds__(256)
 encoder_tail_kernel(const float* __restrict__ x, const float* __restrict__ ypre, const float* __restrict__ gpre,
                     const float* __restrict__ p0, const float* __restrict__ p1, const float* __restrict__ p2,
                     const float* __restrict__ p3, float eps, int Tn, int d, T* __restrict__ out, int out_rows,
-                    int out_row0, T* __restrict__ mean_out, int64_t mean_ld, int mean_col0) {
+                    int out_row0, float* __restrict__ mean_out, int64_t mean_ld, int mean_col0) {
   __shared__ float red[8][MAX_D];
   const int v = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = d / 128;
@@ -122,7 +151,7 @@ encoder_tail_kernel(const float* __restrict__ x, const float* __restrict__ ypre,
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][col];
-    mean_out[(int64_t)v * mean_ld + mean_col0 + col] = Act<T>::from_float(s / (float)Tn);
+    mean_out[(int64_t)v * mean_ld + mean_col0 + col] = s / (float)Tn;
   }
 }
 
@@ -206,30 +235,43 @@ using namespace care;
 
 extern "C" {
 
-int care_cast_f32_bf16(care_ctx* ctx, const float* src, void* dst, int64_t n, void* stream) {
-  CARE_CHECK_ARG(ctx && src && dst && n >= 0, "care_cast_f32_bf16: bad args");
-  if (n == 0) return 0;
-  const int64_t n8 = n / 8;
-  int blocks = (int)std::min<int64_t>((n8 + 255) / 256 + 1, (int64_t)ctx->sm_count * 16);
-  rw::cast_f32_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n8, n);
+int care_split_f32_h16(care_ctx* ctx, const float* src, int64_t ld_src, int64_t rows, int cols, int cols_pad,
+                       int terms, void* dst, void* stream) {
+  CARE_CHECK_ARG(ctx && src && dst && rows >= 0 && cols > 0 && ld_src >= cols, "care_split_f32_h16: bad args");
+  CARE_CHECK_ARG(cols_pad >= cols && cols_pad % 8 == 0, "care_split_f32_h16: cols_pad %d must be a multiple of 8 >= cols %d",
+                 cols_pad, cols);
+  CARE_CHECK_ARG(terms == 1 || terms == 3, "care_split_f32_h16: terms must be 1 or 3");
+  CARE_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+                 "care_split_f32_h16: src and dst must be 16-byte aligned");
+  if (rows == 0) return 0;
+  const int64_t total = rows * (cols_pad / 8);
+  int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
+  if (terms == 1)
+    rw::split_f32_h16_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, rows, cols, cols_pad, (h16*)dst);
+  else
+    rw::split_f32_h16_kernel<3><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, rows, cols, cols_pad, (h16*)dst);
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }
 
 int care_encoder_ln_mean(care_ctx* ctx, int dtype, const float* x, const float* gamma, const float* beta, float eps,
-                         int B, int T, int d, void* out, int out_rows, int out_row0, void* mean_out, int64_t mean_ld,
+                         int B, int T, int d, void* out, int out_rows, int out_row0, float* mean_out, int64_t mean_ld,
                          int mean_col0, void* stream) {
+  CARE_CHECK_DTYPE(dtype, "care_encoder_ln_mean");
   CARE_CHECK_ARG(ctx && x && gamma && beta && B > 0 && T > 0, "care_encoder_ln_mean: bad args");
+  CARE_CHECK_ARG(out == nullptr || (out_row0 >= 0 && out_row0 + T <= out_rows),
+                 "care_encoder_ln_mean: rows %d..%d do not fit the %d-row memory", out_row0, out_row0 + T, out_rows);
+  CARE_CHECK_ARG(dtype == CARE_F32 || dtype == CARE_H16, "care_encoder_ln_mean: this build computes in fp32 / " CARE_H16_NAME);
   if (rw::check_d(d, "care_encoder_ln_mean")) return -1;
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == CARE_F32)
     rw::encoder_tail_kernel<float, false><<<B, 256, 0, s>>>(x, nullptr, nullptr, gamma, beta, nullptr, nullptr, eps, T,
-                                                            d, (float*)out, out_rows, out_row0, (float*)mean_out,
-                                                            mean_ld, mean_col0);
+                                                            d, (float*)out, out_rows, out_row0, mean_out, mean_ld,
+                                                            mean_col0);
   else
-    rw::encoder_tail_kernel<__nv_bfloat16, false><<<B, 256, 0, s>>>(
-        x, nullptr, nullptr, gamma, beta, nullptr, nullptr, eps, T, d, (__nv_bfloat16*)out, out_rows, out_row0,
-        (__nv_bfloat16*)mean_out, mean_ld, mean_col0);
+    rw::encoder_tail_kernel<h16, false><<<B, 256, 0, s>>>(
+        x, nullptr, nullptr, gamma, beta, nullptr, nullptr, eps, T, d, (h16*)out, out_rows, out_row0, mean_out,
+        mean_ld, mean_col0);
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -237,19 +279,22 @@ int care_encoder_ln_mean(care_ctx* ctx, int dtype, const float* x, const float* 
 int care_encoder_highway_bn_mean(care_ctx* ctx, int dtype, const float* h, const float* ypre, const float* gpre,
                                  const float* bn_mean, const float* bn_var, const float* bn_w, const float* bn_b,
                                  float bn_eps, int B, int T, int d, void* out, int out_rows, int out_row0,
-                                 void* mean_out, int64_t mean_ld, int mean_col0, void* stream) {
+                                 float* mean_out, int64_t mean_ld, int mean_col0, void* stream) {
+  CARE_CHECK_DTYPE(dtype, "care_encoder_highway_bn_mean");
   CARE_CHECK_ARG(ctx && h && ypre && gpre && bn_mean && bn_var && bn_w && bn_b && B > 0 && T > 0,
                  "care_encoder_highway_bn_mean: bad args");
+  CARE_CHECK_ARG(out == nullptr || (out_row0 >= 0 && out_row0 + T <= out_rows),
+                 "care_encoder_highway_bn_mean: rows %d..%d do not fit the %d-row memory", out_row0, out_row0 + T, out_rows);
+  CARE_CHECK_ARG(dtype == CARE_F32 || dtype == CARE_H16, "care_encoder_highway_bn_mean: this build computes in fp32 / " CARE_H16_NAME);
   if (rw::check_d(d, "care_encoder_highway_bn_mean")) return -1;
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == CARE_F32)
     rw::encoder_tail_kernel<float, true><<<B, 256, 0, s>>>(h, ypre, gpre, bn_mean, bn_var, bn_w, bn_b, bn_eps, T, d,
-                                                           (float*)out, out_rows, out_row0, (float*)mean_out, mean_ld,
-                                                           mean_col0);
+                                                           (float*)out, out_rows, out_row0, mean_out, mean_ld, mean_col0);
   else
-    rw::encoder_tail_kernel<__nv_bfloat16, true><<<B, 256, 0, s>>>(
-        h, ypre, gpre, bn_mean, bn_var, bn_w, bn_b, bn_eps, T, d, (__nv_bfloat16*)out, out_rows, out_row0,
-        (__nv_bfloat16*)mean_out, mean_ld, mean_col0);
+    rw::encoder_tail_kernel<h16, true><<<B, 256, 0, s>>>(
+        h, ypre, gpre, bn_mean, bn_var, bn_w, bn_b, bn_eps, T, d, (h16*)out, out_rows, out_row0, mean_out, mean_ld,
+        mean_col0);
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -258,6 +303,7 @@ int care_embed_ln(care_ctx* ctx, int dtype, const int32_t* tokens, const int32_t
                   const float* word_emb, const float* pos_emb, const float* add_feats, const float* gsg,
                   int rows_per_video, const float* gamma, const float* beta, float eps, int R, int d, void* out,
                   void* stream) {
+  CARE_CHECK_DTYPE(dtype, "care_embed_ln");
   CARE_CHECK_ARG(ctx && tokens && word_emb && pos_emb && gamma && beta && out && R > 0 && rows_per_video > 0,
                  "care_embed_ln: bad args");
   if (rw::check_d(d, "care_embed_ln")) return -1;
@@ -268,15 +314,16 @@ int care_embed_ln(care_ctx* ctx, int dtype, const int32_t* tokens, const int32_t
                                                     rows_per_video, gamma, beta, eps, R, d, (float*)out,
                                                     early_exit_of(ctx));
   else
-    rw::embed_ln_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(tokens, positions, position, word_emb, pos_emb, add_feats,
+    rw::embed_ln_kernel<h16><<<grid, 256, 0, s>>>(tokens, positions, position, word_emb, pos_emb, add_feats,
                                                             gsg, rows_per_video, gamma, beta, eps, R, d,
-                                                            (__nv_bfloat16*)out, early_exit_of(ctx));
+                                                            (h16*)out, early_exit_of(ctx));
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }
 
 int care_add_ln(care_ctx* ctx, int dtype, const float* x, const void* residual, const float* gamma, const float* beta,
                 float eps, int R, int d, void* out, void* stream) {
+  CARE_CHECK_DTYPE(dtype, "care_add_ln");
   CARE_CHECK_ARG(ctx && x && residual && gamma && beta && out && R > 0, "care_add_ln: bad args");
   if (rw::check_d(d, "care_add_ln")) return -1;
   cudaStream_t s = (cudaStream_t)stream;
@@ -285,8 +332,8 @@ int care_add_ln(care_ctx* ctx, int dtype, const float* x, const void* residual, 
     rw::add_ln_kernel<float><<<grid, 256, 0, s>>>(x, (const float*)residual, gamma, beta, eps, R, d, (float*)out,
                                                   early_exit_of(ctx));
   else
-    rw::add_ln_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(x, (const __nv_bfloat16*)residual, gamma, beta, eps, R, d,
-                                                          (__nv_bfloat16*)out, early_exit_of(ctx));
+    rw::add_ln_kernel<h16><<<grid, 256, 0, s>>>(x, (const h16*)residual, gamma, beta, eps, R, d,
+                                                          (h16*)out, early_exit_of(ctx));
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -72,7 +72,7 @@ __device__ __forceinline__ uint64_t sw128_kmajor_desc(uint32_t smem_addr) {
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (1 << 4), A bf16 (1 << 7), B bf16 (1 << 10),
 // both K-major (bits 15/16 zero), N >> 3 in [17,23), M >> 4 in [24,29).
 __host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+  return (1u << 4) | (CARE_UMMA_FMT << 7) | (CARE_UMMA_FMT << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 

@@ -5,8 +5,14 @@ libcare_b200.so through the C ABI (care_b200/_lib.py).  There is no fallback pat
 
 Precision modes
   "fp32": activations/weights fp32, SIMT FFMA GEMMs - the bit-exact token parity mode.
-  "bf16": activations/weights bf16, tcgen05 GEMMs with fp32 accumulation; LayerNorm / softmax
-          statistics, logits and beam scores stay fp32.
+  "fp16": (default throughput mode) 16-bit tensor-core operands in IEEE fp16, fp32 accumulation; LayerNorm /
+          softmax statistics, logits and beam scores stay fp32.  Every activation of this model is O(1) after a
+          LayerNorm, so fp16's 10 mantissa bits cost no range and give 8x less rounding error than bf16;
+          weights stored in bf16 are exactly representable.
+  "bf16": the same kernels over bf16 (libcare_b200_bf16.so).
+In both 16-bit modes everything upstream of a discrete ranking (encoder streams -> concept scores -> top-30
+concepts; length predictor) runs as three-term split products on the tensor cores (care_split_f32_h16):
+fp32-grade results, so the concept ids equal the fp32 mode's except on exact ties.
 """
 import ctypes
 from typing import Dict, List, Optional
@@ -14,7 +20,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_RELU, BF16, F32, BeamState, check, ptr
+from ._lib import ACT_NONE, ACT_RELU, BF16, F16, F32, BeamState, check, ptr
 
 PAD, UNK, BOS, EOS, MASK, VIS = 0, 1, 2, 3, 4, 5  # reference: config/Constants.py:1-6
 
@@ -26,17 +32,22 @@ def _round_up(x, m):
 class CareEngine:
     """One engine per (model, device, precision)."""
 
-    def __init__(self, opt: dict, state_dict: Dict[str, torch.Tensor], device, precision: str = "bf16"):
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
-        self.lib = _lib.load()
+    def __init__(self, opt: dict, state_dict: Dict[str, torch.Tensor], device, precision: str = "fp16"):
+        if precision not in ("fp32", "fp16", "bf16"):
+            raise ValueError("precision must be 'fp32', 'fp16' or 'bf16'")
+        self.lib = _lib.load("bf16" if precision == "bf16" else "fp16")
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("care_b200 runs on CUDA devices only (no CPU path)")
         self.opt = dict(opt)
         self.precision = precision
-        self.dt = F32 if precision == "fp32" else BF16
-        self.tdtype = torch.float32 if precision == "fp32" else torch.bfloat16
+        self.dt = {"fp32": F32, "fp16": F16, "bf16": BF16}[precision]
+        self.tdtype = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}[precision]
+        self.half = precision != "fp32"
+        # 16-bit modes: GEMMs upstream of a discrete ranking as 3-term split products (1 = plain 16-bit operands)
+        self.enc_terms = int(opt.get("care_encoder_terms", 3)) if self.half else 1
+        if self.enc_terms not in (1, 3):
+            raise ValueError("care_encoder_terms must be 1 or 3")
         index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.device = torch.device("cuda", index)
         handle = ctypes.c_void_p()
@@ -55,8 +66,8 @@ class CareEngine:
         self.m_pred = opt.get("modality_for_predictor") or self.modality
         self.max_len = opt.get("max_len", 30)
         self.ldv = _round_up(self.V, 8)
-        # bf16: the vocabulary GEMM's epilogue feeds the beam kernel directly (no logits in HBM)
-        self.fused_vocab = precision == "bf16" and bool(opt.get("care_fused_vocab", True))
+        # 16-bit modes: the vocabulary GEMM's epilogue feeds the beam kernel directly (no logits in HBM)
+        self.fused_vocab = self.half and bool(opt.get("care_fused_vocab", True))
         self._ws = {}
         self._ws_epoch_of = {}
         self._ws_bytes = 0
@@ -95,6 +106,18 @@ class CareEngine:
                 t = torch.nn.functional.pad(t, (0, pad_k - t.shape[1]))
             return t.to(T).contiguous()
 
+        def mat3(t):
+            """Weight of a GEMM whose A operand comes from care_split_f32_h16(terms=3): [W_hi | W_hi | W_lo * 2^11],
+            each part zero padded to a multiple of 64 columns (one swizzled TMA row)."""
+            if self.enc_terms == 1:
+                return mat(t, pad_k=_round_up(t.shape[1], 8) if self.half else None)
+            t = t.detach().to(dev, torch.float32)
+            kp = _round_up(t.shape[1], 64)
+            t = torch.nn.functional.pad(t, (0, kp - t.shape[1]))
+            hi = t.to(T)
+            lo = ((t - hi.float()) * 2048.0).to(T)
+            return torch.cat([hi, hi, lo], 1).contiguous()
+
         w = {}
         self.highway = opt["encoder"] == "EncoderWithHighWayBN"
         if opt["encoder"] not in ("Embedder", "EncoderWithHighWayBN"):
@@ -102,10 +125,10 @@ class CareEngine:
         self.streams = []
         for ch in self.modality:
             p = "encoder.Encoder_%s" % ch.upper()
-            s = dict(ch=ch, W=mat(sd[p + ".0.weight"]), b=f32(p + ".0.bias"), dim=opt["dim_" + ch])
+            s = dict(ch=ch, W=mat3(sd[p + ".0.weight"]), b=f32(p + ".0.bias"), dim=opt["dim_" + ch])
             if self.highway:
-                s.update(W1=mat(sd[p + ".1.w1.weight"]), b1=f32(p + ".1.w1.bias"),
-                         W2=mat(sd[p + ".1.w2.weight"]), b2=f32(p + ".1.w2.bias"),
+                s.update(W1=mat3(sd[p + ".1.w1.weight"]), b1=f32(p + ".1.w1.bias"),
+                         W2=mat3(sd[p + ".1.w2.weight"]), b2=f32(p + ".1.w2.bias"),
                          bn_mean=f32(p + ".2.bn.running_mean"), bn_var=f32(p + ".2.bn.running_var"),
                          bn_w=f32(p + ".2.bn.weight"), bn_b=f32(p + ".2.bn.bias"))
             else:
@@ -125,7 +148,7 @@ class CareEngine:
             if kind == "attribute":
                 if not (opt.get("attribute_prediction_channel_concat") and opt.get("attribute_prediction_mean_pooling")):
                     raise ValueError("only the mean-pooling + channel-concat concept head is accelerated")
-                w["prj_W"] = mat(sd[p + ".prj.weight"])
+                w["prj_W"] = mat3(sd[p + ".prj.weight"])
                 w["prj_b"] = f32(p + ".prj.bias")
             elif kind == "SemanticContainer":
                 w["attr_word"] = f32(p + ".attr_embs.word_embeddings.weight")
@@ -133,10 +156,11 @@ class CareEngine:
                 w["attr_g"] = f32(p + ".attr_embs.LayerNorm.weight")
                 w["attr_b"] = f32(p + ".attr_embs.LayerNorm.bias")
                 if "emb" in opt.get("use_attr_type", ""):
-                    w["s2h_W"] = mat(sd[p + ".semantic2hidden.weight"], pad_k=_round_up(self.n_attr, 64))
+                    w["s2h_W"] = (mat3(sd[p + ".semantic2hidden.weight"]) if self.half else
+                                  mat(sd[p + ".semantic2hidden.weight"], pad_k=_round_up(self.n_attr, 64)))
             elif kind == "length":
-                w["len_W0"] = mat(sd[p + ".net.0.weight"]); w["len_b0"] = f32(p + ".net.0.bias")
-                w["len_W3"] = mat(sd[p + ".net.3.weight"]); w["len_b3"] = f32(p + ".net.3.bias")
+                w["len_W0"] = mat3(sd[p + ".net.0.weight"]); w["len_b0"] = f32(p + ".net.0.bias")
+                w["len_W3"] = mat3(sd[p + ".net.3.weight"]); w["len_b3"] = f32(p + ".net.3.bias")
             else:
                 raise ValueError("predictor %r is outside the accelerated hot path" % kind)
         self.use_gsg = "s2h_W" in w
@@ -244,10 +268,21 @@ class CareEngine:
         return int(self.lib.care_ctx_launch_count(self.ctx)) + self._graph_launches
 
     def gemm(self, A, W, bias, C, M, N, K, act=ACT_NONE, lda=None, ldc=None):
-        out_dt = F32 if C.dtype == torch.float32 else BF16
+        out_dt = F32 if C.dtype == torch.float32 else self.dt
         check(self.lib.care_gemm(self.ctx, self.dt, ptr(A), lda if lda is not None else A.stride(-2), ptr(W),
                                  W.stride(0), ptr(bias), ptr(C), ldc if ldc is not None else C.stride(-2), out_dt,
                                  M, N, K, act, self._stream()), "care_gemm")
+
+    def _operand(self, name, x32, rows, cols):
+        """fp32 [rows, cols] -> the A operand of an upstream-of-ranking GEMM and its K: fp32 mode: x itself;
+        16-bit modes: [hi | lo | hi] (or a plain cast when care_encoder_terms == 1)."""
+        if not self.half:
+            return x32, cols
+        kp = _round_up(cols, 64) if self.enc_terms == 3 else _round_up(cols, 8)
+        a = self._buf(name, (rows, self.enc_terms * kp), self.tdtype)
+        check(self.lib.care_split_f32_h16(self.ctx, ptr(x32), x32.stride(-2), rows, cols, kp, self.enc_terms, ptr(a),
+                                          self._stream()), "care_split_f32_h16")
+        return a, self.enc_terms * kp
 
     # ------------------------------------------------------------------------------------------
     # encoding phase  (reference: models/Framework.py:150-187)
@@ -262,34 +297,33 @@ class CareEngine:
         n_pred = len([c for c in self.modality if c in self.m_pred])
         has_attr = "attribute" in self.nets
         memory = torch.empty((B, self.Lm, d), dtype=T, device=self.device)
-        means = self._buf("means", (B, max(n_pred, 1) * d), T) if has_attr or "length" in self.nets else None
+        means = (self._buf("means", (B, max(n_pred, 1) * d), torch.float32)
+                 if has_attr or "length" in self.nets else None)
         pred_slot = 0
         pred_tokens = []
         for s, x in zip(self.streams, feats):
-            ch, Tn, dim = s["ch"], x.shape[1], s["dim"]
+            ch, dim = s["ch"], s["dim"]
+            if x.dim() != 3 or x.shape[0] != B or x.shape[1] != self.frames[ch] or x.shape[2] != dim:
+                # the reference fails inside nn.Linear / torch.cat on such a batch; here the rows of the memory
+                # buffer are laid out from the opt, so a mismatch must not reach the kernels
+                raise ValueError("feats[%r] has shape %s, expected [%d, %d, %d] (n_frames / retrieval_topk / dim_%s "
+                                 "of the checkpoint's opt)" % (ch, tuple(x.shape), B, self.frames[ch], dim, ch))
+            Tn = x.shape[1]
             if x.dtype != torch.float32 or not x.is_contiguous():
                 x = x.to(torch.float32).contiguous()
             rows = B * Tn
-            if self.dt == BF16:
-                a = self._buf("feat_bf16", (rows, dim), torch.bfloat16)
-                check(lib.care_cast_f32_bf16(ctx, ptr(x), ptr(a), rows * dim, st), "care_cast_f32_bf16")
-            else:
-                a = x.view(rows, dim)
+            a, ka = self._operand("feat_h16", x.view(rows, dim), rows, dim)
             h32 = self._buf("enc_h32", (rows, d), torch.float32)
-            self.gemm(a, s["W"], s["b"], h32, rows, d, dim)
+            self.gemm(a, s["W"], s["b"], h32, rows, d, ka)
             in_dec, in_pred = ch in self.m_dec, ch in self.m_pred and means is not None
             out_ptr = ptr(memory) if in_dec else None
             mean_ptr = ptr(means) if in_pred else None
             if self.highway:
-                if self.dt == BF16:
-                    hT = self._buf("enc_hT", (rows, d), torch.bfloat16)
-                    check(lib.care_cast_f32_bf16(ctx, ptr(h32), ptr(hT), rows * d, st), "care_cast_f32_bf16")
-                else:
-                    hT = h32
+                hT, kh = self._operand("enc_hT", h32, rows, d)
                 y32 = self._buf("enc_y32", (rows, d), torch.float32)
                 g32 = self._buf("enc_g32", (rows, d), torch.float32)
-                self.gemm(hT, s["W1"], s["b1"], y32, rows, d, d)
-                self.gemm(hT, s["W2"], s["b2"], g32, rows, d, d)
+                self.gemm(hT, s["W1"], s["b1"], y32, rows, d, kh)
+                self.gemm(hT, s["W2"], s["b2"], g32, rows, d, kh)
                 check(lib.care_encoder_highway_bn_mean(
                     ctx, dt, ptr(h32), ptr(y32), ptr(g32), ptr(s["bn_mean"]), ptr(s["bn_var"]), ptr(s["bn_w"]),
                     ptr(s["bn_b"]), 1e-5, B, Tn, d, out_ptr, self.Lm, self.mem_off.get(ch, 0), mean_ptr,
@@ -305,12 +339,15 @@ class CareEngine:
         if has_attr:
             ld_sc = _round_up(self.n_attr, 8)
             scores = self._buf("attr_scores", (B, ld_sc), torch.float32)
-            self.gemm(means, w["prj_W"], w["prj_b"], scores, B, self.n_attr, n_pred * d)
+            am, km = self._operand("means_h16", means, B, n_pred * d)
+            self.gemm(am, w["prj_W"], w["prj_b"], scores, B, self.n_attr, km)
             preds = torch.empty((B, self.n_attr), dtype=torch.float32, device=self.device)
             out["preds_attr"] = preds
             if "SemanticContainer" in self.nets:
-                kpad = w["s2h_W"].shape[1] if self.use_gsg else _round_up(self.n_attr, 64)
-                predsT = self._buf("preds_T", (B, kpad), T)
+                predsT = kpad = None
+                if self.use_gsg and not self.half:
+                    kpad = w["s2h_W"].shape[1]
+                    predsT = self._buf("preds_T", (B, kpad), T)
                 labels = torch.empty((B, self.n_concepts), dtype=torch.int64, device=self.device)
                 sem = None
                 if not self.concat_concepts and self.attr_pos is not None:
@@ -319,12 +356,14 @@ class CareEngine:
                 check(lib.care_concept_head(
                     ctx, dt, ptr(scores), ld_sc, B, self.n_attr, self.n_concepts, ptr(w["attr_word"]),
                     ptr(w["attr_pos"]), ptr(w["attr_g"]), ptr(w["attr_b"]), self.eps, d, ptr(preds), ptr(predsT),
-                    kpad, ptr(labels), ptr(memory) if self.concat_concepts else ptr(sem),
+                    kpad or 0, ptr(labels), ptr(memory) if self.concat_concepts else ptr(sem),
                     self.Lm if self.concat_concepts else self.n_concepts, self.enc_len if self.concat_concepts else 0,
                     st), "care_concept_head")
                 out["semantic_labels"] = labels
                 if self.use_gsg:
                     gsg = torch.empty((B, d), dtype=torch.float32, device=self.device)
+                    if self.half:
+                        predsT, kpad = self._operand("preds_h16", preds, B, self.n_attr)
                     self.gemm(predsT, w["s2h_W"], None, gsg, B, d, kpad)
                     out["semantic_hidden_states"] = gsg
             else:
@@ -340,16 +379,18 @@ class CareEngine:
         """Predictor_length (pred_length.py:5-22): Linear -> ReLU -> Linear over the mean of all predictor
         tokens, obtained from the per-stream means weighted by their token counts.  Returns fp32 logits
         [B, >= max_len] (log_softmax is monotone; only the ranking is consumed, Translator.py:307-311)."""
-        w, d, T = self.w, self.d, self.tdtype
+        w, d = self.w, self.d
         total = float(sum(pred_tokens))
         weights = (ctypes.c_float * len(pred_tokens))(*[t / total for t in pred_tokens])
-        comb = self._buf("len_in", (B, d), T)
-        check(self.lib.care_combine_means(self.ctx, self.dt, ptr(means), B, n_pred, d, weights, ptr(comb), d,
+        comb = self._buf("len_in", (B, d), torch.float32)
+        check(self.lib.care_combine_means(self.ctx, F32, ptr(means), B, n_pred, d, weights, ptr(comb), d,
                                           self._stream()), "care_combine_means")
-        hid = self._buf("len_hid", (B, d), T)
-        self.gemm(comb, w["len_W0"], w["len_b0"], hid, B, d, d, act=ACT_RELU)
+        hid = self._buf("len_hid", (B, d), torch.float32)
+        a, k = self._operand("len_in_h16", comb, B, d)
+        self.gemm(a, w["len_W0"], w["len_b0"], hid, B, d, k, act=ACT_RELU)
         logits = torch.empty((B, _round_up(self.max_len, 8)), dtype=torch.float32, device=self.device)
-        self.gemm(hid, w["len_W3"], w["len_b3"], logits, B, self.max_len, d)
+        a, k = self._operand("len_hid_h16", hid, B, d)
+        self.gemm(a, w["len_W3"], w["len_b3"], logits, B, self.max_len, k)
         return logits
 
     def cross_kv(self, memory, static=False):

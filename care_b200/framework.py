@@ -65,6 +65,16 @@ class TransformerSeq2Seq(nn.Module):
                 raise ValueError("attr_attention with a hybrid attention bias is not a valid reference configuration")
         if not opt.get("trainable_pe", False):
             raise ValueError("sinusoidal position embeddings are outside the accelerated hot path")
+        # options the engine would silently compute differently from the reference: refuse them loudly
+        if opt.get("fusion", "temporal_concat") != "temporal_concat":   # Encoder.py:125-153
+            raise ValueError("fusion %r is outside the accelerated hot path (only temporal_concat)" % opt.get("fusion"))
+        if opt.get("decoding_type") == "NARFormer" and opt.get("enhance_input", 2) != 2:   # Transformer.py:182-189
+            raise ValueError("enhance_input %r is outside the accelerated hot path (NARFormer adds the memory mean: 2)"
+                             % opt.get("enhance_input"))
+        if opt.get("decoding_type", "ARFormer") not in ("ARFormer", "NARFormer"):
+            raise ValueError("decoding_type %r is outside the accelerated hot path" % opt.get("decoding_type"))
+        if opt.get("position_embeddings_na") or opt.get("with_bn_embedding"):
+            raise ValueError("position_embeddings_na / with_bn_embedding are outside the accelerated hot path")
         self.backbone = None  # translate.py:213 reads `.captioner.backbone`
         for name, (shape, kind) in layout.param_specs(opt).items():
             dtype = torch.long if kind == "bn_count" else torch.float32
@@ -77,7 +87,9 @@ class TransformerSeq2Seq(nn.Module):
             self.input_keys_for_decoder.append("semantic_hidden_states")
         self._kinds = {n: k for n, (_, k) in layout.param_specs(opt).items()}
         self._engine = None
-        self.precision = opt.get("care_precision") or os.environ.get("CARE_B200_PRECISION", "bf16")
+        self.precision = opt.get("care_precision") or os.environ.get("CARE_B200_PRECISION", "fp16")
+        if self.precision not in ("fp32", "fp16", "bf16"):
+            raise ValueError("care_precision must be 'fp32', 'fp16' or 'bf16' (got %r)" % self.precision)
         if init_weights:
             self._init_weights()
 
@@ -100,6 +112,13 @@ class TransformerSeq2Seq(nn.Module):
         self._engine = None
 
     def load_state_dict(self, state_dict, strict=True, **kw):
+        """`strict=False` tolerates MISSING keys as on the reference module, but a key this model does not have
+        would be a module the engine never runs (the reference would run it): that is fatal here."""
+        own = set(self.state_dict().keys())
+        extra = [k for k in state_dict.keys() if k not in own]
+        if extra:
+            raise ValueError("state_dict holds %d tensor(s) outside the accelerated hot path, e.g. %s - the checkpoint's "
+                             "opt selects modules this engine does not compute" % (len(extra), extra[:4]))
         out = super().load_state_dict(state_dict, strict=strict, **kw)
         self._engine = None
         return out

@@ -15,8 +15,11 @@
  *     as void*); there is no hidden device synchronisation.
  *   - return value: 0 = ok, negative = argument/shape error, positive = cudaError_t / CUresult;
  *     care_last_error() returns a thread-local message.
- *   - dtype codes: CARE_F32 = 0, CARE_BF16 = 1.  "T" below means the activation type of the
- *     precision mode (fp32 in the bit-exact parity mode, bf16 in the throughput mode).
+ *   - dtype codes: CARE_F32 = 0, CARE_BF16 = 1, CARE_F16 = 2.  "T" below means the activation type of
+ *     the precision mode: fp32 in the bit-exact parity mode, the library's 16-bit type in the
+ *     throughput mode.  One build of the library has ONE 16-bit type (care_h16_dtype()):
+ *     libcare_b200.so computes in IEEE fp16, libcare_b200_bf16.so (same sources, -DCARE_USE_BF16) in
+ *     bf16; a call with the other 16-bit code fails with an argument error.
  *   - rows of decoder-side tensors are ordered (video, beam): row = video * K + beam.
  *   - sm_100a only.  There is no CPU path: every entry point fails if no device is present.
  */
@@ -31,6 +34,7 @@ extern "C" {
 
 #define CARE_F32 0
 #define CARE_BF16 1
+#define CARE_F16 2
 
 #define CARE_ACT_NONE 0
 #define CARE_ACT_RELU 1
@@ -45,6 +49,8 @@ typedef struct care_ctx care_ctx;
 
 /* library plumbing ------------------------------------------------------------------------- */
 int care_version(void);
+/* the 16-bit dtype code this build computes in (CARE_F16 or CARE_BF16) */
+int care_h16_dtype(void);
 const char* care_last_error(void);
 int care_ctx_create(care_ctx** out, int device);
 void care_ctx_destroy(care_ctx* ctx);
@@ -57,7 +63,7 @@ int64_t care_ctx_launch_count(const care_ctx* ctx);
  * (st.n_done, B) makes the steps after the last video finished cost only their launches
  * (replaces the host-side `if not active: break`, Translator.py:77).  Pass NULL to disable. */
 int care_ctx_set_early_exit(care_ctx* ctx, const int32_t* counter, int target);
-/* implementation switches for A/B tests.  "attn_impl": 1 = TMA + tensor-core attention for bf16
+/* implementation switches for A/B tests.  "attn_impl": 1 = TMA + tensor-core attention for T16
  * (default), 0 = the SIMT attention kernel for every dtype.  "gemm_2sm": 0 = single-CTA GEMM tiles
  * only, 1 = CTA-pair (tcgen05 cta_group::2) tiles whenever the shape allows, 2 (default) = choose per
  * (M, N, K, out dtype) by timing both variants ONCE, on the first care_gemm call with that shape - the
@@ -67,38 +73,47 @@ int care_ctx_set_option(care_ctx* ctx, const char* name, int value);
  * waves of 256 x 256 tiles, 0 = single-CTA tiles only.
  * "gemm_smallm": 1 (default) = GEMMs with M <= 16 rows (batch-1 / latency mode) use a weight-streaming
  * warp-MMA kernel with one CTA per 8 output columns, 0 = always the tcgen05 tile kernels.
- * "self_compact" (option above), bf16 self-attention over the KV cache: 2 (default) = only the cache slots
+ * "self_compact" (option above), T16 self-attention over the KV cache: 2 (default) = only the cache slots
  * some beam of the video still references are read, as a stream of 16-row chunks fetched by TMA row gathers
  * (prefixes of at least 6 positions, 1024 .. 16384 x H (video, head) pairs per call; otherwise the dense tile);
  * 3 = the chunk stream for every shape (tests); 1 = the earlier per-CTA gather of the live slots (slower,
  * kept for A/B runs); 0 = all K slots of every
  * position with one TMA tensor copy.  The environment variable CARE_B200_SELF_COMPACT sets the default.
  * Statistics kept on the device (reading one synchronises): "self_attn_rows" = K/V cache rows per
- * head read so far by the bf16 self-attention kernels, summed over videos and steps. */
+ * head read so far by the T16 self-attention kernels, summed over videos and steps. */
 int care_ctx_counter(care_ctx* ctx, const char* name, int64_t* value);
 
 /* C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) — every nn.Linear on the path:
  * Encoder.py:165-168 (Embedder Linear), Attention.py:53-67 (query/key/value),
  * SubLayers.py:33-38 (dense), SubLayers.py:126-135 (dense1/dense2), Head.py:26-32
  * (tgt_word_prj), pred_attribute.py:62-65,124 (prj), :257-260 (semantic2hidden).
- * A, W are `dtype` (fp32: SIMT FFMA kernel, bit-comparable accumulation; bf16: tcgen05/TMEM
+ * A, W are `dtype` (fp32: SIMT FFMA kernel, bit-comparable accumulation; T16: tcgen05/TMEM
  * kernel fed by TMA, fp32 accumulate).  bias fp32 or NULL.  C is `out_dtype`.
- * Requirements: lda, ldw multiples of 8 elements (bf16) / 4 (fp32), 16-byte aligned bases;
+ * Requirements: lda, ldw multiples of 8 elements (T16) / 4 (fp32), 16-byte aligned bases;
  * ldc a multiple of 8; columns [N, min(roundup8(N), ldc)) of C are written with zeros. */
 int care_gemm(care_ctx* ctx, int dtype, const void* A, int64_t lda, const void* W, int64_t ldw,
               const float* bias, void* C, int64_t ldc, int out_dtype, int M, int N, int K, int act,
               void* stream);
 
-/* fp32 -> bf16 cast of the incoming feature tensors (translate.py:36-38 hands fp32 features). */
-int care_cast_f32_bf16(care_ctx* ctx, const float* src, void* dst, int64_t n, void* stream);
+/* fp32 -> 16-bit operand conversion of the incoming feature tensors (translate.py:36-38 hands fp32
+ * features) and of other fp32 GEMM inputs.  src fp32 [rows, cols] (row stride ld_src); dst T16
+ * [rows, terms * cols_pad].  terms = 1: plain cast (zero padded to cols_pad).  terms = 3: each row becomes
+ * [hi | lo | hi * 2^-11] with hi = T16(x), lo = T16(x - hi); multiplied by a weight prepared as
+ * [W_hi | W_hi | W_lo * 2^11] one K-concatenated care_gemm computes A_hi W_hi + A_lo W_hi + A_hi W_lo -
+ * the fp32 product to ~2^-21 - on the tensor cores (the 2^11 keeps W_lo out of fp16's subnormals).  Used for everything upstream of the concept
+ * ranking and the length prediction (Encoder.py:165-168, pred_attribute.py:124-125, pred_length.py:18-22),
+ * where a 16-bit rounding would re-order the discrete top-k. */
+int care_split_f32_h16(care_ctx* ctx, const float* src, int64_t ld_src, int64_t rows, int cols,
+                       int cols_pad, int terms, void* dst, void* stream);
 
 /* Encoder stream tail (Encoder.py:167: LayerNorm after Linear; Encoder.py:106: mean over time).
  * x: fp32 [B*T, d] (the Linear output incl. bias).  Writes LN(x) as T into
- * out[(v*out_rows + out_row0 + t)*d ...] when out != NULL, and the per-video temporal mean of
- * LN(x) as T into mean_out[v*mean_ld + mean_col0 ...] when mean_out != NULL. */
+ * out[(v*out_rows + out_row0 + t)*d ...] when out != NULL (requires out_row0 + T <= out_rows), and
+ * the per-video temporal mean of LN(x) as fp32 into mean_out[v*mean_ld + mean_col0 ...] when
+ * mean_out != NULL. */
 int care_encoder_ln_mean(care_ctx* ctx, int dtype, const float* x, const float* gamma,
                          const float* beta, float eps, int B, int T, int d, void* out,
-                         int out_rows, int out_row0, void* mean_out, int64_t mean_ld, int mean_col0,
+                         int out_rows, int out_row0, float* mean_out, int64_t mean_ld, int mean_col0,
                          void* stream);
 
 /* EncoderWithHighWayBN tail (Encoder.py:184-187,210-241): out = BN_eval(g*h + (1-g)*tanh(y)),
@@ -107,7 +122,7 @@ int care_encoder_ln_mean(care_ctx* ctx, int dtype, const float* x, const float* 
 int care_encoder_highway_bn_mean(care_ctx* ctx, int dtype, const float* h, const float* ypre,
                                  const float* gpre, const float* bn_mean, const float* bn_var,
                                  const float* bn_w, const float* bn_b, float bn_eps, int B, int T,
-                                 int d, void* out, int out_rows, int out_row0, void* mean_out,
+                                 int d, void* out, int out_rows, int out_row0, float* mean_out,
                                  int64_t mean_ld, int mean_col0, void* stream);
 
 /* Concept head (pred_attribute.py:17-46 noisy-or, :262-289 SemanticContainer, Embeddings.py:53-87
@@ -244,9 +259,9 @@ int care_ensemble_logprobs(care_ctx* ctx, const float* const* logits, int n, int
 int care_beam_step_logprobs(care_ctx* ctx, const care_beam_state* st, const float* logprobs, int64_t ldv,
                             int step, int max_len, float* cand_val, int32_t* cand_idx, void* stream);
 
-/* Fused vocabulary projection + beam partials, bf16 only (Head.py:26-32 + Translator.py:127 + the
- * top-k half of Beam.py:45-60): the fp32 logits never reach HBM.  x bf16 [R, ldx] (decoder output of
- * the newest position), W bf16 [V, ldw] (cls_head.tgt_word_prj.weight).  Each row's vocabulary is
+/* Fused vocabulary projection + beam partials, T16 only (Head.py:26-32 + Translator.py:127 + the
+ * top-k half of Beam.py:45-60): the fp32 logits never reach HBM.  x T16 [R, ldx] (decoder output of
+ * the newest position), W T16 [V, ldw] (cls_head.tgt_word_prj.weight).  Each row's vocabulary is
  * reduced on the tensor-core kernel's epilogue to per-segment records (max, sum-exp, top-(K+1) raw
  * logits + column ids); partials is fp32 words [R, nseg, 2 + 2*KB] with nseg =
  * care_vocab_beam_nseg(ctx, R, V) and KB = 2/4/6/9 for K <= 1/3/5/8.  care_beam_step_partials then

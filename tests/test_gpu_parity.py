@@ -1,9 +1,11 @@
 """End-to-end parity of the CUDA path (through the reference-shaped API and the C ABI) against
 (1) the golden outputs of the unmodified reference (tests/golden/*.json) and (2) the CPU oracle run
 on the same seeded inputs.  fp32 mode: token sequences and concept ids exact (any mismatch must be
-explained by an oracle decision margin below 1e-4, i.e. an fp32 summation-order tie).  bf16 mode:
-logits within 1e-2 relative, per-step log-probs within 1e-3 of the bf16-rounded-weights oracle
-(tolerances from BASELINE.json `north_star`)."""
+explained by an oracle decision margin below 1e-4, i.e. an fp32 summation-order tie).  16-bit mode
+(fp16 operands, the default and benchmarked mode): logits within 1e-2 relative and per-step log-probs
+within 1e-3 (scaled by the logit magnitude) of the oracle - the tolerances of BASELINE.json `north_star` -
+and the measured sequence exact-match on 512 videos with trained-like weights (see
+test_h16_exact_match_512 and DESIGN.md section 5 for what that number is and is not)."""
 import os
 
 import pytest
@@ -15,7 +17,17 @@ from tests.helpers import load_golden, rebuild_case
 pytestmark = pytest.mark.gpu
 
 AR_CASES = ["cfg1_plain", "cfg1_sharp", "cfg2_plain", "cfg2_sharp", "cfg2_sharp_k3_nbest3_a07",
-            "cfg2_sharp_greedy", "cfg3_sharp", "cfg4_sharp", "cab_sharp", "cab_attr2cross_sharp"]
+            "cfg2_sharp_greedy", "cfg3_sharp", "cfg4_sharp", "cab_sharp", "cab_attr2cross_sharp",
+            "cfg4_plain", "cfg3_trained", "cfg4_trained"]
+
+
+def _round_weights(sd, precision):
+    """The oracle's weights for a 16-bit comparison: the GEMM weight matrices as the engine stores them."""
+    if precision == "fp32":
+        return sd
+    dt = torch.float16 if precision.startswith("fp16") else torch.bfloat16
+    return {k: (v.to(dt).float() if v.dim() == 2 and "embeddings" not in k and "hybrid_bias" not in k else v)
+            for k, v in sd.items()}
 
 
 def _gpu_model(opt, sd, precision):
@@ -59,12 +71,11 @@ def test_fp32_matches_reference_golden(name):
             if labels[v].tolist() != rec["semantic_labels"][v]:
                 # only an fp32 summation-order tie may reorder concepts
                 assert gaps[v] < 1e-6, "concept ids differ with a clear margin %g (video %d)" % (gaps[v], v)
-                assert sorted(labels[v].tolist())[1:-1] == sorted(rec["semantic_labels"][v])[1:-1] or True
                 tie_videos.add(v)
         assert (enc["preds_attr"].cpu() - p).abs().max().item() < 2e-6
         if "semantic_hidden_states" in o_enc:
             assert (enc["semantic_hidden_states"].cpu() - o_enc["semantic_hidden_states"]).abs().max().item() < 1e-4
-        if "semantic_embs" in o_enc and v not in tie_videos:
+        if "semantic_embs" in o_enc:
             sem_err = (enc["semantic_embs"].float().cpu() - o_enc["semantic_embs"]).abs().amax(dim=(1, 2))
             assert all(float(sem_err[i]) < 1e-4 for i in range(len(sem_err)) if i not in tie_videos)
     for v in range(mem_err.shape[0]):
@@ -80,9 +91,11 @@ def test_fp32_matches_reference_golden(name):
                 assert v in tie_videos or abs(a - b) < 1e-4 * max(1.0, abs(b)), (v, a, b)
         elif v not in tie_videos:
             assert margins[v] < 1e-4, "video %d differs although the oracle margin is %g" % (v, margins[v])
-    print("\n%s fp32: %d/%d sequences identical to the reference (concept-tie videos: %s)" % (
-        name, exact, len(hyps), sorted(tie_videos)))
-    assert exact >= 0.8 * len(hyps), "only %d/%d sequences exact" % (exact, len(hyps))
+    near_tie = [v for v in range(len(hyps)) if hyps[v] != rec["hyps"][v]]
+    print("\n%s fp32: %d/%d sequences identical to the reference (concept-tie videos: %s, near-tie videos: %s)" % (
+        name, exact, len(hyps), sorted(tie_videos), near_tie))
+    # every video is exact unless it sits on an fp32 summation-order tie (audited above); at most one such video
+    assert exact >= len(hyps) - max(1, len(tie_videos)), "only %d/%d sequences exact" % (exact, len(hyps))
 
 
 def _prefixes_from_trace(step_rec, B, K):
@@ -97,8 +110,9 @@ def _prefixes_from_trace(step_rec, B, K):
     return torch.tensor(rows, dtype=torch.long)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16-stream"])
-@pytest.mark.parametrize("name", ["cfg2_sharp", "cfg1_sharp", "cfg4_sharp", "cab_sharp"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16-stream", "bf16"])
+@pytest.mark.parametrize("name", ["cfg2_sharp", "cfg1_sharp", "cfg4_sharp", "cab_sharp", "cfg3_trained", "cfg4_trained",
+                                  "cfg4_plain"])
 def test_teacher_forced_step_logits(name, precision):
     """Every step's logits from the KV-cached, ancestry-indirected CUDA path against the oracle's
     full-prefix recompute on exactly the prefixes the GPU beam holds at that step.  "bf16-stream" forces the
@@ -106,12 +120,9 @@ def test_teacher_forced_step_logits(name, precision):
     import care_b200
     rec = load_golden(name)
     opt, sd, feats = rebuild_case(rec, batch=3)
-    if precision == "bf16-stream":
-        opt, precision = dict(opt, care_self_compact=3), "bf16"
-    if precision == "bf16":
-        sd_o = {k: (v.bfloat16().float() if v.dim() == 2 and "embeddings" not in k else v) for k, v in sd.items()}
-    else:
-        sd_o = sd
+    sd_o = _round_weights(sd, precision)
+    if precision == "fp16-stream":
+        opt, precision = dict(opt, care_self_compact=3), "fp16"
     model = _gpu_model(opt, sd, precision)
     eng = model.engine()
     enc = model.encoding_phase([f.cuda() for f in feats])
@@ -142,30 +153,141 @@ def test_teacher_forced_step_logits(name, precision):
     print("\n%s %s: max rel logit err %.3e, max log-prob err (scaled) %.3e" % (name, precision, worst_logit, worst_lp))
     if precision == "fp32":
         assert worst_logit < 2e-5 and worst_lp < 2e-5
+    elif precision == "fp16":
+        assert worst_logit < 1e-2       # north_star: 16-bit logits within 1e-2 relative (measured: < 1e-3)
+        assert worst_lp < 1e-3          # north_star: per-step log-probs within 1e-3
     else:
-        assert worst_logit < 1e-2       # north_star: bf16 logits within 1e-2 relative
+        assert worst_logit < 1e-2       # the bf16 build: 8x coarser operands, logits still within the 1e-2 bound
         assert worst_lp < 1e-2
 
 
-@pytest.mark.parametrize("name", ["cfg2_plain", "cfg2_sharp", "cfg3_sharp", "cab_sharp"])
-def test_bf16_sequences(name):
-    """bf16 mode end to end: sequences against the fp32 reference golden; mismatching videos must have a
-    small oracle decision margin relative to bf16 logit noise."""
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+@pytest.mark.parametrize("name", ["cfg2_plain", "cfg2_sharp", "cfg3_sharp", "cab_sharp", "cfg3_trained", "cfg4_trained"])
+def test_h16_sequences(name, precision):
+    """16-bit modes end to end on the small goldens: concept ids equal the fp32 reference's (the encoder runs as
+    split products), sequences against the fp32 reference golden; a mismatching video must have a small oracle
+    decision margin relative to the mode's logit noise."""
     import care_b200
     rec = load_golden(name)
     opt, sd, feats = rebuild_case(rec)
-    model = _gpu_model(opt, sd, "bf16")
+    model = _gpu_model(opt, sd, precision)
+    if "semantic_labels" in rec:
+        labels = model.encoding_phase([f.cuda() for f in feats])["semantic_labels"].cpu().tolist()
+        p = co.encoding_phase(sd, opt, feats)["preds_attr"].sort(dim=1, descending=True)[0]
+        k = opt["use_attr_topk"]
+        gaps = (p[:, :k] - p[:, 1:k + 1]).min(dim=1)[0]
+        for v in range(len(labels)):
+            assert labels[v] == rec["semantic_labels"][v] or gaps[v] < 2e-5, (v, float(gaps[v]))
     tr = care_b200.get_translator(opt)
     hyps, scores = tr.translate_batch([model], {"feats": [f.cuda() for f in feats]})
     _, _, margins, _ = _oracle_margins(sd, opt, feats)
     exact = sum(int(hyps[v] == rec["hyps"][v]) for v in range(len(hyps)))
-    print("\n%s bf16: %d/%d sequences identical to the fp32 reference; margins of the rest: %s" % (
-        name, exact, len(hyps), ["%.2e" % margins[v] for v in range(len(hyps)) if hyps[v] != rec["hyps"][v]]))
+    print("\n%s %s: %d/%d sequences identical to the fp32 reference; margins of the rest: %s" % (
+        name, precision, exact, len(hyps), ["%.2e" % margins[v] for v in range(len(hyps)) if hyps[v] != rec["hyps"][v]]))
+    scale = 20.0 if "trained" in name else 6.0 if "sharp" in name else 1.0   # logit magnitude of the weight set
+    noise = (1e-3 if precision == "fp16" else 1e-2) * scale                  # the mode's log-prob error bound
     for v in range(len(hyps)):
         if hyps[v] != rec["hyps"][v]:
-            assert margins[v] < 0.25, "video %d differs although the oracle margin is %g" % (v, margins[v])
+            assert margins[v] < noise, "video %d differs although the oracle margin is %g" % (v, margins[v])
         else:
             assert abs(scores[v][0] - rec["scores"][v][0]) < 0.05 * max(1.0, abs(rec["scores"][v][0]))
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_h16_exact_match_512(precision):
+    """The north-star population: VATEX-large shape (cfg4), beam 5, 512 videos, trained-like peaked weights
+    (oracle/weights.py TRAINED), 16-bit mode against the hypotheses of the UNMODIFIED reference run on the CPU in
+    fp32 (tests/golden/cfg4_trained_512.json).  Writes the exact-match rate per oracle-margin bucket to
+    gpurun_out/ (committed under profiles/).  The fp32 mode must reproduce the golden exactly (near-ties aside);
+    the 16-bit rate is asserted at its measured level - see DESIGN.md section 5 for the error budget behind it."""
+    import json
+    import care_b200
+    rec = load_golden("cfg4_trained_512")
+    opt, sd, feats = rebuild_case(rec)
+    dev = [f.cuda() for f in feats]
+    tr = care_b200.get_translator(opt)
+    margins = rec["oracle_min_margin"]
+    out = {}
+    for prec in ("fp32", precision):
+        model = _gpu_model(opt, sd, prec)
+        labels = model.encoding_phase(dev)["semantic_labels"].cpu().tolist()
+        hyps, scores = tr.translate_batch([model], {"feats": dev})
+        same = [hyps[v] == rec["hyps"][v] for v in range(len(hyps))]
+        concept_same = sum(int(labels[v] == rec["semantic_labels"][v]) for v in range(len(hyps)))
+        buckets = [0.0, 1e-4, 1e-3, 1e-2, 3e-2, 1e-1, 3e-1, 1e9]
+        curve = []
+        for lo, hi in zip(buckets[:-1], buckets[1:]):
+            idx = [v for v in range(len(hyps)) if lo <= margins[v] < hi]
+            curve.append(dict(margin_lo=lo, margin_hi=hi, videos=len(idx), exact=sum(int(same[v]) for v in idx)))
+        out[prec] = dict(exact=sum(same), videos=len(hyps), concept_ids_exact=concept_same, by_oracle_margin=curve)
+        print("\ncfg4 trained-like, 512 videos, %s: %d/%d sequences identical to the reference (%.2f%%), concept ids "
+              "identical for %d videos" % (prec, sum(same), len(hyps), 100.0 * sum(same) / len(hyps), concept_same))
+        for c in curve:
+            print("   oracle margin [%.0e, %.0e): %d/%d" % (c["margin_lo"], c["margin_hi"], c["exact"], c["videos"]))
+        if prec == "fp32":
+            bad = [v for v in range(len(hyps)) if not same[v] and margins[v] >= 1e-4]
+            assert not bad, "fp32 mode differs from the reference on videos %s with clear margins" % bad[:8]
+            assert concept_same >= len(hyps) - 2
+        else:
+            lens = [len(h[0]) for h in rec["hyps"]]
+            assert min(lens) <= 5 and max(lens) >= 25     # the population really spreads over short and long captions
+            assert concept_same >= len(hyps) - 3          # split-product encoder: concept ranking as in fp32
+            floor = 0.95 if prec == "fp16" else 0.70
+            assert sum(same) >= floor * len(hyps), "%s exact-match %d/%d" % (prec, sum(same), len(hyps))
+            # a mismatch may only happen where the reference's own decision margin is within the mode's noise
+            noise = (1e-3 if prec == "fp16" else 1e-2) * 20.0 * 3
+            assert all(same[v] or margins[v] < noise for v in range(len(hyps)))
+        del model
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", "h16_exact_match_%s.json" % precision), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+def test_fused_vocab_records_direct():
+    """The bench's largest single kernel checked directly (not through the unfused CUDA path): the
+    (max, sum-exp, top-(K+1)) records of care_vocab_beam_partials at R = 20480, V = 14745 against fp32 torch
+    logsumexp / topk of the same 16-bit inputs."""
+    import ctypes
+    from care_b200 import _lib
+    lib = _lib.load("fp16")
+    h = ctypes.c_void_p()
+    _lib.check(lib.care_ctx_create(ctypes.byref(h), 0), "ctx")
+    try:
+        R, V, d, K = 20480, 14745, 1024, 5
+        g = torch.Generator(device="cuda").manual_seed(3)
+        x = torch.randn(R, d, device="cuda", generator=g).half()
+        W = (torch.randn(V, d, device="cuda", generator=g) * 0.08).half()
+        nseg = int(lib.care_vocab_beam_nseg(h, R, V))
+        kb = 6
+        part = torch.full((R, nseg, 2 + 2 * kb), float("nan"), device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.care_vocab_beam_partials(h, x.data_ptr(), d, W.data_ptr(), d, R, V, d, K, part.data_ptr(), nseg,
+                                                st), "vocab_beam")
+        torch.cuda.synchronize()
+        worst_lse = worst_top = 0.0
+        for r0 in range(0, R, 2048):
+            logits = x[r0:r0 + 2048].float() @ W.float().t()
+            lse_ref = torch.logsumexp(logits, 1)
+            top_ref, idx_ref = logits.topk(K + 1, dim=1)
+            p = part[r0:r0 + 2048]
+            m, se = p[:, :, 0], p[:, :, 1]
+            gm = m.max(dim=1, keepdim=True)[0]
+            lse = gm.squeeze(1) + torch.log((se * torch.exp(m - gm)).sum(1))
+            vals = p[:, :, 2:2 + kb].reshape(p.shape[0], -1)
+            ids = p[:, :, 2 + kb:2 + 2 * kb].reshape(p.shape[0], -1).contiguous().view(torch.int32)
+            top, pos = vals.topk(K + 1, dim=1)
+            worst_lse = max(worst_lse, (lse - lse_ref).abs().max().item())
+            worst_top = max(worst_top, (top - top_ref).abs().max().item())
+            got_idx = ids.gather(1, pos)
+            # ids must match wherever the reference's adjacent candidates are separated by more than the error
+            gap = (top_ref[:, :-1] - top_ref[:, 1:]).min(dim=1)[0]
+            clear = gap > 1e-3
+            assert torch.equal(got_idx[clear].long(), idx_ref[clear]), "candidate ids differ on rows with clear gaps"
+        print("\nfused vocab records at R=%d V=%d: max |lse err| %.2e, max |top-(K+1) value err| %.2e" % (
+            R, V, worst_lse, worst_top))
+        assert worst_lse < 2e-4 and worst_top < 2e-4
+    finally:
+        lib.care_ctx_destroy(h)
 
 
 def test_wrapper_checkpoint_roundtrip(tmp_path):
@@ -229,13 +351,14 @@ def test_nar_fp32_matches_reference_golden(name):
     assert exact >= 0.75 * len(hyps)
 
 
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
 @pytest.mark.parametrize("name", ["cfg5_sharp", "cfg5_plain"])
-def test_nar_bf16(name):
-    """bf16 mask-predict: well-formed output, same chosen length for most videos, token agreement."""
+def test_nar_h16(name, precision):
+    """16-bit mask-predict: well-formed output, same chosen length for most videos, token agreement."""
     import care_b200
     rec = load_golden(name)
     opt, sd, feats = rebuild_case(rec)
-    model = _gpu_model(opt, sd, "bf16")
+    model = _gpu_model(opt, sd, precision)
     tr = care_b200.get_translator(opt)
     hyps, lprobs = tr.translate_batch([model], {"feats": [f.cuda() for f in feats]})
     assert len(hyps) == len(rec["hyps"])
@@ -249,11 +372,11 @@ def test_nar_bf16(name):
         if n_ref == n_got:
             total += n_ref
             agree += sum(int(a == b) for a, b in zip(got[:n_ref], ref[:n_ref]))
-    print("\n%s bf16: %d/%d tokens identical on same-length outputs" % (name, agree, total))
-    assert total > 0 and agree >= 0.6 * total
+    print("\n%s %s: %d/%d tokens identical on same-length outputs" % (name, precision, agree, total))
+    assert total > 0 and agree >= (0.9 if precision == "fp16" else 0.6) * total
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
 @pytest.mark.parametrize("name", ["cfg2_sharp", "cfg5_sharp", "cab_attr2cross_sharp"])
 def test_decoding_phase_stateless(name, precision):
     """Framework.decoding_phase(input_ids, inputs) (full prefix, no cache) against the oracle, for
@@ -271,14 +394,13 @@ def test_decoding_phase_stateless(name, precision):
     ids[1, 4] = 0
     ids[4, L - 1] = 0
     o_inputs = {k: co.repeat_rows(v.float().cpu(), rep) for k, v in inputs.items()}
-    sd_o = sd if precision == "fp32" else {
-        k: (v.bfloat16().float() if v.dim() == 2 and "embeddings" not in k else v) for k, v in sd.items()}
+    sd_o = _round_weights(sd, precision)
     ref_all = co.decoding_phase(sd_o, opt, ids, o_inputs)
     ref_last = co.decoding_phase(sd_o, opt, ids, o_inputs, last_time_step_logits=True)
     got_all = model.decoding_phase(ids.cuda(), inputs)["logits"].cpu()
     enlarged = {k: co.repeat_rows(v, rep) for k, v in inputs.items()}
     got_last = model.decoding_phase(ids.cuda(), enlarged, last_time_step_logits=True)["logits"].cpu()
-    tol = 2e-5 if precision == "fp32" else 1e-2
+    tol = {"fp32": 2e-5, "fp16": 2e-3, "bf16": 1e-2}[precision]
     scale = ref_all.abs().max().item()
     assert got_all.shape == ref_all.shape and got_last.shape == ref_last.shape
     assert (got_all - ref_all).abs().max().item() < tol * scale
@@ -343,7 +465,7 @@ def test_workspace_limit_evicts_stale_sets_and_keeps_results():
     assert len({k[1] for k in roomy.engine()._ws if k[0] == "bs_scores"}) == 2   # both sizes stay resident
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
 def test_cuda_graph_replay_matches_eager(precision):
     """Small batches replay the whole decode as one CUDA graph: first call (eager + capture), replays,
     and a graph-free engine must all return the same hypotheses; replays count their launches."""
@@ -433,7 +555,7 @@ def test_randomised_differential_fp32():
 
 def test_full_size_batch_properties():
     """BASELINE.json's full size (cfg4, 4096 videos = 20480 beam rows per GPU), where no CPU oracle run is
-    affordable for every video: size-independent properties.  (1) bf16: the second half of the batch is a
+    affordable for every video: size-independent properties.  (1) fp16: the second half of the batch is a
     copy of the first, so both halves must decode to identical captions (rows are independent; this
     exercises every kernel's addressing at the high row indices, the multi-segment vocabulary records and
     the CTA-pair GEMM tiles).  (2) fp32: eight videos spread over the batch match the CPU oracle and the
@@ -446,7 +568,7 @@ def test_full_size_batch_properties():
     half = make_feats(opt, 2048, seed=77)
     feats = [torch.cat([f, f]).cuda() for f in half]
     tr = care_b200.get_translator(opt)
-    m16 = _gpu_model(opt, sd, "bf16")
+    m16 = _gpu_model(opt, sd, "fp16")
     hyps, scores = tr.translate_batch([m16], {"feats": feats})
     assert len(hyps) == 4096 and all(len(h) == 1 and 1 <= len(h[0]) <= 29 for h in hyps)
     assert hyps[:2048] == hyps[2048:] and scores[:2048] == scores[2048:]
@@ -498,7 +620,7 @@ def test_model_ensembling_matches_reference_golden(name):
     for a, b in zip(scores, rec["scores"]):
         for x, y in zip(a, b):
             assert abs(x - y) < 1e-4 * max(1.0, abs(y))
-    # bf16 engines: same driver, well-formed output
-    m16 = [_gpu_model(opt, sd, "bf16") for sd in sds]
+    # 16-bit engines: same driver, well-formed output
+    m16 = [_gpu_model(opt, sd, "fp16") for sd in sds]
     h16, _ = tr.translate_batch(m16, {"feats": [f.cuda() for f in feats]})
     assert len(h16) == len(hyps) and all(1 <= len(h[0]) <= opt["max_len"] - 1 for h in h16)
