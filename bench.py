@@ -8,8 +8,10 @@ One "step" = one `translate_batch` over one batch of synthetic videos: encoder +
 29 beam-search decode steps + hypothesis extraction (+ the NCCL all-gather of the decoded ids when
 N > 1).  `value` times it with the feature tensors already resident in HBM; `e2e` times the same call
 through the public Translator API from pinned HOST feature buffers to host Python lists.  Videos are
-independent units, so the batch is sharded over the ranks with a fixed per-GPU batch ("weak").
-Prints ONE JSON line on rank 0.
+independent units: the GLOBAL batch of 4096 videos (BASELINE.json configs[3]: "batch 4096 sharded across
+1/2/4/8 B200") is split over the ranks - "scaling": "strong"; the weak-scaling number (4096 videos on every
+GPU) rides along as `config.other_scaling` when N > 1.  `--config cfg5` runs BASELINE.json configs[4]
+(mask-predict, global batch 1024).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -34,7 +36,13 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="care", choices=["care", "reference"])
     ap.add_argument("--config", default="cfg4")
-    ap.add_argument("--batch", type=int, default=4096, help="videos per GPU per step")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="videos per step: the GLOBAL batch (strong scaling) or the per-GPU batch (weak); "
+                         "default 4096 (cfg4) / 1024 (cfg5), BASELINE.json configs[3] / configs[4]")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): one global batch sharded over the GPUs, as BASELINE.json configs[3] "
+                         "words it; weak: --batch videos on every GPU")
+    ap.add_argument("--no-other-scaling", action="store_true", help="N > 1: skip the secondary (weak) record")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"],
                     help="fp16 (default) / bf16: 16-bit tensor-core operands, fp32 accumulation; fp32: the bit-exact parity mode")
     ap.add_argument("--cpu-batch", type=int, default=16, help="videos per CPU-baseline sample")
@@ -47,9 +55,16 @@ def parse():
     return ap.parse_args()
 
 
-def workload_name(cfg, batch, precision):
-    return "%s: VATEX-shape Transformer large CARE (d=1024,H=16,F=4096,V=14745,Lm=114), beam 5, 29 steps, " \
-           "%d videos/GPU, %s" % (cfg, batch, precision) if cfg == "cfg4" else "%s batch %d %s" % (cfg, batch, precision)
+def workload_name(cfg, n_global, world, precision, scaling="strong"):
+    how = "global batch %d sharded over %d GPU(s)" % (n_global, world) if scaling == "strong" else \
+        "%d videos on each of %d GPU(s)" % (n_global // max(world, 1), world)
+    if cfg == "cfg4":
+        return "cfg4: VATEX-shape Transformer large CARE (d=1024,H=16,F=4096,V=14745,Lm=114), beam 5, 29 steps, " \
+               "%s, %s" % (how, precision)
+    if cfg == "cfg5":
+        return "cfg5: MSRVTT-shape NACF CARE (ARB encoder, d=512,V=10547,Lm=114), mask-predict: 6 length " \
+               "candidates, coarse templates + 5 iterations, %s, %s" % (how, precision)
+    return "%s, %s, %s" % (cfg, how, precision)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -58,12 +73,12 @@ def workload_name(cfg, batch, precision):
 def time_cpu_oracle(cfg, cpu_batch, steps, warmup):
     import torch
     from oracle import care_oracle as co
-    from oracle.shapes import CONFIGS, make_feats, make_opt
-    from oracle.weights import make_state_dict
+    from synth.shapes import CONFIGS, make_feats, make_opt
+    from synth.weights import make_state_dict
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     opt = make_opt(**CONFIGS[cfg])
-    sd = make_state_dict(opt, seed=0)
+    sd = make_state_dict(opt, seed=0, perturb=opt["decoding_type"] == "NARFormer")
     feats = make_feats(opt, cpu_batch, seed=0)
     for _ in range(warmup):
         co.translate(sd, opt, feats)
@@ -90,13 +105,14 @@ def run_reference_arm(args):
         return
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
     value, ms, cores = time_cpu_oracle(args.config, args.cpu_batch, steps, warmup)
-    sample = "%d videos per step (full 29-step beam-5 decode), %d timed steps, oracle port of the reference's " \
+    sample = "%d videos per step (full decode), %d timed steps, oracle port of the reference's " \
              "CPU path, fp32, %d torch threads on %s" % (args.cpu_batch, steps, cores, cpu_model_name())
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.config, args.cpu_batch, "fp32 (CPU)"), "beam_size": 5},
+        "config": {"workload": workload_name(args.config, args.cpu_batch, 1, "fp32 (CPU, %d-video sample per step)"
+                                             % args.cpu_batch), "beam_size": 5},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -171,11 +187,18 @@ class TimedLib:
         return wrapped
 
 
-def kernel_work_table(esz):
-    """name -> f(args) = (kernel label, bound, algorithmic units of one launch); DESIGN.md section 4."""
+def kernel_work_table(esz, lib, ctx):
+    """name -> f(args) = (kernel label, bound, algorithmic units of one launch); DESIGN.md section 4.  The label of
+    a family with several kernel variants is the variant the call actually launched (care_ctx_last_kernel)."""
+    def last(family, default):
+        def f():
+            n = lib.care_ctx_last_kernel(ctx, family.encode())
+            return n.decode() if n else default
+        return f
+    gemm, vocab, selfk = last("gemm", "gemm"), last("vocab", "vocab_beam"), last("self_attn", "self_attn")
     return {
-        "care_gemm": lambda a: ("gemm_bf16_tcgen05_kernel / gemm_bf16_2sm_kernel", "tensor", 2.0 * a[10] * a[11] * a[12]),
-        "care_vocab_beam_partials": lambda a: ("vocab_beam_tcgen05_kernel", "tensor", 2.0 * a[5] * a[6] * a[7]),
+        "care_gemm": lambda a: (gemm(), "tensor", 2.0 * a[10] * a[11] * a[12]),
+        "care_vocab_beam_partials": lambda a: (vocab(), "tensor", 2.0 * a[5] * a[6] * a[7]),
         # cross: K/V of every video once + q in + ctx out
         "care_cross_attn_step": lambda a: ("attn_mma_kernel<cross>", "hbm",
                                            (a[6] * a[5] * 2.0 * a[9] + 2.0 * a[6] * a[7] * a[9]) * esz),
@@ -184,6 +207,8 @@ def kernel_work_table(esz):
         # read, counted on the device, when the live-slot stream kernel is in use)
         "care_self_attn_step": lambda a: (SELF_LABEL, "hbm",
                                           (a[4] * a[5] * a[3] * 2.0 * a[7] + 2.0 * a[4] * a[5] * a[7]) * esz),
+        # full-sequence attention (mask-predict passes): per group K and V once + q in + ctx out
+        "care_group_attn": lambda a: ("group_attn_mma_kernel", "hbm", a[8] * (a[10] * 2.0 + a[9] * 2.0) * a[12] * esz),
         "care_add_ln": lambda a: ("add_ln_kernel", "hbm", a[7] * a[8] * (4.0 + 2 * esz)),
         "care_beam_step": lambda a: ("beam_row_kernel", "hbm", 0.0),
     }
@@ -216,7 +241,7 @@ def summarise_kernels(records, peaks, units_override=None):
             psrc = src + " hbm_gbs (measured copy bandwidth)"
         else:
             ach, peak, unit = d["units"] / (d["ms"] * 1e-3) / 1e12, tens, "TFLOP/s"
-            psrc = src + " bf16_tflops_sustained (kernel timed inside a long step)"
+            psrc = src + " bf16_tflops_sustained (16-bit dense tensor peak; kernel timed inside a long step)"
         out.append({"kernel": label, "bound": d["bound"], "achieved": ach, "peak": peak, "unit": unit,
                     "frac": ach / peak, "traffic": None, "launches_timed": d["n"],
                     "avg_launch_ms": d["ms"] / d["n"], "total_ms": d["ms"],
@@ -232,6 +257,25 @@ def read_counter(eng, name):
     return int(v.value) if rc == 0 else 0
 
 
+def percentile(xs, q):
+    xs = sorted(xs)
+    if not xs:
+        return None
+    k = (len(xs) - 1) * q
+    lo, hi = int(k), min(int(k) + 1, len(xs) - 1)
+    return xs[lo] + (xs[hi] - xs[lo]) * (k - lo)
+
+
+def make_host_feats(opt, n, seed_base):
+    """Pinned host features of n distinct videos, generated in chunks to bound host memory."""
+    import torch
+    from synth.shapes import make_feats
+    chunks = []
+    for c in range(0, max(n, 1), 512):
+        chunks.append(make_feats(opt, min(512, n - c), seed=seed_base + c))
+    return [torch.cat([ch[i] for ch in chunks]).pin_memory() for i in range(len(opt["modality"]))]
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -240,8 +284,8 @@ def run_care_arm(args):
     import torch.distributed as dist
     import care_b200
     from care_b200 import sharding
-    from oracle.shapes import CONFIGS, make_feats, make_opt      # synthetic shapes/weights only
-    from oracle.weights import make_state_dict
+    from synth.shapes import CONFIGS, make_opt      # synthetic shapes / weights: pure data builders
+    from synth.weights import make_state_dict
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -251,7 +295,8 @@ def run_care_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     opt = make_opt(**CONFIGS[args.config])
-    sd = make_state_dict(opt, seed=0)
+    nar = opt["decoding_type"] == "NARFormer"
+    sd = make_state_dict(opt, seed=0, perturb=nar)
     model = care_b200.get_framework(dict(opt, care_precision=args.precision, care_self_compact=args.self_compact))
     # (care_self_compact None keeps the library default)
     model.load_state_dict(sd)
@@ -259,34 +304,44 @@ def run_care_arm(args):
     del sd
     tr = care_b200.get_translator(opt)
     eng = model.engine()
-    B = args.batch
     Tm = opt["max_len"] - 1
-    # distinct videos per rank: seeds differ, generated in chunks to bound host memory
-    chunks = []
-    for c in range(0, B, 512):
-        n = min(512, B - c)
-        chunks.append(make_feats(opt, n, seed=1000 * rank + c))
-    host_feats = [torch.cat([ch[i] for ch in chunks]).pin_memory() for i in range(len(opt["modality"]))]
-    del chunks
+    K = 1 if nar else opt["beam_size"]
+    G = args.batch if args.batch else (1024 if nar else 4096)          # videos per step
+    if args.scaling == "strong":      # BASELINE.json configs[3]/[4]: ONE global batch sharded over the GPUs
+        lo, hi = sharding.shard_range(G, rank, world)
+        B, n_global = hi - lo, G
+    else:                             # fixed per-GPU batch
+        B, n_global = G, G * world
+    host_feats = make_host_feats(opt, B, 100000 * rank)
     dev_feats = [f.to(dev) for f in host_feats]
     h2d_bytes = sum(f.numel() * f.element_size() for f in host_feats)
 
-    def step_resident():
-        out = tr.decode_on_device(model, dev_feats)
+    def pack(out):
+        return sharding.pack_nar(*out, opt["max_len"]) if nar else sharding.pack_hypotheses(*out)
+
+    def step_resident(feats=None, total=None):
+        out = tr.decode_on_device(model, dev_feats if feats is None else feats)
         if world > 1:  # the one collective of the path: all-gather of the decoded ids
-            return sharding.gather_hypotheses(sharding.pack_hypotheses(*out), world * B)
+            return sharding.gather_hypotheses(pack(out), n_global if total is None else total)
         return out
 
     # N > 1: every rank ends a step holding (a) the all-gathered ids of ALL videos, read back to a pinned host
     # tensor, and (b) Python lists for its own shard (what a per-rank caption writer consumes)
-    gathered_host = torch.empty((world * B, 1, Tm + 3), dtype=torch.int32).pin_memory() if world > 1 else None
+    rec_w = 2 * opt["max_len"] + 1 if nar else Tm + 3
+    gathered_host = torch.empty((n_global, 1, rec_w), dtype=torch.int32).pin_memory() if world > 1 else None
 
     def gather_hook(out):
-        full = sharding.gather_hypotheses(sharding.pack_hypotheses(*out), world * B)
+        full = sharding.gather_hypotheses(pack(out), n_global)
         gathered_host.copy_(full, non_blocking=True)
         return out
 
     def step_e2e():
+        if nar:
+            with torch.no_grad():
+                out = tr.decode_on_device(model, host_feats)
+            if world > 1:
+                out = gather_hook(out)
+            return out[0].cpu().tolist(), out[1].cpu().tolist()
         if world > 1:
             with torch.no_grad():
                 if B > tr.pipeline_chunk:
@@ -303,8 +358,15 @@ def run_care_arm(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     esz = 4 if args.precision == "fp32" else 2
-    timed = TimedLib(eng.lib, kernel_work_table(esz))
+    raw_lib = eng.lib
+    timed = TimedLib(raw_lib, kernel_work_table(esz, raw_lib, eng.ctx))
     eng.lib = timed
 
     for _ in range(args.warmup):
@@ -324,13 +386,9 @@ def run_care_arm(args):
     sync_all()
     timed.on = False
     launches = eng.launch_count() - launches0
-    self_rows = read_counter(eng, "self_attn_rows") - rows0   # K/V cache rows the bf16 self-attention kernels read
-    elapsed_ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    value = world * B * args.steps / (elapsed_ms / 1e3)
+    self_rows = read_counter(eng, "self_attn_rows") - rows0   # K/V cache rows the self-attention kernels read
+    elapsed_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    value = n_global * args.steps / (elapsed_ms / 1e3)
 
     # e2e: host pinned features -> H2D -> decode -> (all-gather) -> D2H -> Python lists, public API.
     # (a) one synchronous Translator.translate_batch call per step;
@@ -339,67 +397,138 @@ def run_care_arm(args):
     e2e_value = e2e_call_value = None
     e2e_steps = e2e_stream_steps = 0
     hyps = None
+    stages = {}
     if not args.no_e2e:
-        for _ in range(1):
-            step_e2e()
+        step_e2e()
         sync_all()
         t0 = time.perf_counter()
         e2e_steps = max(1, min(args.steps, 3))
         for _ in range(e2e_steps):
             hyps, scores = step_e2e()
         torch.cuda.synchronize(dev)
-        e2e_call_ms = (time.perf_counter() - t0) * 1e3
-        t = torch.tensor([e2e_call_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_call_value = world * B * e2e_steps / (float(t.item()) / 1e3)
+        e2e_call_value = n_global * e2e_steps / (max_over_ranks((time.perf_counter() - t0) * 1e3) / 1e3)
+        if nar:     # mask-predict has no stream API: the synchronous call is the e2e number
+            e2e_value, e2e_stream_steps = e2e_call_value, e2e_steps
+        else:
+            def stream_steps(n):
+                got = 0
+                hook = gather_hook if world > 1 else None
+                for h, s_ in tr.translate_stream([model], ({"feats": host_feats} for _ in range(n)), device_hook=hook):
+                    got += len(h)
+                return got
 
-        def stream_steps(n):
-            got = 0
-            hook = gather_hook if world > 1 else None
-            for h, s_ in tr.translate_stream([model], ({"feats": host_feats} for _ in range(n)), device_hook=hook):
-                got += len(h)
-            return got
-
-        stream_steps(2)
-        sync_all()
-        # a loader loop runs many batches; 16 keeps the one-off pipeline fill (first H2D, last read-back) in proportion
-        e2e_stream_steps = max(args.steps, 16)
-        t0 = time.perf_counter()
-        got = stream_steps(e2e_stream_steps)
-        torch.cuda.synchronize(dev)
-        e2e_ms = (time.perf_counter() - t0) * 1e3
-        assert got == B * e2e_stream_steps
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_value = world * B * e2e_stream_steps / (float(t.item()) / 1e3)
+            stream_steps(2)
+            sync_all()
+            # a loader loop runs many batches; 16 keeps the one-off pipeline fill (first H2D, last read-back) in proportion
+            e2e_stream_steps = max(args.steps, 16)
+            t0 = time.perf_counter()
+            got = stream_steps(e2e_stream_steps)
+            torch.cuda.synchronize(dev)
+            e2e_ms = (time.perf_counter() - t0) * 1e3
+            assert got == B * e2e_stream_steps
+            e2e_value = n_global * e2e_stream_steps / (max_over_ranks(e2e_ms) / 1e3)
+        if world == 1 and not nar:
+            # the stages of one host-fed batch, each timed alone (in the stream they overlap)
+            stage_dev = [torch.empty_like(f) for f in dev_feats]
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for d_, s_ in zip(stage_dev, host_feats):
+                d_.copy_(s_, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            stages["h2d_ms"] = (time.perf_counter() - t0) * 1e3
+            out = tr.decode_on_device(model, dev_feats, early_exit_every=0)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            host_out = [t.cpu() for t in out]
+            stages["d2h_ms"] = (time.perf_counter() - t0) * 1e3
+            t0 = time.perf_counter()
+            care_b200.engine.hyps_from_device(*host_out, tr.beam_alpha, tr.topk)
+            stages["lists_ms"] = (time.perf_counter() - t0) * 1e3
+            stages["decode_ms"] = elapsed_ms / args.steps
+            del stage_dev
     clocks = sampler.stop() if rank == 0 else None
-    d2h_bytes = B * world * (Tm + 3) * 4
-    assert hyps is None or (len(hyps) == B and all(1 <= len(h[0]) <= Tm for h in hyps[:64]))
-    if hyps is not None and world > 1:   # the gathered record of this rank's first video matches its own list
-        lo = rank * B
-        assert gathered_host[lo, 0, :len(hyps[0][0])].tolist() == hyps[0][0]
+    d2h_bytes = n_global * rec_w * 4
+    if hyps is not None and not nar:
+        assert len(hyps) == B and all(1 <= len(h[0]) <= Tm for h in hyps[:64])
+        if world > 1 and B:   # the gathered record of this rank's first video matches its own list
+            lo = sharding.shard_range(n_global, rank, world)[0] if args.scaling == "strong" else rank * B
+            assert gathered_host[lo, 0, :len(hyps[0][0])].tolist() == hyps[0][0]
 
-    # per-step decode latency at small batches (launch-bound regime: the decode is replayed as one CUDA graph)
+    # per-step decode latency: every beam step of the eager decode bracketed by CUDA events (this rank's shard),
+    # and whole-decode latency at small batches (launch-bound regime: replayed as one CUDA graph)
     latency = {}
-    if world == 1 and not args.no_latency:
+    step_lat = None
+    if not args.no_latency and not nar:
         timed.on = False
-        for lb in (1, 64):
-            small = [f[:lb].contiguous() for f in dev_feats]
+        step_ms = []
+        enc = model.encoding_phase(dev_feats)
+        orig = eng.decode_step
+
+        def timed_step(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = orig(*a, **k)
+            e1.record()
+            step_ms.append((e0, e1))
+            return r
+
+        eng.decode_step = timed_step
+        use_graphs = eng.use_graphs
+        eng.use_graphs = False
+        try:
             for _ in range(3):
-                tr.decode_on_device(model, small)
-            torch.cuda.synchronize(dev)
-            reps = 10
-            l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            l0.record()
-            for _ in range(reps):
-                tr.decode_on_device(model, small)
-            l1.record()
-            torch.cuda.synchronize(dev)
-            ms = l0.elapsed_time(l1) / reps
-            latency["batch_%d" % lb] = {"ms_per_caption_batch": ms, "us_per_beam_step": ms / Tm * 1e3,
-                                        "captions_per_sec": lb / ms * 1e3}
+                eng.ar_decode(enc, B, beam_size=tr.beam_size, topk=tr.topk, beam_alpha=tr.beam_alpha, early_exit_every=0)
+        finally:
+            eng.decode_step, eng.use_graphs = orig, use_graphs
+        torch.cuda.synchronize(dev)
+        per = [a.elapsed_time(b) for a, b in step_ms[Tm:]]     # first decode = warm-up
+        step_lat = {"videos": B, "beam_rows": B * K, "samples": len(per), "mean_ms": sum(per) / len(per),
+                    "p50_ms": percentile(per, 0.5), "p99_ms": percentile(per, 0.99), "max_ms": max(per),
+                    "note": "CUDA events around each of the %d beam steps (13 layer launches + fused vocabulary + "
+                            "beam update) of the eager decode, 2 decodes after one warm-up" % Tm}
+        if world == 1:
+            for lb in (1, 64, 512):
+                if lb > B:
+                    continue
+                small = [f[:lb].contiguous() for f in dev_feats]
+                for _ in range(3):
+                    tr.decode_on_device(model, small)
+                torch.cuda.synchronize(dev)
+                reps = 10
+                l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                l0.record()
+                for _ in range(reps):
+                    tr.decode_on_device(model, small)
+                l1.record()
+                torch.cuda.synchronize(dev)
+                ms = l0.elapsed_time(l1) / reps
+                latency["batch_%d" % lb] = {"ms_per_caption_batch": ms, "us_per_beam_step": ms / Tm * 1e3,
+                                            "captions_per_sec": lb / ms * 1e3}
+
+    # the other scaling mode as a secondary record (N > 1): weak = 4096 videos on every GPU
+    other = None
+    if world > 1 and not args.no_other_scaling:
+        if args.scaling == "strong":
+            ob, ototal = G, G * world
+        else:
+            olo, ohi = sharding.shard_range(G, rank, world)
+            ob, ototal = ohi - olo, G
+        ofe = [f.to(dev) for f in make_host_feats(opt, ob, 100000 * rank + 7)]
+        for _ in range(2):
+            step_resident(ofe, ototal)
+        sync_all()
+        osteps = max(2, args.steps // 2)
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record()
+        for _ in range(osteps):
+            step_resident(ofe, ototal)
+        o1.record()
+        sync_all()
+        oms = max_over_ranks(o0.elapsed_time(o1))
+        other = {"scaling": "weak" if args.scaling == "strong" else "strong", "global_batch": ototal,
+                 "per_gpu_batch": ob, "steps": osteps, "ms_per_step": oms / osteps,
+                 "value": ototal * osteps / (oms / 1e3), "unit": UNIT}
+        del ofe
 
     peaks = {}
     try:
@@ -409,7 +538,7 @@ def run_care_arm(args):
     override = {}
     if self_rows > 0:   # algorithmic bytes of the self-attention = the rows actually read + q in + ctx out
         n_self = sum(1 for r in timed.records if r[0] == "care_self_attn_step")
-        override[SELF_LABEL] = (self_rows * 2.0 * eng.d + n_self * 2.0 * B * opt["beam_size"] * eng.d) * esz
+        override[SELF_LABEL] = (self_rows * 2.0 * eng.d + n_self * 2.0 * B * K * eng.d) * esz
     kernels = summarise_kernels(timed.records, peaks, override)
     # DRAM traffic per launch from the committed `ncu --set full` capture of one decode step (profiles/)
     import glob
@@ -430,31 +559,36 @@ def run_care_arm(args):
     if not args.no_cpu_baseline and world == 1:
         cv, cms, cores = time_cpu_oracle(args.config, args.cpu_batch, 3, 1)
         cpu = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d videos per pass, 3 timed passes of the full 29-step beam-5 decode (%.1f s each) after one "
+               "sample": "%d videos per pass, 3 timed passes of the full decode (%.1f s each) after one "
                          "warm-up, oracle port of the reference CPU path, fp32, %d torch threads on %s" % (
                              args.cpu_batch, cms / 1e3, cores, cpu_model_name())}
-    step_ms = elapsed_ms / args.steps
+    step_ms_avg = elapsed_ms / args.steps
     roofline = dict(kernels[0]) if kernels else None
     if roofline is not None:
         roofline["share_of_step"] = roofline["total_ms"] / elapsed_ms
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": step_ms_avg, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
-        "config": {"workload": workload_name(args.config, B, args.precision), "beam_size": opt["beam_size"],
-                   "per_gpu_batch": B, "global_batch": B * world, "parallelism": "video-sharded x%d" % world,
-                   "decode_ms_per_beam_step": step_ms / Tm,
+        "config": {"workload": workload_name(args.config, n_global, world, args.precision, args.scaling),
+                   "beam_size": K, "per_gpu_batch": B, "global_batch": n_global,
+                   "parallelism": "video-sharded x%d" % world,
+                   "decode_ms_per_beam_step": None if nar else step_ms_avg / Tm,
+                   "per_step_latency": step_lat,
                    "small_batch_latency": latency,
+                   "other_scaling": other,
                    "l2_note": "inputs larger than L2: per-step working set (cross K/V 1.9 GB, KV cache up to 3.6 GB, "
-                              "features 1.4 GB) >> 126 MB L2"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                              "features 1.4 GB at 4096 videos) >> 126 MB L2"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world,
+                "d2h_bytes_per_step": d2h_bytes,
                 "steps": e2e_stream_steps or e2e_steps,
-                "single_call_value": e2e_call_value,
+                "single_call_value": e2e_call_value, "stages_ms": stages,
                 "note": "value: Translator.translate_stream over the steps' pinned HOST batches -> Python lists "
                         "(every step's H2D copy and D2H read inside the timed region; step i+1's copy overlaps step "
                         "i's decode; N>1: + the per-step NCCL all-gather of ids, read back in full to pinned host memory on every rank, "
                         "Python lists built for the rank's own shard).  single_call_value: one synchronous "
-                        "Translator.translate_batch per step (H2D chunked in 2048-video halves)"},
+                        "Translator.translate_batch per step (H2D chunked in 2048-video halves).  stages_ms: the "
+                        "stages of one batch timed alone (N=1); in the stream they overlap"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "roofline_other_kernels": [{k: r[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic",
                                                        "launches_timed", "avg_launch_ms", "total_ms",

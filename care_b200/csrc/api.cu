@@ -133,6 +133,14 @@ int care_ctx_counter(care_ctx* ctx, const char* name, int64_t* value) {
   return -1;
 }
 
+const char* care_ctx_last_kernel(const care_ctx* ctx, const char* family) {
+  if (!ctx || !family) return "";
+  if (strcmp(family, "gemm") == 0) return ctx->last_gemm;
+  if (strcmp(family, "vocab") == 0) return ctx->last_vocab;
+  if (strcmp(family, "self_attn") == 0) return ctx->last_self_attn;
+  return "";
+}
+
 int care_ctx_sm_count(const care_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
 int64_t care_ctx_launch_count(const care_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -172,6 +180,18 @@ int care_ctx_set_option(care_ctx* ctx, const char* name, int value) {
   }
   if (strcmp(name, "gemm_2sm") == 0) {
     ctx->gemm_2sm = value;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->gemm_choice.clear();
+    return 0;
+  }
+  if (strcmp(name, "gemm_bn") == 0) {   // 0: pick the tile width per shape; 64..256 (multiple of 32): force it
+    if (value != 0 && (value < 64 || value > 256 || value % 32 != 0)) {
+      care::set_error("care_ctx_set_option: gemm_bn must be 0 or a multiple of 32 in [64, 256]");
+      return -1;
+    }
+    ctx->gemm_bn = value;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->gemm_choice.clear();
     return 0;
   }
   care::set_error("care_ctx_set_option: unknown option '%s'", name);

@@ -291,6 +291,7 @@ static int launch(care_ctx* ctx, const CUtensorMap& tmap, const Params& p, cudaS
     configured = smem;
   }
   kern<<<p.n_items, WARPS * 32, smem, stream>>>(tmap, p);
+  if (SELF) ctx->last_self_attn = "attn_mma_kernel<self>";
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -817,6 +818,7 @@ static int launch_stream_t(care_ctx* ctx, const CUtensorMap& tmap, const Params&
   const int grid = std::min((p.n_items + WARPS - 1) / WARPS, ctx->sm_count * ctas_per_sm);
   kern<<<grid, WARPS * 32, Cfg<STAGES>::SMEM_BYTES, stream>>>(tmap, p, (int)R, ctx->compact_info, ctx->self_attn_rows,
                                                               early_exit_of(ctx));
+  ctx->last_self_attn = "attn_self_stream_kernel";
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

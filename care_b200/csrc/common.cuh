@@ -125,6 +125,10 @@ struct care_ctx {
   // 0: single-CTA tiles only, 1: CTA-pair (cta_group::2) tiles whenever the shape allows, 2 (default): pick per
   // (M, N, K, out dtype) by timing both once on the first call with that shape (skipped while capturing)
   int gemm_2sm = 2;
+  const char* last_gemm = "";    // variant names of the most recent launches (care_ctx_last_kernel)
+  const char* last_vocab = "";
+  const char* last_self_attn = "";
+  int gemm_bn = 0;   // > 0: force this tile width in the single-CTA GEMM (A/B runs)
   int debug = 0;
   int vocab_2sm = 1;   // fused vocabulary kernel on CTA pairs when the shape has >= two waves of pair tiles
   std::unordered_map<uint64_t, int> gemm_choice;

@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(THREADS)
 concept_head_kernel(const float* __restrict__ scores, int64_t ld_scores, int n_attr, int topk,
                     const float* __restrict__ attr_word, const float* __restrict__ attr_pos,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int d,
-                    float* __restrict__ preds_f32, T* __restrict__ preds_T, int64_t ld_preds_T,
+                    float* __restrict__ preds_f32, float* __restrict__ preds_T, int64_t ld_preds_T,
                     int64_t* __restrict__ labels, T* __restrict__ memory, int mem_rows, int mem_row0) {
   __shared__ float prob[MAX_ATTR];
   __shared__ float sort_p[MAX_ATTR];
@@ -36,10 +36,10 @@ concept_head_kernel(const float* __restrict__ scores, int64_t ld_scores, int n_a
     const float out = 1.0f - expf(raw);
     prob[a] = out;
     if (preds_f32) preds_f32[(int64_t)v * n_attr + a] = out;
-    if (preds_T) preds_T[(int64_t)v * ld_preds_T + a] = Act<T>::from_float(out);
+    if (preds_T) preds_T[(int64_t)v * ld_preds_T + a] = out;
   }
   if (preds_T)
-    for (int a = n_attr + tid; a < ld_preds_T; a += THREADS) preds_T[(int64_t)v * ld_preds_T + a] = Act<T>::from_float(0.f);
+    for (int a = n_attr + tid; a < ld_preds_T; a += THREADS) preds_T[(int64_t)v * ld_preds_T + a] = 0.f;
   __syncthreads();
 
   // order the concepts by (probability desc, index asc): bitonic sort of the padded array in shared memory
@@ -146,7 +146,7 @@ extern "C" int care_concept_head(care_ctx* ctx, int dtype, const float* scores, 
         ld_preds_T, labels, (float*)memory, mem_rows, mem_row0);
   else if (dtype == CARE_H16)
     concept_head::concept_head_kernel<h16><<<B, concept_head::THREADS, 0, s>>>(
-        scores, ld_scores, n_attr, topk, attr_word, attr_pos, gamma, beta, eps, d, preds_f32, (h16*)preds_T,
+        scores, ld_scores, n_attr, topk, attr_word, attr_pos, gamma, beta, eps, d, preds_f32, (float*)preds_T,
         ld_preds_T, labels, (h16*)memory, mem_rows, mem_row0);
   else {
     care::set_error("care_concept_head: bad dtype %d", dtype);

@@ -100,6 +100,79 @@ gemm_f32_kernel(const float* __restrict__ A, int64_t lda, const float* __restric
   }
 }
 
+// Same product on 64x64 tiles (4x4 outputs per thread) for shapes whose 128x128 tiling would leave most SMs idle
+// (the per-video heads at a few hundred videos).  Every output still accumulates k = 0..K-1 in order with fmaf,
+// so the result is bit-identical to the large-tile kernel's.
+constexpr int SB = 64, ST = 4;
+template <typename OutT>
+__global__ void __launch_bounds__(THREADS)
+gemm_f32_small_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ W, int64_t ldw,
+                      const float* __restrict__ bias, OutT* __restrict__ C, int64_t ldc, int M, int N, int n_store,
+                      int K, int relu, const EarlyExit ee) {
+  if (all_done(ee)) return;
+  __shared__ __align__(16) float As[2][BK][SB + 4];
+  __shared__ __align__(16) float Ws[2][BK][SB + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * SB, n0 = blockIdx.x * SB;
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;   // one float4 of A and one of W per thread per k-tile
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[ST][ST];
+#pragma unroll
+  for (int i = 0; i < ST; ++i)
+#pragma unroll
+    for (int j = 0; j < ST; ++j) acc[i][j] = 0.f;
+  float4 ra, rw;
+  auto gload = [&](int k0) {
+    const int gm = m0 + lrow, gn = n0 + lrow, gk = k0 + lk;
+    ra = make_float4(0.f, 0.f, 0.f, 0.f);
+    rw = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gm < M && gk < K) ra = *reinterpret_cast<const float4*>(A + (int64_t)gm * lda + gk);
+    if (gn < N && gk < K) rw = *reinterpret_cast<const float4*>(W + (int64_t)gn * ldw + gk);
+  };
+  auto sstore = [&](int buf) {
+    As[buf][lk + 0][lrow] = ra.x; As[buf][lk + 1][lrow] = ra.y; As[buf][lk + 2][lrow] = ra.z; As[buf][lk + 3][lrow] = ra.w;
+    Ws[buf][lk + 0][lrow] = rw.x; Ws[buf][lk + 1][lrow] = rw.y; Ws[buf][lk + 2][lrow] = rw.z; Ws[buf][lk + 3][lrow] = rw.w;
+  };
+  const int k_tiles = (K + BK - 1) / BK;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < k_tiles; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < k_tiles) gload((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 w4 = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int i = 0; i < ST; ++i)
+#pragma unroll
+        for (int j = 0; j < ST; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    if (kt + 1 < k_tiles) {
+      sstore(buf ^ 1);
+      __syncthreads();
+    }
+  }
+  const int col = n0 + tx * 4;
+  if (col >= n_store) return;
+#pragma unroll
+  for (int i = 0; i < ST; ++i) {
+    const int row = m0 + ty * 4 + i;
+    if (row >= M) continue;
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x = acc[i][j];
+      if (bias != nullptr && col + j < N) x += __ldg(bias + col + j);
+      if (col + j >= N) x = 0.f;
+      o[j] = relu ? fmaxf(x, 0.f) : x;
+    }
+    Act<OutT>::store4(C + (int64_t)row * ldc + col, o);
+  }
+}
+
 int gemm_f32(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
              int64_t ldc, int out_dtype, int M, int N, int K, int act, cudaStream_t stream) {
   CARE_CHECK_ARG(lda % 4 == 0 && ldw % 4 == 0 && K % 4 == 0,
@@ -113,6 +186,21 @@ int gemm_f32(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t l
   const int n_pad = n_pad8 <= ldc ? n_pad8 : ((N + 3) & ~3);
   CARE_CHECK_ARG(n_pad <= ldc, "care_gemm(f32): ldc %lld too small for N=%d", (long long)ldc, N);
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  if ((int)(grid.x * grid.y) * 4 <= ctx->sm_count) {   // too few large tiles to fill the machine
+    dim3 sgrid((N + SB - 1) / SB, (M + SB - 1) / SB);
+    if (out_dtype == CARE_F32)
+      gemm_f32_small_kernel<float><<<sgrid, THREADS, 0, stream>>>((const float*)A, lda, (const float*)W, ldw, bias,
+                                                                 (float*)C, ldc, M, N, n_pad, K,
+                                                                 act == CARE_ACT_RELU, early_exit_of(ctx));
+    else
+      gemm_f32_small_kernel<h16><<<sgrid, THREADS, 0, stream>>>((const float*)A, lda, (const float*)W, ldw, bias,
+                                                               (h16*)C, ldc, M, N, n_pad, K, act == CARE_ACT_RELU,
+                                                               early_exit_of(ctx));
+    ctx->last_gemm = "gemm_f32_small_kernel";
+    CARE_LAUNCH_CHECK(ctx);
+    return 0;
+  }
+  ctx->last_gemm = "gemm_f32_kernel";
   if (out_dtype == CARE_F32)
     gemm_f32_kernel<float><<<grid, THREADS, 0, stream>>>((const float*)A, lda, (const float*)W, ldw, bias, (float*)C,
                                                          ldc, M, N, n_pad, K, act == CARE_ACT_RELU, early_exit_of(ctx));

@@ -81,6 +81,7 @@ int gemm_bf16_smallm(care_ctx* ctx, const void* A, int64_t lda, const void* W, i
     gemm_smallm_kernel<h16><<<grid, WARPS * 32, 0, stream>>>(
         static_cast<const h16*>(A), lda, static_cast<const h16*>(W), ldw, bias,
         static_cast<h16*>(C), ldc, M, N, n_store, K, relu, early_exit_of(ctx));
+  ctx->last_gemm = "gemm_smallm_kernel";
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -29,8 +29,22 @@ int gemm_bf16_smallm(care_ctx* ctx, const void* A, int64_t lda, const void* W, i
 namespace tc {
 
 constexpr int GEMM_EPI_BYTES = 8 * 4096;   // one 32x32 fp32 staging block per epilogue warp
+// Tile widths in steps of 32 columns: with a few thousand rows (a 512-video shard has 20 row blocks) the
+// number of 128 x BN tiles decides how many of the 148 SMs work, e.g. N = 1024: 256-wide tiles -> 80 tiles,
+// 160-wide -> 140 tiles in one wave.
 template <int BN>
-constexpr int gemm_smem_bytes() { return Cfg<BN>::STAGES * Cfg<BN>::STAGE_BYTES + GEMM_EPI_BYTES + 256 + 1024; }
+struct GCfg {
+  static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "tile width: multiple of 32 in [64, 256]");
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;     // a multiple of 1024 (SWIZZLE_128B atom)
+  static constexpr int TMEM_COLS = BN <= 64 ? 128 : (BN <= 128 ? 256 : 512);   // power of two, two accumulators
+  static constexpr int ACC_STRIDE = TMEM_COLS / 2;
+  static constexpr int MAX_STAGES = (227 * 1024 - GEMM_EPI_BYTES - 256 - 1024) / STAGE_BYTES;
+  static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
+};
+template <int BN>
+constexpr int gemm_smem_bytes() { return GCfg<BN>::STAGES * GCfg<BN>::STAGE_BYTES + GEMM_EPI_BYTES + 256 + 1024; }
 constexpr int GEMM_THREADS = 384;   // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-7, 8-11: two epilogue groups
 
 template <int BN, typename OutT>
@@ -39,7 +53,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
                          const float* __restrict__ bias, OutT* __restrict__ C, int64_t ldc, int M, int N,
                          int n_store, int K, int relu, const EarlyExit ee) {
   if (all_done(ee)) return;   // uniform over the grid: written by an earlier kernel of the stream
-  using cfg = Cfg<BN>;
+  using cfg = GCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
@@ -112,7 +126,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
         mbar_wait(tempty_bar(acc), aph ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * cfg::ACC_STRIDE;
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const int s = it % cfg::STAGES;
           const uint32_t ph = (it / cfg::STAGES) & 1u;
@@ -150,7 +164,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           const int col0 = n_blk * BN + c * 32;
           if (col0 >= n_store) break;
           uint32_t v[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + grp * BN + c * 32, v);
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + grp * cfg::ACC_STRIDE + c * 32, v);
           __syncwarp();   // the previous chunk's staged rows have been read
           if constexpr (sizeof(OutT) == 4) {
             // stage the 32x32 fp32 block (row = lane) with a 16-byte XOR swizzle, read it back row-major:
@@ -245,7 +259,6 @@ static int get_tmap(care_ctx* ctx, const void* ptr, uint64_t rows, uint64_t cols
 template <int BN, typename OutT>
 static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, void* C, int64_t ldc,
                   int M, int N, int n_store, int K, int act, cudaStream_t stream) {
-  using cfg = Cfg<BN>;
   static bool configured_all[64] = {false};   // per device: function attributes are per device
   bool& configured = configured_all[ctx->device & 63];
   auto kern = gemm_bf16_tcgen05_kernel<BN, OutT>;
@@ -257,6 +270,7 @@ static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, c
   const int grid = std::min(m_tiles * n_tiles, ctx->sm_count);
   kern<<<grid, GEMM_THREADS, gemm_smem_bytes<BN>(), stream>>>(ta, tb, bias, reinterpret_cast<OutT*>(C), ldc, M, N, n_store, K,
                                                        act == CARE_ACT_RELU ? 1 : 0, early_exit_of(ctx));
+  ctx->last_gemm = sizeof(OutT) == 4 ? "gemm_bf16_tcgen05_kernel<float>" : "gemm_bf16_tcgen05_kernel<h16>";
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -348,17 +362,18 @@ int gemm_bf16(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t 
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   auto tiles = [&](int bn) { return m_tiles * ((N + bn - 1) / bn); };
   // tile width: fewest (waves x per-tile cost); per-tile cost ~ BN + a fixed part (A tile load, epilogue
-  // set-up), so narrow tiles win when 256-wide tiles would leave most SMs idle in the last wave
+  // set-up), so narrower tiles win when 256-wide tiles would leave most SMs idle in the last wave
   int bn = 256;
   int64_t best = INT64_MAX;
-  for (int cand : {256, 128, 64}) {
+  for (int cand : {256, 224, 192, 160, 128, 96, 64}) {
     const int64_t waves = (tiles(cand) + ctx->sm_count - 1) / ctx->sm_count;
-    const int64_t cost = waves * (cand + 64);
+    const int64_t cost = waves * (cand + 48);
     if (cost < best) {
       best = cost;
       bn = cand;
     }
   }
+  if (ctx->gemm_bn > 0) bn = ctx->gemm_bn;   // A/B runs
   CUtensorMap ta, tb;
   int rc = get_tmap(ctx, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BLOCK_M, &ta);
   if (rc) return rc;
@@ -367,9 +382,15 @@ int gemm_bf16(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t 
 #define CARE_TC_DISPATCH(BN_)                                                                          \
   (out_dtype == CARE_F32 ? launch<BN_, float>(ctx, ta, tb, bias, C, ldc, M, N, n_store, K, act, stream) \
                          : launch<BN_, h16>(ctx, ta, tb, bias, C, ldc, M, N, n_store, K, act, stream))
-  if (bn == 256) return CARE_TC_DISPATCH(256);
-  if (bn == 128) return CARE_TC_DISPATCH(128);
-  return CARE_TC_DISPATCH(64);
+  switch (bn) {
+    case 256: return CARE_TC_DISPATCH(256);
+    case 224: return CARE_TC_DISPATCH(224);
+    case 192: return CARE_TC_DISPATCH(192);
+    case 160: return CARE_TC_DISPATCH(160);
+    case 128: return CARE_TC_DISPATCH(128);
+    case 96: return CARE_TC_DISPATCH(96);
+    default: return CARE_TC_DISPATCH(64);
+  }
 #undef CARE_TC_DISPATCH
 }
 

@@ -276,6 +276,7 @@ static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, c
   const int n_clusters = std::min(tiles, ctx->sm_count / 2);
   kern<<<2 * n_clusters, THREADS, SMEM_BYTES, stream>>>(ta, tb, bias, reinterpret_cast<OutT*>(C), ldc, M, N, n_store, K,
                                                         act == CARE_ACT_RELU ? 1 : 0, early_exit_of(ctx));
+  ctx->last_gemm = sizeof(OutT) == 4 ? "gemm_bf16_2sm_kernel<float>" : "gemm_bf16_2sm_kernel<h16>";
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -515,6 +515,7 @@ static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
       configured = true;
     }
     kern<<<2 * (int)l.G, VB_THREADS, p2::SMEM_BYTES, stream>>>(ta, tb, partials, nseg, R, V, d, early_exit_of(ctx));
+    ctx->last_vocab = "vocab_beam_2sm_kernel";
   } else {
     auto kern = vocab_beam_tcgen05_kernel<KB>;
     if (!configured) {
@@ -522,6 +523,7 @@ static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
       configured = true;
     }
     kern<<<(int)l.G, VB_THREADS, cfg::SMEM_BYTES, stream>>>(ta, tb, partials, nseg, R, V, d, early_exit_of(ctx));
+    ctx->last_vocab = "vocab_beam_tcgen05_kernel";
   }
   CARE_LAUNCH_CHECK(ctx);
   return 0;

@@ -106,6 +106,16 @@ class CareEngine:
                 t = torch.nn.functional.pad(t, (0, pad_k - t.shape[1]))
             return t.to(T).contiguous()
 
+        def head32(t, pad_k=None):
+            """Weights of the small ranking heads (concept scores, GSG vector, length logits; M = videos): kept in
+            fp32 and multiplied by the FFMA kernel in every mode - the tensor cores' truncating fp32 accumulation
+            (~2^-18 over a few thousand k) is enough to swap neighbouring concepts, and these GEMMs are ~1 % of a
+            batch."""
+            t = t.detach().to(dev, torch.float32)
+            if pad_k is not None and t.shape[1] != pad_k:
+                t = torch.nn.functional.pad(t, (0, pad_k - t.shape[1]))
+            return t.contiguous()
+
         def mat3(t):
             """Weight of a GEMM whose A operand comes from care_split_f32_h16(terms=3): [W_hi | W_hi | W_lo * 2^11],
             each part zero padded to a multiple of 64 columns (one swizzled TMA row)."""
@@ -148,7 +158,7 @@ class CareEngine:
             if kind == "attribute":
                 if not (opt.get("attribute_prediction_channel_concat") and opt.get("attribute_prediction_mean_pooling")):
                     raise ValueError("only the mean-pooling + channel-concat concept head is accelerated")
-                w["prj_W"] = mat3(sd[p + ".prj.weight"])
+                w["prj_W"] = head32(sd[p + ".prj.weight"])
                 w["prj_b"] = f32(p + ".prj.bias")
             elif kind == "SemanticContainer":
                 w["attr_word"] = f32(p + ".attr_embs.word_embeddings.weight")
@@ -156,11 +166,10 @@ class CareEngine:
                 w["attr_g"] = f32(p + ".attr_embs.LayerNorm.weight")
                 w["attr_b"] = f32(p + ".attr_embs.LayerNorm.bias")
                 if "emb" in opt.get("use_attr_type", ""):
-                    w["s2h_W"] = (mat3(sd[p + ".semantic2hidden.weight"]) if self.half else
-                                  mat(sd[p + ".semantic2hidden.weight"], pad_k=_round_up(self.n_attr, 64)))
+                    w["s2h_W"] = head32(sd[p + ".semantic2hidden.weight"], pad_k=_round_up(self.n_attr, 64))
             elif kind == "length":
-                w["len_W0"] = mat3(sd[p + ".net.0.weight"]); w["len_b0"] = f32(p + ".net.0.bias")
-                w["len_W3"] = mat3(sd[p + ".net.3.weight"]); w["len_b3"] = f32(p + ".net.3.bias")
+                w["len_W0"] = head32(sd[p + ".net.0.weight"]); w["len_b0"] = f32(p + ".net.0.bias")
+                w["len_W3"] = head32(sd[p + ".net.3.weight"]); w["len_b3"] = f32(p + ".net.3.bias")
             else:
                 raise ValueError("predictor %r is outside the accelerated hot path" % kind)
         self.use_gsg = "s2h_W" in w
@@ -267,9 +276,9 @@ class CareEngine:
         """Kernels launched so far: eager launches counted by the library + launches replayed by graphs."""
         return int(self.lib.care_ctx_launch_count(self.ctx)) + self._graph_launches
 
-    def gemm(self, A, W, bias, C, M, N, K, act=ACT_NONE, lda=None, ldc=None):
+    def gemm(self, A, W, bias, C, M, N, K, act=ACT_NONE, lda=None, ldc=None, dt=None):
         out_dt = F32 if C.dtype == torch.float32 else self.dt
-        check(self.lib.care_gemm(self.ctx, self.dt, ptr(A), lda if lda is not None else A.stride(-2), ptr(W),
+        check(self.lib.care_gemm(self.ctx, self.dt if dt is None else dt, ptr(A), lda if lda is not None else A.stride(-2), ptr(W),
                                  W.stride(0), ptr(bias), ptr(C), ldc if ldc is not None else C.stride(-2), out_dt,
                                  M, N, K, act, self._stream()), "care_gemm")
 
@@ -339,15 +348,14 @@ class CareEngine:
         if has_attr:
             ld_sc = _round_up(self.n_attr, 8)
             scores = self._buf("attr_scores", (B, ld_sc), torch.float32)
-            am, km = self._operand("means_h16", means, B, n_pred * d)
-            self.gemm(am, w["prj_W"], w["prj_b"], scores, B, self.n_attr, km)
+            self.gemm(means, w["prj_W"], w["prj_b"], scores, B, self.n_attr, n_pred * d, dt=F32)
             preds = torch.empty((B, self.n_attr), dtype=torch.float32, device=self.device)
             out["preds_attr"] = preds
             if "SemanticContainer" in self.nets:
                 predsT = kpad = None
-                if self.use_gsg and not self.half:
+                if self.use_gsg:
                     kpad = w["s2h_W"].shape[1]
-                    predsT = self._buf("preds_T", (B, kpad), T)
+                    predsT = self._buf("preds_T", (B, kpad), torch.float32)
                 labels = torch.empty((B, self.n_concepts), dtype=torch.int64, device=self.device)
                 sem = None
                 if not self.concat_concepts and self.attr_pos is not None:
@@ -362,9 +370,7 @@ class CareEngine:
                 out["semantic_labels"] = labels
                 if self.use_gsg:
                     gsg = torch.empty((B, d), dtype=torch.float32, device=self.device)
-                    if self.half:
-                        predsT, kpad = self._operand("preds_h16", preds, B, self.n_attr)
-                    self.gemm(predsT, w["s2h_W"], None, gsg, B, d, kpad)
+                    self.gemm(predsT, w["s2h_W"], None, gsg, B, d, kpad, dt=F32)
                     out["semantic_hidden_states"] = gsg
             else:
                 check(lib.care_concept_head(
@@ -386,11 +392,9 @@ class CareEngine:
         check(self.lib.care_combine_means(self.ctx, F32, ptr(means), B, n_pred, d, weights, ptr(comb), d,
                                           self._stream()), "care_combine_means")
         hid = self._buf("len_hid", (B, d), torch.float32)
-        a, k = self._operand("len_in_h16", comb, B, d)
-        self.gemm(a, w["len_W0"], w["len_b0"], hid, B, d, k, act=ACT_RELU)
+        self.gemm(comb, w["len_W0"], w["len_b0"], hid, B, d, d, act=ACT_RELU, dt=F32)
         logits = torch.empty((B, _round_up(self.max_len, 8)), dtype=torch.float32, device=self.device)
-        a, k = self._operand("len_hid_h16", hid, B, d)
-        self.gemm(a, w["len_W3"], w["len_b3"], logits, B, self.max_len, k)
+        self.gemm(hid, w["len_W3"], w["len_b3"], logits, B, self.max_len, d, dt=F32)
         return logits
 
     def cross_kv(self, memory, static=False):

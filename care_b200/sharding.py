@@ -72,14 +72,52 @@ def gather_hypotheses(payload: torch.Tensor, n_total: int, group=None) -> torch.
     return torch.cat(parts, dim=0)
 
 
+def pack_nar(tokens: torch.Tensor, lprobs: torch.Tensor, max_len: int) -> torch.Tensor:
+    """Mask-predict results of one rank -> int32 records [B, 1, 2 * max_len + 1]: ids (PAD = 0 beyond the rank's
+    canvas length L), log-probability bits (0.0 = log 1 beyond L, what the reference holds at <pad> slots,
+    na_algorithms.py:78-79) and L itself - ranks see different longest length candidates (Translator.py:273)."""
+    B, _, L = tokens.shape
+    rec = tokens.new_zeros((B, 1, 2 * max_len + 1), dtype=torch.int32)
+    rec[..., :L] = tokens
+    rec[..., max_len:max_len + L] = lprobs.contiguous().view(torch.int32)
+    rec[..., 2 * max_len] = L
+    return rec
+
+
+def unpack_nar(payload: torch.Tensor, max_len: int):
+    """Inverse of pack_nar over the gathered records; the canvas length of the whole batch is the largest L."""
+    if payload.shape[0] == 0:
+        return payload[..., :0], payload[..., :0].view(torch.float32)
+    L = int(payload[..., 2 * max_len].max().item())
+    return payload[..., :L].contiguous(), payload[..., max_len:max_len + L].contiguous().view(torch.float32)
+
+
 def translate_sharded(translator, model, batch: Dict, group=None) -> Tuple[List, List]:
-    """`Translator_ARFormer.translate_batch` over the whole batch with the videos sharded over the
-    ranks of `group`; every rank returns the full (hyps, scores) in input order."""
+    """`translate_batch` (Translator_ARFormer or Translator_NARFormer) over the whole batch with the videos
+    sharded over the ranks of `group`; every rank returns the full (hyps, scores) in input order.  A rank whose
+    shard is empty (fewer videos than ranks) skips the decode and contributes zero records to the gather."""
     from .engine import hyps_from_device
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     n_total = batch["feats"][0].shape[0]
+    if n_total == 0:
+        return [], []
     local = shard_batch(batch, rank, world)
+    n_local = local["feats"][0].shape[0]
+    dev = model.engine().device if model is not None else local["feats"][0].device   # (None: CPU stand-in tests)
+    nar = hasattr(translator, "length_beam_size")
+    Tm = translator.max_len - 1
     with torch.no_grad():
-        out = translator.decode_on_device(model, local["feats"])
-    full = gather_hypotheses(pack_hypotheses(*out), n_total, group)
+        if nar:
+            if n_local:
+                payload = pack_nar(*translator.decode_on_device(model, local["feats"]), translator.max_len)
+            else:
+                payload = torch.zeros((0, 1, 2 * translator.max_len + 1), dtype=torch.int32, device=dev)
+        elif n_local:
+            payload = pack_hypotheses(*translator.decode_on_device(model, local["feats"]))
+        else:
+            payload = torch.zeros((0, translator.topk, Tm + 3), dtype=torch.int32, device=dev)
+    full = gather_hypotheses(payload, n_total, group)
+    if nar:
+        tokens, lprobs = unpack_nar(full, translator.max_len)
+        return tokens.cpu().tolist(), lprobs.cpu().tolist()
     return hyps_from_device(*unpack_hypotheses(full), translator.beam_alpha, translator.topk)

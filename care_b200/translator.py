@@ -229,9 +229,15 @@ class Translator_NARFormer(object):
         model = _single_model(models)
         if batch["feats"][0].shape[0] == 0:
             return [], []
-        eng = model.engine()
         with torch.no_grad():
-            enc = model.encoding_phase(batch["feats"])
-            tokens, lprobs = eng.mask_predict(enc, self.opt, self.length_beam_size, self.length_bias,
-                                              self.beam_alpha)
+            tokens, lprobs = self.decode_on_device(model, batch["feats"])
         return tokens.cpu().tolist(), lprobs.cpu().tolist()
+
+    def decode_on_device(self, model, feats, trace=None):
+        """Returns device tensors: ids [B, 1, L] int32 (PAD after each caption's length) and per-token
+        log-probabilities [B, 1, L] fp32, L = the longest length candidate of THIS batch (Translator.py:273)."""
+        eng = model.engine()
+        if eng.max_len != self.max_len:
+            raise ValueError("translator max_len %d != model max_len %d" % (self.max_len, eng.max_len))
+        enc = model.encoding_phase(feats)
+        return eng.mask_predict(enc, self.opt, self.length_beam_size, self.length_bias, self.beam_alpha, trace=trace)

@@ -55,6 +55,10 @@ const char* care_last_error(void);
 int care_ctx_create(care_ctx** out, int device);
 void care_ctx_destroy(care_ctx* ctx);
 int care_ctx_sm_count(const care_ctx* ctx);
+/* name of the kernel variant the most recent call of a family launched through this ctx: family = "gemm"
+ * (care_gemm), "vocab" (care_vocab_beam_partials) or "self_attn" (care_self_attn_step); bench.py labels its
+ * roofline records with it */
+const char* care_ctx_last_kernel(const care_ctx* ctx, const char* family);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches claim) */
 int64_t care_ctx_launch_count(const care_ctx* ctx);
 /* Device-side early exit for a decode loop with no host polling: while `counter` is non-NULL every
@@ -127,7 +131,8 @@ int care_encoder_highway_bn_mean(care_ctx* ctx, int dtype, const float* h, const
 
 /* Concept head (pred_attribute.py:17-46 noisy-or, :262-289 SemanticContainer, Embeddings.py:53-87
  * NaiveEmbeddings, Framework.py:184-185 concat).  scores fp32 [B, ld_scores] = prj output incl. bias.
- * preds_f32 [B, n_attr]; preds_T [B, ld_preds_T] (A operand of semantic2hidden, zero padded);
+ * preds_f32 [B, n_attr]; preds_T fp32 [B, ld_preds_T] (A operand of semantic2hidden, zero padded; fp32 in
+ * every mode: the small ranking heads run on the FFMA GEMM);
  * labels int64 [B, topk] sorted by (prob desc, index asc); LN(word[label]+pos[rank]) written as T
  * into memory rows mem_row0 .. mem_row0+topk-1 of each video ([B, mem_rows, d]). */
 int care_concept_head(care_ctx* ctx, int dtype, const float* scores, int64_t ld_scores, int B,

@@ -14,8 +14,8 @@ import sys
 import torch
 
 from oracle import ref_harness as rh
-from oracle.shapes import CONFIGS, make_feats, make_opt
-from oracle.weights import SHARP, TRAINED, make_state_dict, param_count
+from synth.shapes import CONFIGS, make_feats, make_opt
+from synth.weights import SHARP, TRAINED, make_state_dict, param_count
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 

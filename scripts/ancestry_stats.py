@@ -8,13 +8,13 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import care_b200  # noqa: E402
-from oracle.shapes import CONFIGS, make_feats, make_opt  # noqa: E402
-from oracle.weights import SHARP, make_state_dict  # noqa: E402
+from synth.shapes import CONFIGS, make_feats, make_opt  # noqa: E402
+from synth.weights import SHARP, make_state_dict  # noqa: E402
 
 for name, kw in (("plain", dict(seed=0)), ("sharp", dict(seed=1, perturb=True, sharpen=SHARP))):
     opt = make_opt(**CONFIGS["cfg4"])
     sd = make_state_dict(opt, **kw)
-    model = care_b200.get_framework(dict(opt, care_precision="bf16", care_cuda_graph=False))
+    model = care_b200.get_framework(dict(opt, care_precision="fp16", care_cuda_graph=False))
     model.load_state_dict(sd)
     model = model.eval().cuda()
     tr = care_b200.get_translator(opt)

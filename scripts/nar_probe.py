@@ -7,13 +7,13 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import care_b200  # noqa: E402
-from oracle.shapes import CONFIGS, make_feats, make_opt  # noqa: E402
-from oracle.weights import make_state_dict  # noqa: E402
+from synth.shapes import CONFIGS, make_feats, make_opt  # noqa: E402
+from synth.weights import make_state_dict  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 opt = make_opt(**CONFIGS["cfg5"])
-model = care_b200.get_framework(dict(opt, care_precision="bf16"))
+model = care_b200.get_framework(dict(opt, care_precision="fp16"))
 model.load_state_dict(make_state_dict(opt, seed=0, perturb=True))
 model = model.eval().cuda()
 tr = care_b200.get_translator(opt)

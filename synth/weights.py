@@ -1,0 +1,160 @@
+"""Seeded synthetic checkpoints with the reference's state_dict layout.
+
+TEST / BENCH INFRASTRUCTURE.  Builds `{name: fp32 tensor}` with exactly the keys and shapes the
+reference's `get_framework(opt).state_dict()` has (checked against the real reference in
+tests/test_oracle_vs_reference.py and against tests/golden/state_dict_*.json), following the
+distributions of `Seq2SeqBase._init_weights` (models/Framework.py:115-134): xavier-uniform
+Linear / Embedding weights, zero biases, LayerNorm gamma=1 beta=0, PAD row of the decoder word
+embedding zeroed, `hybrid_bias` zeros (models/components/Attention.py:51), BatchNorm running
+stats (0, 1).
+
+`perturb=True` additionally randomises everything the plain init leaves degenerate (biases, LN
+affine, hybrid_bias, BN stats) so parity tests exercise those terms.  `sharpen` rescales the
+vocabulary projection so that beams actually reach <eos>/<pad> (SURVEY.md §7 "hard parts").
+The generator is torch's CPU Philox/MT stream, which is reproducible on the GPU box (same image).
+"""
+import math
+from collections import OrderedDict
+
+import torch
+
+PAD, UNK, BOS, EOS, MASK, VIS = 0, 1, 2, 3, 4, 5  # config/Constants.py:1-6
+
+
+def _xavier(gen, rows, cols):
+    bound = math.sqrt(6.0 / (rows + cols))
+    return (torch.rand(rows, cols, generator=gen) * 2.0 - 1.0) * bound
+
+
+def _linear(sd, gen, name, out_f, in_f, bias=True):
+    sd[name + ".weight"] = _xavier(gen, out_f, in_f)
+    if bias:
+        sd[name + ".bias"] = torch.zeros(out_f)
+
+
+def _layernorm(sd, name, d):
+    sd[name + ".weight"] = torch.ones(d)
+    sd[name + ".bias"] = torch.zeros(d)
+
+
+def hybrid_length(opt):
+    """models/components/Layers.py:85-90"""
+    modality = opt.get("modality_for_decoder") or opt["modality"]
+    n = opt["n_frames"] * len(modality) + opt.get("use_attr_topk", 30)
+    if "r" in modality:
+        n += opt["retrieval_topk"] - opt["n_frames"]
+    return n
+
+
+def make_state_dict(opt, seed=0, perturb=False, sharpen=None):
+    gen = torch.Generator().manual_seed(1000003 * seed + 17)
+    d = opt["dim_hidden"]
+    sd = OrderedDict()
+    highway = opt["encoder"] == "EncoderWithHighWayBN"
+    for ch in opt["modality"]:
+        p = "encoder.Encoder_%s" % ch.upper()
+        _linear(sd, gen, p + ".0", d, opt["dim_" + ch])
+        if highway:  # models/Encoder.py:184-187
+            _linear(sd, gen, p + ".1.w1", d, d)
+            _linear(sd, gen, p + ".1.w2", d, d)
+            sd[p + ".2.bn.weight"] = torch.ones(d)
+            sd[p + ".2.bn.bias"] = torch.zeros(d)
+            sd[p + ".2.bn.running_mean"] = torch.zeros(d)
+            sd[p + ".2.bn.running_var"] = torch.ones(d)
+            sd[p + ".2.bn.num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+        else:  # models/Encoder.py:165-168
+            _layernorm(sd, p + ".1", d)
+    net = 0
+    if "attribute" in opt["crits"]:
+        nm = len(opt.get("modality_for_predictor") or opt["modality"])
+        _linear(sd, gen, "predictor.nets.%d.prj" % net, opt["attribute_prediction_k"], d * nm)
+        net += 1
+    length_net = "length" in opt["crits"]
+    if length_net and not opt.get("load_teacher_weights", False):
+        # models/Predictor/__init__.py:30-58: crit order unless load_teacher_weights moves it last
+        _linear(sd, gen, "predictor.nets.%d.net.0" % net, d, d)
+        _linear(sd, gen, "predictor.nets.%d.net.3" % net, opt["max_len"], d)
+        net += 1
+        length_net = False
+    if "SemanticContainer" in opt.get("predictors_to_be_added", []):
+        p = "predictor.nets.%d" % net
+        sd[p + ".attr_embs.word_embeddings.weight"] = _xavier(gen, opt["attribute_prediction_k"], d)
+        sd[p + ".attr_embs.position_embeddings.weight"] = _xavier(gen, opt["use_attr_topk"], d)
+        _layernorm(sd, p + ".attr_embs.LayerNorm", d)
+        if "emb" in opt.get("use_attr_type", ""):   # pred_attribute.py:258-260
+            _linear(sd, gen, p + ".semantic2hidden", d, opt["attribute_prediction_k"], bias=False)
+        net += 1
+    if length_net:
+        _linear(sd, gen, "predictor.nets.%d.net.0" % net, d, d)
+        _linear(sd, gen, "predictor.nets.%d.net.3" % net, opt["max_len"], d)
+        net += 1
+    we = _xavier(gen, opt["vocab_size"], d)
+    we[PAD].zero_()
+    sd["decoder.embedding.word_embeddings.weight"] = we
+    sd["decoder.embedding.position_embeddings.weight"] = _xavier(gen, opt["max_len"], d)
+    _layernorm(sd, "decoder.embedding.LayerNorm", d)
+    L = "decoder.layers.0."
+    atts = ["intra_attention", "inter_attention"]
+    if opt.get("use_attr", False) and "att" in opt.get("use_attr_type", "att"):
+        atts.append("attr_attention")   # deepcopy of inter_attention (models/components/Layers.py:117-119)
+    for att in atts:
+        if att != "intra_attention" and opt.get("add_hybrid_attention_bias", False):
+            sd[L + att + ".SDPA.hybrid_bias"] = torch.zeros(opt["num_attention_heads"], hybrid_length(opt))
+        for nm_ in ("query", "key", "value"):
+            _linear(sd, gen, L + att + ".SDPA." + nm_, d, d)
+        _linear(sd, gen, L + att + ".dense", d, d)
+        _layernorm(sd, L + att + ".LayerNorm", d)
+    _linear(sd, gen, L + "ffn.dense1", opt["intermediate_size"], d)
+    _linear(sd, gen, L + "ffn.dense2", d, opt["intermediate_size"])
+    _layernorm(sd, L + "ffn.LayerNorm", d)
+    _linear(sd, gen, "cls_head.tgt_word_prj", opt["vocab_size"], d, bias=False)
+
+    if perturb:
+        for k in list(sd.keys()):
+            v = sd[k]
+            if k.endswith("num_batches_tracked"):
+                continue
+            if k.endswith("running_var"):
+                sd[k] = 0.5 + torch.rand(v.shape, generator=gen)
+            elif k.endswith("running_mean") or k.endswith("hybrid_bias"):
+                sd[k] = 0.3 * torch.randn(v.shape, generator=gen)
+            elif k.endswith(".bias"):
+                sd[k] = 0.05 * torch.randn(v.shape, generator=gen)
+            elif "LayerNorm.weight" in k or k.endswith(".1.weight") and v.dim() == 1 or k.endswith("bn.weight"):
+                sd[k] = 1.0 + 0.1 * torch.randn(v.shape, generator=gen)
+    if sharpen:
+        w = sd["cls_head.tgt_word_prj.weight"]
+        w.mul_(float(sharpen.get("scale", 1.0)))
+        if sharpen.get("row_lognorm"):
+            # heavy-tailed logits: per-token log-normal row norms (a trained head has frequent / rare tokens)
+            w.mul_(torch.exp(float(sharpen["row_lognorm"]) * torch.randn(w.shape[0], 1, generator=gen)))
+        w[EOS].mul_(float(sharpen.get("eos_scale", 1.0)))
+        w[PAD].mul_(float(sharpen.get("pad_scale", 1.0)))
+        sd["decoder.embedding.word_embeddings.weight"].mul_(float(sharpen.get("emb_scale", 1.0)))
+        for k in sd:
+            if k.endswith("semantic2hidden.weight"):
+                sd[k].mul_(float(sharpen.get("gsg_scale", 1.0)))
+    return sd
+
+
+def param_count(sd):
+    return sum(v.numel() for k, v in sd.items()
+               if not (k.endswith("running_mean") or k.endswith("running_var")
+                       or k.endswith("num_batches_tracked")))
+
+
+# A sharpening preset under which beams end at many different lengths and <pad> is generated
+# (found empirically with the oracle; see oracle/make_golden.py).
+SHARP = dict(scale=6.0, eos_scale=2.0, pad_scale=2.0, emb_scale=30.0, gsg_scale=0.1)
+
+# "Trained-like" peakedness (round 2): the vocabulary projection is scaled until the fp32 model's
+# next-token distributions on its own beam prefixes look like a trained captioner's (top-1 probability
+# median ~0.6, entropy ~1-2 nats instead of ln V = 9.6) and <eos> is boosted so that captions end at
+# lengths spread over ~5-25 tokens.  tests/bf16_budget.py prints the statistics.
+TRAINED = dict(scale=20.0, eos_scale=2.5, pad_scale=1.0, emb_scale=30.0, gsg_scale=0.1)
+
+PRESETS = {
+    "plain": dict(seed=0),
+    "sharp": dict(seed=5, perturb=True, sharpen=SHARP),
+    "trained": dict(seed=31, perturb=True, sharpen=TRAINED),
+}

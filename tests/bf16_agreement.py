@@ -8,8 +8,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import care_b200  # noqa: E402
-from oracle.shapes import CONFIGS, make_feats, make_opt  # noqa: E402
-from oracle.weights import SHARP, make_state_dict  # noqa: E402
+from synth.shapes import CONFIGS, make_feats, make_opt  # noqa: E402
+from synth.weights import SHARP, make_state_dict  # noqa: E402
 
 for cfg, kw, name in (("cfg4", dict(seed=0), "plain"), ("cfg4", dict(seed=5, perturb=True, sharpen=SHARP), "sharp")):
     opt = make_opt(**CONFIGS[cfg])

@@ -28,8 +28,8 @@ import torch
 import torch.nn.functional as F
 
 from oracle import care_oracle as co
-from oracle.shapes import CONFIGS, make_feats, make_opt
-from oracle.weights import PRESETS, make_state_dict
+from synth.shapes import CONFIGS, make_feats, make_opt
+from synth.weights import PRESETS, make_state_dict
 
 PAD = 0
 

@@ -13,8 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import care_b200  # noqa: E402
 from oracle import care_oracle as co  # noqa: E402
-from oracle.shapes import CONFIGS, make_feats, make_opt  # noqa: E402
-from oracle.weights import SHARP, make_state_dict  # noqa: E402
+from synth.shapes import CONFIGS, make_feats, make_opt  # noqa: E402
+from synth.weights import SHARP, make_state_dict  # noqa: E402
 
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 0)

@@ -3,8 +3,8 @@ import glob
 import json
 import os
 
-from oracle.shapes import CONFIGS, make_feats, make_opt
-from oracle.weights import make_state_dict
+from synth.shapes import CONFIGS, make_feats, make_opt
+from synth.weights import make_state_dict
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 

@@ -49,8 +49,8 @@ def test_product_never_imports_oracle():
 
 def test_framework_layout_and_cpu_refusal():
     import care_b200
-    from oracle.shapes import CONFIGS, make_opt
-    from oracle.weights import make_state_dict
+    from synth.shapes import CONFIGS, make_opt
+    from synth.weights import make_state_dict
     for cfg in ("cfg1", "cfg2", "cfg5", "cab"):
         opt = make_opt(**CONFIGS[cfg])
         m = care_b200.get_framework(opt)

@@ -147,6 +147,29 @@ def test_gemm_cta_pair_matches_single_cta(env, M, N, K, out_dtype):
     assert (outs[0].float() - outs[1].float()).abs().max().item() < tol * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("bn", [64, 96, 128, 160, 192, 224, 256])
+@pytest.mark.parametrize("M,N,K", [(2560, 1024, 1024), (300, 1000, 4096), (2560, 3072, 1024)])
+def test_gemm_tile_widths(env, bn, M, N, K):
+    """Every tile width of the single-CTA tensor-core GEMM (forced through the `gemm_bn` option) against fp64."""
+    lib, h, L = env
+    g = torch.Generator(device="cuda").manual_seed(bn + M)
+    A = torch.randn(M, K, device="cuda", generator=g).to(TH)
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(TH)
+    b = torch.randn(N, device="cuda", generator=g)
+    ref = A.double() @ W.double().t() + b.double()
+    try:
+        L.check(lib.care_ctx_set_option(h, b"gemm_2sm", 0), "opt")
+        L.check(lib.care_ctx_set_option(h, b"gemm_bn", bn), "opt")
+        for out_dtype in (torch.float32, TH):
+            C = _gemm(env, H16, A, W, b, out_dtype, 0)
+            err = (C[:, :N].double() - ref).abs().max().item()
+            tol = 2e-5 if out_dtype == torch.float32 else (2e-3 if H16_NAME == "fp16" else 1.6e-2)
+            assert err < tol * max(1.0, ref.abs().max().item()), (bn, out_dtype, err)
+    finally:
+        lib.care_ctx_set_option(h, b"gemm_bn", 0)
+        lib.care_ctx_set_option(h, b"gemm_2sm", 2)
+
+
 def test_gemm_bf16_strided_output(env):
     """QKV GEMM writes straight into a [T, R, 3d] cache slice and reads strided A."""
     lib, h, L = env
@@ -192,7 +215,8 @@ def test_split_cast(env, cols):
     err = (C[:, :N].double() - ref).abs().max().item() / ref.abs().max().item()
     plain = (_gemm(env, H16, y1, whi.contiguous(), None, torch.float32)[:, :N].double() - ref).abs().max().item() / ref.abs().max().item()
     print("split-3 product rel err %.2e (plain 16-bit operands: %.2e)" % (err, plain))
-    assert err < (2e-6 if H16_NAME == "fp16" else 5e-5)
+    # operands carry ~22 bits; what remains is the tensor core's truncating fp32 accumulation (~2^-18 over K/16 steps)
+    assert err < (6e-6 if H16_NAME == "fp16" else 5e-5)
 
 
 def test_other_16bit_code_is_refused(env):
@@ -259,7 +283,7 @@ def test_concept_head(env, dt, T):
     ap = torch.randn(topk, d, device="cuda")
     g, b = torch.randn(d, device="cuda"), torch.randn(d, device="cuda")
     preds = torch.empty(B, n_attr, device="cuda")
-    predsT = torch.full((B, 512), 7.0, device="cuda", dtype=T)
+    predsT = torch.full((B, 512), 7.0, device="cuda", dtype=torch.float32)
     labels = torch.empty(B, topk, device="cuda", dtype=torch.int64)
     mem = torch.zeros(B, Lm, d, device="cuda", dtype=T)
     L.check(lib.care_concept_head(h, dt, scores.data_ptr(), 504, B, n_attr, topk, aw.data_ptr(), ap.data_ptr(),
@@ -270,7 +294,7 @@ def test_concept_head(env, dt, T):
     ref = 1.0 - torch.exp(torch.log(torch.clamp(1.0 - torch.sigmoid(s), 1e-12, 1)))
     assert (preds - ref).abs().max().item() < 1e-6
     assert (predsT[:, n_attr:] == 0).all()
-    assert (predsT[:, :n_attr].float() - preds).abs().max().item() < (1e-7 if dt == F32 else 4e-3)
+    assert (predsT[:, :n_attr].float() - preds).abs().max().item() == 0.0
     # ordering rule on the kernel's own probabilities: (prob desc, index asc)
     p = preds.cpu().numpy()
     for v in range(B):

@@ -500,8 +500,8 @@ def test_unusual_shapes_fp32_vs_oracle(over):
     """Beam widths up to the kernels' limit (8), n_best > 1, short max_len, odd vocabulary sizes: the fp32
     CUDA path against the oracle (no golden for these; the oracle itself is pinned to the reference)."""
     import care_b200
-    from oracle.shapes import CONFIGS, make_feats, make_opt
-    from oracle.weights import SHARP, make_state_dict
+    from synth.shapes import CONFIGS, make_feats, make_opt
+    from synth.weights import SHARP, make_state_dict
     opt = make_opt(**{**CONFIGS["cfg2"], **over})
     sd = make_state_dict(opt, seed=31, perturb=True, sharpen=SHARP)
     feats = make_feats(opt, 7, seed=13)
@@ -561,8 +561,8 @@ def test_full_size_batch_properties():
     the CTA-pair GEMM tiles).  (2) fp32: eight videos spread over the batch match the CPU oracle and the
     same videos decoded alone."""
     import care_b200
-    from oracle.shapes import CONFIGS, make_feats, make_opt
-    from oracle.weights import SHARP, make_state_dict
+    from synth.shapes import CONFIGS, make_feats, make_opt
+    from synth.weights import SHARP, make_state_dict
     opt = make_opt(**CONFIGS["cfg4"])
     sd = make_state_dict(opt, seed=5, perturb=True, sharpen=SHARP)
     half = make_feats(opt, 2048, seed=77)

@@ -6,7 +6,7 @@ import torch
 
 import care_b200
 from care_b200.engine import carry_n_best, hyps_from_device
-from oracle.shapes import CONFIGS, make_opt
+from synth.shapes import CONFIGS, make_opt
 
 
 def test_to_sentence_stops_at_eos_and_pad():

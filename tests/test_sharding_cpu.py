@@ -45,7 +45,7 @@ def test_shard_batch_slices_every_per_video_field():
 
 class _FakeTranslator:
     """Stands in for Translator_ARFormer: 'decodes' video v to tokens derived from its features."""
-    beam_alpha, topk = 1.0, 1
+    beam_alpha, topk, max_len = 1.0, 1, 7
 
     def decode_on_device(self, model, feats):
         x = feats[0]
@@ -58,7 +58,33 @@ class _FakeTranslator:
         return tok, ln.to(torch.int32), score, ln.to(torch.int32)
 
 
-def _worker(rank, world, port, n, q):
+class _FakeNarTranslator:
+    """Stands in for Translator_NARFormer: the canvas length L depends on the shard's content."""
+    max_len, length_beam_size = 9, 6
+
+    def decode_on_device(self, model, feats):
+        key = feats[0].view(feats[0].shape[0], -1)[:, 0].to(torch.int32)
+        B = key.shape[0]
+        lens = key % 5 + 4
+        L = int(lens.max())
+        pos = torch.arange(L, dtype=torch.int32).view(1, 1, L)
+        tok = torch.where(pos < lens.view(B, 1, 1), key.view(B, 1, 1) + pos + 6, torch.zeros_like(pos))
+        lp = torch.where(pos < lens.view(B, 1, 1), -(key.view(B, 1, 1) + pos).float() / 7, torch.zeros(1, 1, L))
+        return tok.to(torch.int32).contiguous(), lp.contiguous()
+
+
+def test_pack_unpack_nar_roundtrip():
+    tr = _FakeNarTranslator()
+    tok, lp = tr.decode_on_device(None, [torch.arange(6).float().view(6, 1, 1) + 3])
+    rec = sharding.pack_nar(tok, lp, tr.max_len)
+    assert rec.shape == (6, 1, 2 * tr.max_len + 1)
+    t2, l2 = sharding.unpack_nar(rec, tr.max_len)
+    assert torch.equal(t2, tok) and torch.equal(l2, lp)
+
+
+def _worker(rank, world, port, n, q, nar=False):
+    if nar:
+        return _worker_nar(rank, world, port, n, q)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -71,7 +97,41 @@ def _worker(rank, world, port, n, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n", [7, 8])
+def _worker_nar(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        feats = [torch.arange(n).float().view(n, 1, 1) + 3]
+        hyps, scores = sharding.translate_sharded(_FakeNarTranslator(), None, {"feats": feats})
+        q.put((rank, hyps, scores))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [1, 5, 8])
+def test_translate_sharded_nar_gloo_world2(n):
+    """Mask-predict results through the sharded path: ranks with different canvas lengths (and, for n = 1, an
+    EMPTY shard on rank 1) still return the single-process answer on every rank."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q, True)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    tok, lp = _FakeNarTranslator().decode_on_device(None, [torch.arange(n).float().view(n, 1, 1) + 3])
+    for rank, hyps, scores in results:
+        assert hyps == tok.tolist() and scores == lp.tolist(), rank
+
+
+@pytest.mark.parametrize("n", [1, 7, 8])
 def test_translate_sharded_gloo_world2(n):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

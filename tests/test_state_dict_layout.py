@@ -4,8 +4,8 @@ reference's own state_dict captured in tests/golden/state_dict_layout.json."""
 import json
 import os
 
-from oracle.shapes import CONFIGS, make_opt
-from oracle.weights import make_state_dict, param_count
+from synth.shapes import CONFIGS, make_opt
+from synth.weights import make_state_dict, param_count
 from tests.helpers import GOLDEN
 
 
