@@ -259,7 +259,10 @@ def test_fused_vocab_records_direct():
         W = (torch.randn(V, d, device="cuda", generator=g) * 0.08).half()
         nseg = int(lib.care_vocab_beam_nseg(h, R, V))
         kb = 6
-        part = torch.full((R, nseg, 2 + 2 * kb), float("nan"), device="cuda")
+        # nseg is the maximum over row blocks; segments a row block does not have stay untouched (beam.cu derives
+        # which exist from the tile schedule), so they start as neutral records here
+        part = torch.full((R, nseg, 2 + 2 * kb), float("-inf"), device="cuda")
+        part[:, :, 1] = 0.0
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(lib.care_vocab_beam_partials(h, x.data_ptr(), d, W.data_ptr(), d, R, V, d, K, part.data_ptr(), nseg,
                                                 st), "vocab_beam")
