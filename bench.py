@@ -209,6 +209,8 @@ def kernel_work_table(esz, lib, ctx):
                                           (a[4] * a[5] * a[3] * 2.0 * a[7] + 2.0 * a[4] * a[5] * a[7]) * esz),
         # full-sequence attention (mask-predict passes): per group K and V once + q in + ctx out
         "care_group_attn": lambda a: ("group_attn_mma_kernel", "hbm", a[8] * (a[10] * 2.0 + a[9] * 2.0) * a[12] * esz),
+        # args: ctx, A, lda, W, ldw, bias, residual, residual_dtype, gamma, beta, eps, out16, out32, M, N, K, stream
+        "care_gemm_add_ln": lambda a: (gemm(), "tensor", 2.0 * a[13] * a[14] * a[15]),
         "care_add_ln": lambda a: ("add_ln_kernel", "hbm", a[7] * a[8] * (4.0 + 2 * esz)),
         "care_beam_step": lambda a: ("beam_row_kernel", "hbm", 0.0),
     }

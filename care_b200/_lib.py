@@ -49,9 +49,11 @@ _SIGNATURES = {
                                   c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_int64, c_void_p,
                                   c_void_p, c_int, c_int, c_void_p]),
     "care_embed_ln": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                              c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p]),
+                              c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "care_add_ln": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int,
                             c_void_p, c_void_p]),
+    "care_gemm_add_ln": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p,
+                                 c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "care_self_attn_step": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "care_cross_attn_step": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int,

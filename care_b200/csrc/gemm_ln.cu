@@ -1,0 +1,448 @@
+// out = LayerNorm(A[M,K] * W[N,K]^T + bias + residual) * gamma + beta, N = d (512 / 768 / 1024), in ONE kernel.
+//
+// The three residual sub-layers of a decoder layer (attention output projections, FFN second Linear) end in
+// dropout(identity) -> + residual -> LayerNorm (models/components/SubLayers.py:68-79,137-152).  A row's
+// LayerNorm needs all d output columns, but d = 1024 fp32 accumulator columns do not fit one SM's tensor
+// memory twice (512 columns).  So a thread-block CLUSTER of CN = d / 256 CTAs shares one 128-row block: CTA r
+// computes columns [256 r, 256 r + 256) with the mainloop of gemm_tcgen05.cu (TMA producer warp, single-thread
+// tcgen05.mma issuer, accumulator double-buffered in TMEM), and the epilogue makes two passes over its
+// accumulator:
+//   pass 1  v = acc + bias + residual, written back to TMEM in place; per-row (sum, sum of squares) over the
+//           CTA's 256 columns stay in the row's thread and are sent to the other CTAs of the cluster with
+//           st.async into their shared memory (completion counted on an mbarrier there - no cluster-wide
+//           barrier, the producer / MMA warps never stop);
+//   pass 2  mean / rstd from the CN partial statistics, y = (v - mean) * rstd * gamma + beta, converted and
+//           stored through a swizzled shared-memory transpose as 64-byte row segments.
+// The fp32 pre-LayerNorm tensor of the unfused path (84 MB written and read back per sub-layer at cfg4) never
+// exists, and a decode step has three launches fewer.  R32 = true keeps the residual stream in fp32: the
+// residual is read as fp32 and the output is written both as fp32 (the next sub-layer's residual) and as the
+// 16-bit GEMM operand.
+#include <algorithm>
+#include <cstdint>
+
+#include "tcgen05_util.cuh"
+
+namespace care {
+namespace gln {
+
+using namespace care::tc;
+
+constexpr int BN = 256;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int B_BYTES = BN * BLOCK_K * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int THREADS = 384;        // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-7, 8-11: two epilogue groups
+constexpr int XP_BYTES = 2048;      // per epilogue warp: one 32-row x 64-byte transposition block
+constexpr int MAX_CN = 4;
+constexpr int STAT_SLOT = BLOCK_M * 8;                          // (sum, sumsq) of 128 rows from one peer CTA
+constexpr int STATS_BYTES = 2 * 2 * (MAX_CN - 1) * STAT_SLOT;   // [group][parity][peer]
+constexpr int PARAM_BYTES = 3 * BN * 4;                         // bias | gamma | beta of this CTA's columns
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * XP_BYTES + STATS_BYTES + PARAM_BYTES + BAR_BYTES + 1024;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+// 8 bytes into a peer CTA's shared memory; the peer's mbarrier counts them (complete_tx)
+__device__ __forceinline__ void st_async_f2(uint32_t remote_addr, float a, float b, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(remote_addr),
+               "f"(a), "f"(b), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+// [32 rows x 64 bytes] transposition block: physical offset of 16-byte chunk c16 of row r; conflict-free both
+// for "lane = row" accesses and for the coalesced mapping (4 lanes per row)
+__device__ __forceinline__ uint32_t xp_off(int r, int c16) { return (uint32_t)(r * 64 + ((c16 ^ ((r >> 1) & 3)) << 4)); }
+
+// coalesced global -> registers: lane handles rows i*8 + (lane >> 2), i = 0..3, 16-byte chunk (lane & 3)
+__device__ __forceinline__ void ldg_block(const uint8_t* base, int64_t ld_bytes, int row0, int M, int lane, uint4 (&g)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2);
+    g[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (row0 + r < M) g[i] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(row0 + r) * ld_bytes + (lane & 3) * 16));
+  }
+}
+// registers (coalesced mapping) -> smem block -> this lane's own row (64 bytes)
+__device__ __forceinline__ void xp_to_rows(uint8_t* xp, int lane, const uint4 (&g)[4], uint4 (&row)[4]) {
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(xp + xp_off(i * 8 + (lane >> 2), lane & 3)) = g[i];
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) row[j] = *reinterpret_cast<const uint4*>(xp + xp_off(lane, j));
+}
+// this lane's own row (64 bytes) -> smem block -> coalesced global stores
+__device__ __forceinline__ void xp_store_rows(uint8_t* xp, int lane, const uint4 (&row)[4], uint8_t* base, int64_t ld_bytes,
+                                              int row0, int M) {
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(xp + xp_off(lane, j)) = row[j];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2);
+    const uint4 val = *reinterpret_cast<const uint4*>(xp + xp_off(r, lane & 3));
+    if (row0 + r < M) *reinterpret_cast<uint4*>(base + (int64_t)(row0 + r) * ld_bytes + (lane & 3) * 16) = val;
+  }
+}
+
+template <bool R32>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_add_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                   const float* __restrict__ bias, const void* __restrict__ residual, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float eps, h16* __restrict__ out16, float* __restrict__ out32, int M,
+                   int N, int K, const EarlyExit ee) {
+  if (all_done(ee)) return;   // uniform over the grid (written by an earlier kernel): whole clusters leave together
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - raw_addr);
+  const uint32_t xp_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t stats_base = xp_base + 8 * XP_BYTES;
+  const uint32_t param_base = stats_base + STATS_BYTES;
+  const uint32_t bar_base = param_base + PARAM_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  auto stats_bar = [&](int g, int p) { return bar_base + 8u * (2 * STAGES + 4 + 2 * g + p); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 8);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  float* param_gen = reinterpret_cast<float*>(smem_gen + (param_base - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
+  const int cluster_id = blockIdx.x / csize, n_clusters = gridDim.x / csize;
+  const int n_blk = (int)crank;
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), EPI_WARPS);
+      mbar_init(stats_bar(a, 0), 1);
+      mbar_init(stats_bar(a, 1), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < BN; i += THREADS) {
+    const int col = n_blk * BN + i;
+    param_gen[i] = (bias != nullptr && col < N) ? __ldg(bias + col) : 0.f;
+    param_gen[BN + i] = col < N ? __ldg(gamma + col) : 0.f;
+    param_gen[2 * BN + i] = col < N ? __ldg(beta + col) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  // every CTA of the cluster has initialised its barriers before any peer writes statistics into it
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t it = 0;
+      for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters) {
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          const uint32_t a_dst = smem_base + s * STAGE_BYTES;
+          tma_load_2d(a_dst, &tma_a, full_bar(s), kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(a_dst + A_BYTES, &tma_b, full_bar(s), kb * BLOCK_K, n_blk * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = instr_desc_bf16(BLOCK_M, BN);
+      uint32_t it = 0, tcount = 0;
+      for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters, ++tcount) {
+        const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + s * STAGE_BYTES;
+          const uint64_t adesc = sw128_kmajor_desc(a_addr);
+          const uint64_t bdesc = sw128_kmajor_desc(a_addr + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            tc_mma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit(empty_bar(s));
+        }
+        tc_commit(tfull_bar(acc));
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: one thread per row (TMEM lane); two groups of 4 warps take alternate row blocks =====
+    const int grp = (warp - 4) >> 2;
+    const int ew = (warp - 4) & 3;   // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
+    uint8_t* xp = smem_gen + (xp_base - smem_base) + (warp - 4) * XP_BYTES;
+    const float* bias_s = param_gen;
+    const float* gamma_s = param_gen + BN;
+    const float* beta_s = param_gen + 2 * BN;
+    const int64_t res_ld = (int64_t)N * (R32 ? 4 : 2);
+    const uint8_t* res_b = reinterpret_cast<const uint8_t*>(residual) + (int64_t)n_blk * BN * (R32 ? 4 : 2);
+    uint8_t* out16_b = reinterpret_cast<uint8_t*>(out16) + (int64_t)n_blk * BN * 2;
+    uint8_t* out32_b = reinterpret_cast<uint8_t*>(out32) + (int64_t)n_blk * BN * 4;
+    constexpr int NSUB = R32 ? 2 : 1;   // 64-byte sub-blocks of the residual per 32-column chunk
+    uint32_t i = grp;
+    for (int m_blk = cluster_id + grp * n_clusters; m_blk < m_tiles; m_blk += 2 * n_clusters, i += 2) {
+      const uint32_t gcount = i >> 1, par = gcount & 1u, sph = (gcount >> 1) & 1u;
+      const int row0 = m_blk * BLOCK_M + ew * 32;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + grp * BN;
+      if (ew == 0 && lane == 0) mbar_expect_tx(stats_bar(grp, par), (csize - 1) * STAT_SLOT);
+      uint4 gn[NSUB][4];
+#pragma unroll
+      for (int sb = 0; sb < NSUB; ++sb) ldg_block(res_b + sb * 64, res_ld, row0, M, lane, gn[sb]);
+      mbar_wait(tfull_bar(grp), gcount & 1u);
+      tc_fence_after();
+      // ---- pass 1: v = acc + bias + residual -> TMEM; row statistics ----
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint4 rr[NSUB][4];
+#pragma unroll
+        for (int sb = 0; sb < NSUB; ++sb) xp_to_rows(xp, lane, gn[sb], rr[sb]);
+        if (c + 1 < BN / 32) {
+#pragma unroll
+          for (int sb = 0; sb < NSUB; ++sb)
+            ldg_block(res_b + (c + 1) * 32 * (R32 ? 4 : 2) + sb * 64, res_ld, row0, M, lane, gn[sb]);
+        }
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bq = *reinterpret_cast<const float4*>(bias_s + c * 32 + q * 4);
+          float r0, r1, r2, r3;
+          if constexpr (R32) {
+            const uint4 u = rr[q >> 2][q & 3];
+            r0 = __uint_as_float(u.x); r1 = __uint_as_float(u.y); r2 = __uint_as_float(u.z); r3 = __uint_as_float(u.w);
+          } else {
+            const uint4 u = rr[0][q >> 1];
+            const uint32_t w0 = (q & 1) ? u.z : u.x, w1 = (q & 1) ? u.w : u.y;
+            r0 = h16_lo(w0); r1 = h16_hi(w0); r2 = h16_lo(w1); r3 = h16_hi(w1);
+          }
+          const float x0 = __uint_as_float(v[4 * q]) + bq.x + r0;
+          const float x1 = __uint_as_float(v[4 * q + 1]) + bq.y + r1;
+          const float x2 = __uint_as_float(v[4 * q + 2]) + bq.z + r2;
+          const float x3 = __uint_as_float(v[4 * q + 3]) + bq.w + r3;
+          s1 += (x0 + x1) + (x2 + x3);
+          s2 = fmaf(x0, x0, s2); s2 = fmaf(x1, x1, s2); s2 = fmaf(x2, x2, s2); s2 = fmaf(x3, x3, s2);
+          v[4 * q] = __float_as_uint(x0); v[4 * q + 1] = __float_as_uint(x1);
+          v[4 * q + 2] = __float_as_uint(x2); v[4 * q + 3] = __float_as_uint(x3);
+        }
+        tmem_st32(taddr + c * 32, v);
+      }
+      tmem_st_wait();
+      // ---- exchange the row statistics with the other CTAs of the cluster ----
+      const uint32_t my_row = (uint32_t)(ew * 32 + lane);
+      for (uint32_t dst = 0; dst < csize; ++dst) {
+        if (dst == crank) continue;
+        const uint32_t slot = crank < dst ? crank : crank - 1;
+        const uint32_t local = stats_base + ((grp * 2 + par) * (MAX_CN - 1) + slot) * STAT_SLOT + my_row * 8;
+        st_async_f2(map_to_cta(local, dst), s1, s2, map_to_cta(stats_bar(grp, par), dst));
+      }
+      mbar_wait_cluster(stats_bar(grp, par), sph);
+      for (uint32_t slot = 0; slot + 1 < csize; ++slot) {
+        const float2 o = *reinterpret_cast<const float2*>(
+            smem_gen + (stats_base - smem_base) + ((grp * 2 + par) * (MAX_CN - 1) + slot) * STAT_SLOT + my_row * 8);
+        s1 += o.x;
+        s2 += o.y;
+      }
+      const float inv_n = 1.0f / (float)N;
+      const float mean = s1 * inv_n;
+      const float rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + eps);
+      // ---- pass 2: normalise, scale, store ----
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        float y[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 gq = *reinterpret_cast<const float4*>(gamma_s + c * 32 + q * 4);
+          const float4 eq = *reinterpret_cast<const float4*>(beta_s + c * 32 + q * 4);
+          y[4 * q] = fmaf((__uint_as_float(v[4 * q]) - mean) * rstd, gq.x, eq.x);
+          y[4 * q + 1] = fmaf((__uint_as_float(v[4 * q + 1]) - mean) * rstd, gq.y, eq.y);
+          y[4 * q + 2] = fmaf((__uint_as_float(v[4 * q + 2]) - mean) * rstd, gq.z, eq.z);
+          y[4 * q + 3] = fmaf((__uint_as_float(v[4 * q + 3]) - mean) * rstd, gq.w, eq.w);
+        }
+        uint4 pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          pk[j] = make_uint4(pack_h16(y[8 * j], y[8 * j + 1]), pack_h16(y[8 * j + 2], y[8 * j + 3]),
+                             pack_h16(y[8 * j + 4], y[8 * j + 5]), pack_h16(y[8 * j + 6], y[8 * j + 7]));
+        xp_store_rows(xp, lane, pk, out16_b + c * 64, (int64_t)N * 2, row0, M);
+        if constexpr (R32) {
+#pragma unroll
+          for (int sb = 0; sb < 2; ++sb) {
+            uint4 pf[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              pf[j] = make_uint4(__float_as_uint(y[16 * sb + 4 * j]), __float_as_uint(y[16 * sb + 4 * j + 1]),
+                                 __float_as_uint(y[16 * sb + 4 * j + 2]), __float_as_uint(y[16 * sb + 4 * j + 3]));
+            xp_store_rows(xp, lane, pf, out32_b + c * 128 + sb * 64, (int64_t)N * 4, row0, M);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(grp));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+  // no CTA leaves while a peer may still send statistics into its shared memory
+  __syncwarp();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+static int get_tmap(care_ctx* ctx, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                    CUtensorMap* out) {
+  const uint64_t gdim[2] = {cols, rows};
+  const uint64_t gstride[1] = {ld * 2};
+  const uint32_t box[2] = {(uint32_t)BLOCK_K, box_rows};
+  return get_tmap_bf16(ctx, ptr, 2, gdim, gstride, box, out);
+}
+
+template <bool R32>
+static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const void* residual,
+                  const float* gamma, const float* beta, float eps, void* out16, float* out32, int M, int N, int K,
+                  cudaStream_t stream) {
+  static bool configured_all[64] = {false};
+  static int max_clusters_all[64][MAX_CN + 1] = {{0}};
+  auto kern = gemm_add_ln_kernel<R32>;
+  const int cn = N / BN;
+  if (!configured_all[ctx->device & 63]) {
+    CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured_all[ctx->device & 63] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cn;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(THREADS, 1, 1);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int& max_clusters = max_clusters_all[ctx->device & 63][cn];
+  if (max_clusters == 0) {
+    cfg.gridDim = dim3((unsigned)(cn * (ctx->sm_count / cn)), 1, 1);
+    int n = 0;
+    CARE_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    CARE_CHECK_ARG(n > 0, "care_gemm_add_ln: no cluster of %d CTAs fits the device", cn);
+    max_clusters = n;
+  }
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  const int clusters = std::min(m_tiles, max_clusters);
+  cfg.gridDim = dim3((unsigned)(clusters * cn), 1, 1);
+  CARE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, bias, residual, gamma, beta, eps, reinterpret_cast<h16*>(out16), out32,
+                               M, N, K, early_exit_of(ctx)));
+  ctx->last_gemm = R32 ? "gemm_add_ln_kernel<f32 residual>" : "gemm_add_ln_kernel<h16 residual>";
+  CARE_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+}  // namespace gln
+}  // namespace care
+
+using namespace care;
+
+extern "C" int care_gemm_add_ln(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                const void* residual, int residual_dtype, const float* gamma, const float* beta,
+                                float eps, void* out16, float* out32, int M, int N, int K, void* stream) {
+  CARE_CHECK_ARG(ctx && A && W && residual && gamma && beta && out16 && M > 0 && K > 0, "care_gemm_add_ln: bad args");
+  CARE_CHECK_ARG(N % gln::BN == 0 && N / gln::BN >= 2 && N / gln::BN <= gln::MAX_CN,
+                 "care_gemm_add_ln: N=%d must be 512, 768 or 1024 (a cluster of N/256 CTAs shares a row block)", N);
+  CARE_CHECK_ARG(residual_dtype == CARE_H16 || residual_dtype == CARE_F32, "care_gemm_add_ln: residual dtype %d",
+                 residual_dtype);
+  CARE_CHECK_ARG(residual_dtype == CARE_H16 || out32 != nullptr,
+                 "care_gemm_add_ln: an fp32 residual stream needs the fp32 output (out32)");
+  CARE_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0, "care_gemm_add_ln: lda/ldw must be multiples of 8");
+  CARE_CHECK_ARG(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(residual) |
+                   reinterpret_cast<uintptr_t>(out16) | reinterpret_cast<uintptr_t>(out32)) & 15) == 0,
+                 "care_gemm_add_ln: pointers must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUtensorMap ta, tb;
+  int rc = gln::get_tmap(ctx, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, tc::BLOCK_M, &ta);
+  if (rc) return rc;
+  rc = gln::get_tmap(ctx, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)gln::BN, &tb);
+  if (rc) return rc;
+  if (residual_dtype == CARE_F32)
+    return gln::launch<true>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, out32, M, N, K, s);
+  return gln::launch<false>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, nullptr, M, N, K, s);
+}

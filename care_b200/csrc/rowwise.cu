@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(256)
 embed_ln_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ positions, int position,
                 const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ add,
                 const float* __restrict__ gsg, int rpv, const float* __restrict__ gamma,
-                const float* __restrict__ beta, float eps, int R, int d, T* __restrict__ out, const EarlyExit ee) {
+                const float* __restrict__ beta, float eps, int R, int d, T* __restrict__ out,
+                float* __restrict__ out32, const EarlyExit ee) {
   if (all_done(ee)) return;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -194,7 +195,10 @@ embed_ln_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ 
   warp_layernorm(r, nch, d, lane, gamma, beta, eps);
 #pragma unroll
   for (int c = 0; c < MAX_CHUNKS; ++c)
-    if (c < nch) Act<T>::store4(out + (int64_t)row * d + c * 128 + lane * 4, r[c]);
+    if (c < nch) {
+      Act<T>::store4(out + (int64_t)row * d + c * 128 + lane * 4, r[c]);
+      if (out32 != nullptr) Act<float>::store4(out32 + (int64_t)row * d + c * 128 + lane * 4, r[c]);
+    }
 }
 
 // out = LN(x + residual)   (SubLayers.py:74-79, 148-150)
@@ -302,7 +306,7 @@ int care_encoder_highway_bn_mean(care_ctx* ctx, int dtype, const float* h, const
 int care_embed_ln(care_ctx* ctx, int dtype, const int32_t* tokens, const int32_t* positions, int position,
                   const float* word_emb, const float* pos_emb, const float* add_feats, const float* gsg,
                   int rows_per_video, const float* gamma, const float* beta, float eps, int R, int d, void* out,
-                  void* stream) {
+                  float* out32, void* stream) {
   CARE_CHECK_DTYPE(dtype, "care_embed_ln");
   CARE_CHECK_ARG(ctx && tokens && word_emb && pos_emb && gamma && beta && out && R > 0 && rows_per_video > 0,
                  "care_embed_ln: bad args");
@@ -312,11 +316,11 @@ int care_embed_ln(care_ctx* ctx, int dtype, const int32_t* tokens, const int32_t
   if (dtype == CARE_F32)
     rw::embed_ln_kernel<float><<<grid, 256, 0, s>>>(tokens, positions, position, word_emb, pos_emb, add_feats, gsg,
                                                     rows_per_video, gamma, beta, eps, R, d, (float*)out,
-                                                    early_exit_of(ctx));
+                                                    out32, early_exit_of(ctx));
   else
     rw::embed_ln_kernel<h16><<<grid, 256, 0, s>>>(tokens, positions, position, word_emb, pos_emb, add_feats,
                                                             gsg, rows_per_video, gamma, beta, eps, R, d,
-                                                            (h16*)out, early_exit_of(ctx));
+                                                            (h16*)out, out32, early_exit_of(ctx));
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

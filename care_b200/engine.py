@@ -15,6 +15,7 @@ concepts; length predictor) runs as three-term split products on the tensor core
 fp32-grade results, so the concept ids equal the fp32 mode's except on exact ties.
 """
 import ctypes
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -68,6 +69,13 @@ class CareEngine:
         self.ldv = _round_up(self.V, 8)
         # 16-bit modes: the vocabulary GEMM's epilogue feeds the beam kernel directly (no logits in HBM)
         self.fused_vocab = self.half and bool(opt.get("care_fused_vocab", True))
+        # 16-bit modes: out-proj / FFN2 + residual + LayerNorm as one cluster kernel (care_gemm_add_ln):
+        # 0 = care_gemm + care_add_ln, 1 = fused with a 16-bit residual stream, 2 = fused with an fp32 residual stream
+        default_ln = int(os.environ.get("CARE_B200_FUSED_LN", "1"))
+        fl = opt.get("care_fused_ln")
+        self.fused_ln = int(default_ln if fl is None else fl) if (self.half and self.d in (512, 768, 1024)) else 0
+        if self.fused_ln not in (0, 1, 2):
+            raise ValueError("care_fused_ln must be 0, 1 or 2")
         self._ws = {}
         self._ws_epoch_of = {}
         self._ws_bytes = 0
@@ -282,6 +290,22 @@ class CareEngine:
                                  W.stride(0), ptr(bias), ptr(C), ldc if ldc is not None else C.stride(-2), out_dt,
                                  M, N, K, act, self._stream()), "care_gemm")
 
+    def _sublayer_tail(self, A, W, bias, gamma, beta, res, out, M, K, y32, res32=None, out32=None):
+        """out = LayerNorm(A W^T + bias + res) (SubLayers.py:68-79,137-152): one cluster kernel in the 16-bit
+        modes, care_gemm -> fp32 y32 -> care_add_ln otherwise.  res32 / out32: the fp32 residual stream
+        (care_fused_ln = 2)."""
+        d = self.d
+        if self.fused_ln:
+            r32 = self.fused_ln == 2
+            check(self.lib.care_gemm_add_ln(self.ctx, ptr(A), A.stride(-2), ptr(W), W.stride(0), ptr(bias),
+                                            ptr(res32 if r32 else res), F32 if r32 else self.dt, ptr(gamma), ptr(beta),
+                                            self.eps, ptr(out), ptr(out32) if r32 else None, M, d, K, self._stream()),
+                  "care_gemm_add_ln")
+            return
+        self.gemm(A, W, bias, y32, M, d, K)
+        check(self.lib.care_add_ln(self.ctx, self.dt, ptr(y32), ptr(res), ptr(gamma), ptr(beta), self.eps, M, d, ptr(out),
+                                   self._stream()), "care_add_ln")
+
     def _operand(self, name, x32, rows, cols):
         """fp32 [rows, cols] -> the A operand of an upstream-of-ranking GEMM and its K: fp32 mode: x itself;
         16-bit modes: [hi | lo | hi] (or a plain cast when care_encoder_terms == 1)."""
@@ -426,19 +450,17 @@ class CareEngine:
                   2 * self.d, self.d)
         return akv
 
-    def _attr_block_step(self, x_in, x_out, akv, B, K, done):
+    def _attr_block_step(self, x_in, x_out, akv, B, K, done, x_in32=None, x_out32=None):
         """attr_attention for the newest position of every beam row: LN(dense(attn(q(x), concepts)) + x)."""
         lib, ctx, dt, w, d, T = self.lib, self.ctx, self.dt, self.w, self.d, self.tdtype
         st = self._stream()
         R = B * K
         qa = self._buf("qa", (R, d), T); cxa = self._buf("ctx_a", (R, d), T)
-        y32 = self._buf("y32", (R, d), torch.float32)
+        y32 = None if self.fused_ln else self._buf("y32", (R, d), torch.float32)
         self.gemm(x_in, w["Waq"], w["baq"], qa, R, d, d)
         check(lib.care_cross_attn_step(ctx, dt, ptr(qa), d, ptr(akv), akv.shape[1], B, K, self.H, d, None, done,
                                        ptr(cxa), st), "care_cross_attn_step(attr)")
-        self.gemm(cxa, w["Wao"], w["bao"], y32, R, d, d)
-        check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x_in), ptr(w["lna_g"]), ptr(w["lna_b"]), self.eps, R, d,
-                              ptr(x_out), st), "care_add_ln")
+        self._sublayer_tail(cxa, w["Wao"], w["bao"], w["lna_g"], w["lna_b"], x_in, x_out, R, d, y32, x_in32, x_out32)
 
     # ------------------------------------------------------------------------------------------
     # auto-regressive beam decode  (reference: models/Translator.py:35-220 + misc/Decoding/Beam.py)
@@ -475,37 +497,38 @@ class CareEngine:
         x0 = self._buf("x0", (R, d), T); x1 = self._buf("x1", (R, d), T)
         x2 = self._buf("x2", (R, d), T); x3 = self._buf("x3", (R, d), T)
         cx = self._buf("ctx", (R, d), T); qc = self._buf("qc", (R, d), T)
-        y32 = self._buf("y32", (R, d), torch.float32)
+        y32 = None if self.fused_ln else self._buf("y32", (R, d), torch.float32)
         hb = self._buf("ffn_h", (R, self.F), T)
+        # fp32 residual stream (care_fused_ln = 2): r0..r3 next to the 16-bit GEMM operands x0..x3
+        r0 = r1 = r2 = r3 = ra = None
+        if self.fused_ln == 2:
+            r0 = self._buf("r0", (R, d), torch.float32); r1 = self._buf("r1", (R, d), torch.float32)
+            r2 = self._buf("r2", (R, d), torch.float32); r3 = self._buf("r3", (R, d), torch.float32)
         gsg = enc.get("semantic_hidden_states")
         done = ptr(bufs["done"])
         check(lib.care_embed_ln(ctx, dt, ptr(bufs["cur_tok"]), None, t - 1, ptr(w["word"]), ptr(w["pos"]), None,
-                                ptr(gsg), K, ptr(w["emb_g"]), ptr(w["emb_b"]), self.eps, R, d, ptr(x0), st),
+                                ptr(gsg), K, ptr(w["emb_g"]), ptr(w["emb_b"]), self.eps, R, d, ptr(x0), ptr(r0), st),
               "care_embed_ln")
         self.gemm(x0, w["Wqkv"], w["bqkv"], cache[t - 1], R, 3 * d, d)
         check(lib.care_self_attn_step(ctx, dt, ptr(cache), t, B, K, self.H, d, ptr(bufs["anc"]), Tm,
                                       ptr(bufs["tok_hist"]), done, ptr(cx), st), "care_self_attn_step")
-        self.gemm(cx, w["Wo"], w["bo"], y32, R, d, d)
-        check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x0), ptr(w["ln1_g"]), ptr(w["ln1_b"]), self.eps, R, d, ptr(x1),
-                              st), "care_add_ln")
+        self._sublayer_tail(cx, w["Wo"], w["bo"], w["ln1_g"], w["ln1_b"], x0, x1, R, d, y32, r0, r1)
         if self.attr_pos == "attr2cross":   # Layers.py:180-187
             xa = self._buf("xa", (R, d), T)
-            self._attr_block_step(x1, xa, akv, B, K, done)
-            x1 = xa
+            ra = self._buf("ra", (R, d), torch.float32) if self.fused_ln == 2 else None
+            self._attr_block_step(x1, xa, akv, B, K, done, r1, ra)
+            x1, r1 = xa, ra
         self.gemm(x1, w["Wxq"], w["bxq"], qc, R, d, d)
         check(lib.care_cross_attn_step(ctx, dt, ptr(qc), d, ptr(kv), self.Lm, B, K, self.H, d, ptr(w["hybrid_bias"]),
                                        done, ptr(cx), st), "care_cross_attn_step")
-        self.gemm(cx, w["Wxo"], w["bxo"], y32, R, d, d)
-        check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x1), ptr(w["ln2_g"]), ptr(w["ln2_b"]), self.eps, R, d, ptr(x2),
-                              st), "care_add_ln")
+        self._sublayer_tail(cx, w["Wxo"], w["bxo"], w["ln2_g"], w["ln2_b"], x1, x2, R, d, y32, r1, r2)
         if self.attr_pos == "cross2attr":   # Layers.py:217-225
             xa = self._buf("xa", (R, d), T)
-            self._attr_block_step(x2, xa, akv, B, K, done)
-            x2 = xa
+            ra = self._buf("ra", (R, d), torch.float32) if self.fused_ln == 2 else None
+            self._attr_block_step(x2, xa, akv, B, K, done, r2, ra)
+            x2, r2 = xa, ra
         self.gemm(x2, w["W1"], w["b1"], hb, R, self.F, d, act=ACT_RELU)
-        self.gemm(hb, w["W2"], w["b2"], y32, R, d, self.F)
-        check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x2), ptr(w["ln3_g"]), ptr(w["ln3_b"]), self.eps, R, d, ptr(x3),
-                              st), "care_add_ln")
+        self._sublayer_tail(hb, w["W2"], w["b2"], w["ln3_g"], w["ln3_b"], x2, x3, R, self.F, y32, r2, r3)
         return x3
 
     def decode_step(self, t, B, K, enc, kv, bufs, bst, audit=None, want_logits=False, akv=None):
@@ -640,17 +663,15 @@ class CareEngine:
     # ------------------------------------------------------------------------------------------
     # full-sequence decoder pass (mask-predict passes and the stateless decoding_phase)
     # ------------------------------------------------------------------------------------------
-    def _attr_block_seq(self, x_in, x_out, akv, n_videos, rpv, N):
+    def _attr_block_seq(self, x_in, x_out, akv, n_videos, rpv, N, x_in32=None, x_out32=None):
         lib, ctx, dt, w, d, T = self.lib, self.ctx, self.dt, self.w, self.d, self.tdtype
         st = self._stream()
         qa = self._buf("sq_qa", (N, d), T); cxa = self._buf("sq_ctx_a", (N, d), T)
-        y32 = self._buf("sq_y32", (N, d), torch.float32)
+        y32 = None if self.fused_ln else self._buf("sq_y32", (N, d), torch.float32)
         self.gemm(x_in, w["Waq"], w["baq"], qa, N, d, d)
         check(lib.care_group_attn(ctx, dt, ptr(qa), d, ptr(akv), 2 * d, 0, d, n_videos, rpv, akv.shape[1], self.H, d,
                                   None, 0, None, ptr(cxa), st), "care_group_attn(attr)")
-        self.gemm(cxa, w["Wao"], w["bao"], y32, N, d, d)
-        check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x_in), ptr(w["lna_g"]), ptr(w["lna_b"]), self.eps, N, d,
-                              ptr(x_out), st), "care_add_ln")
+        self._sublayer_tail(cxa, w["Wao"], w["bao"], w["lna_g"], w["lna_b"], x_in, x_out, N, d, y32, x_in32, x_out32)
 
     def _sequence_hidden(self, tokens, positions, R, L, kv, n_videos, causal, add_feats, gsg, akv=None):
         """Decoder layer over R sequences of L tokens (reference: Decoder/Transformer.py:161-237).
@@ -664,35 +685,35 @@ class CareEngine:
         x2 = self._buf("sq_x2", (N, d), T); x3 = self._buf("sq_x3", (N, d), T)
         cx = self._buf("sq_ctx", (N, d), T); qc = self._buf("sq_qc", (N, d), T)
         qkv = self._buf("sq_qkv", (N, 3 * d), T)
-        y32 = self._buf("sq_y32", (N, d), torch.float32)
+        y32 = None if self.fused_ln else self._buf("sq_y32", (N, d), torch.float32)
         hb = self._buf("sq_ffn", (N, self.F), T)
+        r0 = r1 = r2 = r3 = ra = None
+        if self.fused_ln == 2:
+            r0 = self._buf("sq_r0", (N, d), torch.float32); r1 = self._buf("sq_r1", (N, d), torch.float32)
+            r2 = self._buf("sq_r2", (N, d), torch.float32); r3 = self._buf("sq_r3", (N, d), torch.float32)
         check(lib.care_embed_ln(ctx, dt, ptr(tokens), ptr(positions), 0, ptr(w["word"]), ptr(w["pos"]), ptr(add_feats),
-                                ptr(gsg), rpv, ptr(w["emb_g"]), ptr(w["emb_b"]), self.eps, N, d, ptr(x0), st),
+                                ptr(gsg), rpv, ptr(w["emb_g"]), ptr(w["emb_b"]), self.eps, N, d, ptr(x0), ptr(r0), st),
               "care_embed_ln")
         self.gemm(x0, w["Wqkv"], w["bqkv"], qkv, N, 3 * d, d)
         check(lib.care_group_attn(ctx, dt, ptr(qkv), 3 * d, ptr(qkv), 3 * d, d, 2 * d, R, L, L, self.H, d, ptr(tokens),
                                   1 if causal else 0, None, ptr(cx), st), "care_group_attn(self)")
-        self.gemm(cx, w["Wo"], w["bo"], y32, N, d, d)
-        check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x0), ptr(w["ln1_g"]), ptr(w["ln1_b"]), self.eps, N, d, ptr(x1),
-                              st), "care_add_ln")
+        self._sublayer_tail(cx, w["Wo"], w["bo"], w["ln1_g"], w["ln1_b"], x0, x1, N, d, y32, r0, r1)
         if self.attr_pos == "attr2cross":
             xa = self._buf("sq_xa", (N, d), T)
-            self._attr_block_seq(x1, xa, akv, n_videos, rpv, N)
-            x1 = xa
+            ra = self._buf("sq_ra", (N, d), torch.float32) if self.fused_ln == 2 else None
+            self._attr_block_seq(x1, xa, akv, n_videos, rpv, N, r1, ra)
+            x1, r1 = xa, ra
         self.gemm(x1, w["Wxq"], w["bxq"], qc, N, d, d)
         check(lib.care_group_attn(ctx, dt, ptr(qc), d, ptr(kv), 2 * d, 0, d, n_videos, rpv, self.Lm, self.H, d, None, 0,
                                   ptr(w["hybrid_bias"]), ptr(cx), st), "care_group_attn(cross)")
-        self.gemm(cx, w["Wxo"], w["bxo"], y32, N, d, d)
-        check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x1), ptr(w["ln2_g"]), ptr(w["ln2_b"]), self.eps, N, d, ptr(x2),
-                              st), "care_add_ln")
+        self._sublayer_tail(cx, w["Wxo"], w["bxo"], w["ln2_g"], w["ln2_b"], x1, x2, N, d, y32, r1, r2)
         if self.attr_pos == "cross2attr":
             xa = self._buf("sq_xa", (N, d), T)
-            self._attr_block_seq(x2, xa, akv, n_videos, rpv, N)
-            x2 = xa
+            ra = self._buf("sq_ra", (N, d), torch.float32) if self.fused_ln == 2 else None
+            self._attr_block_seq(x2, xa, akv, n_videos, rpv, N, r2, ra)
+            x2, r2 = xa, ra
         self.gemm(x2, w["W1"], w["b1"], hb, N, self.F, d, act=ACT_RELU)
-        self.gemm(hb, w["W2"], w["b2"], y32, N, d, self.F)
-        check(lib.care_add_ln(ctx, dt, ptr(y32), ptr(x2), ptr(w["ln3_g"]), ptr(w["ln3_b"]), self.eps, N, d, ptr(x3),
-                              st), "care_add_ln")
+        self._sublayer_tail(hb, w["W2"], w["b2"], w["ln3_g"], w["ln3_b"], x2, x3, N, self.F, y32, r2, r3)
         return x3
 
     def _memory_mean(self, memory):

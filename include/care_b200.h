@@ -144,16 +144,30 @@ int care_concept_head(care_ctx* ctx, int dtype, const float* scores, int64_t ld_
 /* Decoder input embedding for ONE position per row (Embeddings.py:134-188):
  * out[r] = LN(((word[tok[r]] + pos[position]) + add_feats[r / rows_per_video]) + gsg[r / rows_per_video]).
  * tokens int32 [R]; add_feats / gsg fp32 [n_videos, d] or NULL; out T [R, d].
- * With positions != NULL (int32 [R]) each row uses its own position (mask-predict passes). */
+ * With positions != NULL (int32 [R]) each row uses its own position (mask-predict passes).
+ * out32 (fp32 [R, d] or NULL): an fp32 copy of the result, the head of an fp32 residual stream
+ * (care_gemm_add_ln with residual_dtype = 0). */
 int care_embed_ln(care_ctx* ctx, int dtype, const int32_t* tokens, const int32_t* positions,
                   int position, const float* word_emb, const float* pos_emb, const float* add_feats,
                   const float* gsg, int rows_per_video, const float* gamma, const float* beta,
-                  float eps, int R, int d, void* out, void* stream);
+                  float eps, int R, int d, void* out, float* out32, void* stream);
 
 /* Post-LN residual block tail (SubLayers.py:74-79, :148-150): out = LN(x + residual).
  * x fp32 [R, d] (Linear output incl. bias), residual T [R, d], out T [R, d]. */
 int care_add_ln(care_ctx* ctx, int dtype, const float* x, const void* residual, const float* gamma,
                 const float* beta, float eps, int R, int d, void* out, void* stream);
+
+/* Output projection / second FFN Linear fused with the residual LayerNorm that follows it
+ * (SubLayers.py:68-79: dense -> dropout(identity) -> + residual -> LayerNorm; SubLayers.py:137-152 likewise for
+ * the FFN), T16 operands only:  out = LayerNorm(A[M,K] W[N,K]^T + bias + residual) * gamma + beta.
+ * N must be 512, 768 or 1024: a thread-block cluster of N/256 CTAs shares one 128-row block and exchanges the
+ * per-row (sum, sum of squares) through distributed shared memory, so the fp32 pre-LayerNorm tensor that
+ * care_gemm + care_add_ln pass through HBM never exists.  residual: T16 [M, N] (residual_dtype = the T16 code)
+ * or fp32 [M, N] (residual_dtype = 0: the residual stream stays fp32; out32 [M, N] then receives the fp32
+ * result next to the T16 copy in out16 that the next GEMM consumes).  out16: T16 [M, N], row stride N. */
+int care_gemm_add_ln(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                     const void* residual, int residual_dtype, const float* gamma, const float* beta, float eps,
+                     void* out16, float* out32, int M, int N, int K, void* stream);
 
 /* Fused decode-step self-attention over the KV cache (Attention.py:81-129 for the newest query
  * position only; masks Transformer.py:15-47,169-174).  qkv_step: T [R, 3d] of THIS step (q|k|v);

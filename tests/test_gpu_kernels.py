@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 H16_NAME = os.environ.get("CARE_TEST_H16", "fp16")
 F32 = 0
 H16 = 2 if H16_NAME == "fp16" else 1
-TH = torch.float16 if H16_NAME == "fp16" else TH
+TH = torch.float16 if H16_NAME == "fp16" else torch.bfloat16
 
 
 @pytest.fixture(scope="module")
@@ -316,18 +316,21 @@ def test_embed_ln_and_add_ln(env, dt, T):
     add, gsg = torch.randn(nv, d, device="cuda"), torch.randn(nv, d, device="cuda")
     g, b = torch.randn(d, device="cuda"), torch.randn(d, device="cuda")
     out = torch.empty(R, d, device="cuda", dtype=T)
+    out32 = torch.empty(R, d, device="cuda")
     L.check(lib.care_embed_ln(h, dt, tok.data_ptr(), None, 7, word.data_ptr(), pos.data_ptr(), add.data_ptr(),
-                              gsg.data_ptr(), K, g.data_ptr(), b.data_ptr(), 1e-12, R, d, out.data_ptr(), _stream()),
-            "embed")
+                              gsg.data_ptr(), K, g.data_ptr(), b.data_ptr(), 1e-12, R, d, out.data_ptr(),
+                              out32.data_ptr(), _stream()), "embed")
     vid = torch.arange(R, device="cuda") // K
     ref = torch.nn.functional.layer_norm(((word[tok.long()] + pos[7]) + add[vid]) + gsg[vid], (d,), g, b, 1e-12)
+    torch.cuda.synchronize()
+    assert (out32 - ref).abs().max().item() < 1e-5 * ref.abs().max().item()   # the fp32 copy (fp32 residual stream)
     torch.cuda.synchronize()
     tol = 1e-5 if dt == F32 else 2e-2
     assert (out.float() - ref).abs().max().item() < tol * ref.abs().max().item()
     # per-row positions, no extras
     posi = torch.randint(0, 30, (R,), device="cuda", dtype=torch.int32)
     L.check(lib.care_embed_ln(h, dt, tok.data_ptr(), posi.data_ptr(), 0, word.data_ptr(), pos.data_ptr(), None, None,
-                              K, g.data_ptr(), b.data_ptr(), 1e-12, R, d, out.data_ptr(), _stream()), "embed")
+                              K, g.data_ptr(), b.data_ptr(), 1e-12, R, d, out.data_ptr(), None, _stream()), "embed")
     ref = torch.nn.functional.layer_norm(word[tok.long()] + pos[posi.long()], (d,), g, b, 1e-12)
     torch.cuda.synchronize()
     assert (out.float() - ref).abs().max().item() < tol * ref.abs().max().item()
@@ -338,6 +341,49 @@ def test_embed_ln_and_add_ln(env, dt, T):
     ref = torch.nn.functional.layer_norm(x + res.float(), (d,), g, b, 1e-12)
     torch.cuda.synchronize()
     assert (out.float() - ref).abs().max().item() < tol * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("resid32", [False, True])
+@pytest.mark.parametrize("M,N,K", [(2560, 1024, 1024), (20480, 1024, 4096), (333, 1024, 1024), (5, 512, 512),
+                                   (1000, 768, 3072), (4097, 512, 2048), (128, 1024, 64), (20480, 1024, 1024)])
+def test_gemm_add_ln_fused(env, M, N, K, resid32):
+    """care_gemm_add_ln (cluster of N/256 CTAs per row block, statistics through distributed shared memory)
+    against fp32 torch: layer_norm(A W^T + bias + residual) on the same 16-bit operands; and against the
+    unfused care_gemm + care_add_ln pair."""
+    lib, h, L = env
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).to(TH)
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(TH)
+    bias = torch.randn(N, device="cuda", generator=g)
+    res32 = torch.randn(M, N, device="cuda", generator=g) + 0.3
+    res = res32 if resid32 else res32.to(TH)
+    gamma = 1.0 + 0.2 * torch.randn(N, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(N, device="cuda", generator=g)
+    eps = 1e-12
+    out16 = torch.full((M, N), float("nan"), dtype=TH, device="cuda")
+    out32 = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda") if resid32 else None
+    for _ in range(2):   # second call: barrier phases / TMEM state of a fresh launch are independent of the first
+        L.check(lib.care_gemm_add_ln(h, A.data_ptr(), K, W.data_ptr(), K, bias.data_ptr(), res.data_ptr(),
+                                     F32 if resid32 else H16, gamma.data_ptr(), beta.data_ptr(), eps, out16.data_ptr(),
+                                     None if out32 is None else out32.data_ptr(), M, N, K, _stream()), "gemm_add_ln")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(A.float() @ W.float().t() + bias + res.float(), (N,), gamma, beta, eps)
+    tol = 2e-3 if TH == torch.float16 else 1.6e-2      # one 16-bit rounding of an O(1..4) value
+    assert torch.isfinite(out16.float()).all()
+    assert (out16.float() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+    if resid32:
+        assert (out32 - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+        assert torch.equal(out32.to(TH), out16)
+    else:
+        # the unfused pair computes the same thing from an fp32 GEMM output
+        y32 = _gemm(env, H16, A, W, bias, torch.float32)
+        out_ref = torch.empty((M, N), dtype=TH, device="cuda")
+        L.check(lib.care_add_ln(h, H16, y32.data_ptr(), res.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, M, N,
+                                out_ref.data_ptr(), _stream()), "add_ln")
+        torch.cuda.synchronize()
+        diff = (out16.float() - out_ref.float()).abs()
+        assert diff.max().item() <= tol * max(1.0, ref.abs().max().item())   # at most one 16-bit ulp apart
+        assert (diff > 0).float().mean().item() < 0.02
 
 
 @pytest.mark.parametrize("dt,T", [(F32, torch.float32), (H16, TH)])
