@@ -107,6 +107,30 @@ __global__ void __launch_bounds__(256) best_logits_kernel(const float* __restric
   }
 }
 
+// one warp per token row of the TEACHER's fp32 logits: softmax probability of a given token (scoring_by_teacher,
+// na_algorithms.py:92-126), times the student's own probability when `probs_in` is given; pad positions count 1
+__global__ void __launch_bounds__(256) teacher_probs_kernel(const float* __restrict__ logits, int64_t ldv,
+                                                            const int32_t* __restrict__ targets,
+                                                            const int32_t* __restrict__ lengths, int R, int L, int V,
+                                                            const float* __restrict__ probs_in, float* __restrict__ out) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= (int64_t)R * L) return;
+  const int r = (int)(row / L), p = (int)(row - (int64_t)r * L);
+  float pr = 1.0f;
+  if (p < lengths[r]) {
+    const float* x = logits + row * ldv;
+    float m = -INFINITY;
+    for (int c = lane; c < V; c += 32) m = fmaxf(m, x[c]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int c = lane; c < V; c += 32) s += expf(x[c] - m);
+    s = warp_sum(s);
+    pr = expf(x[targets[row]] - m) / s;
+  }
+  if (lane == 0) out[row] = probs_in != nullptr ? probs_in[row] * pr : pr;
+}
+
 // same from the fused vocabulary kernel's records (KB = 2); segment existence as in beam.cu
 __global__ void best_partials_kernel(const float* __restrict__ partials, int nseg, int n_tiles, int64_t T, int64_t G,
                                      int row_shift, int rows, int32_t* __restrict__ idx, float* __restrict__ prob) {
@@ -291,6 +315,16 @@ int care_nar_best_logits(care_ctx* ctx, const float* logits, int64_t ldv, int ro
                          void* stream) {
   CARE_CHECK_ARG(ctx && logits && idx && prob && rows > 0 && V > 0, "care_nar_best_logits: bad args");
   nar::best_logits_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(logits, ldv, rows, V, idx, prob);
+  CARE_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int care_nar_teacher_probs(care_ctx* ctx, const float* logits, int64_t ldv, const int32_t* targets,
+                           const int32_t* lengths, int R, int L, int V, const float* probs_in, float* out, void* stream) {
+  CARE_CHECK_ARG(ctx && logits && targets && lengths && out && R > 0 && L > 0 && V > 0, "care_nar_teacher_probs: bad args");
+  const int64_t rows = (int64_t)R * L;
+  nar::teacher_probs_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(logits, ldv, targets, lengths, R,
+                                                                                         L, V, probs_in, out);
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

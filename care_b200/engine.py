@@ -198,8 +198,9 @@ class CareEngine:
         w["Wxq"] = mat(sd[xa + "SDPA.query.weight"]); w["bxq"] = f32(xa + "SDPA.query.bias")
         w["Wxkv"] = mat(torch.cat([sd[xa + "SDPA.key.weight"], sd[xa + "SDPA.value.weight"]], 0))
         w["bxkv"] = torch.cat([f32(xa + "SDPA.key.bias"), f32(xa + "SDPA.value.bias")])
-        w["Wxo"] = mat(sd[xa + "dense.weight"]); w["bxo"] = f32(xa + "dense.bias")
-        w["ln2_g"] = f32(xa + "LayerNorm.weight"); w["ln2_b"] = f32(xa + "LayerNorm.bias")
+        if (xa + "LayerNorm.weight") in sd:   # absent with attr_layer_pos 'parallel' (Layers.py:107-108)
+            w["Wxo"] = mat(sd[xa + "dense.weight"]); w["bxo"] = f32(xa + "dense.bias")
+            w["ln2_g"] = f32(xa + "LayerNorm.weight"); w["ln2_b"] = f32(xa + "LayerNorm.bias")
         hb = xa + "SDPA.hybrid_bias"
         w["hybrid_bias"] = f32(hb) if hb in sd else None
         # attr_attention (CABase): a second cross-attention over the concept embeddings (Layers.py:117-119)
@@ -207,13 +208,20 @@ class CareEngine:
         self.attr_pos = None
         if (aa + "SDPA.query.weight") in sd:
             self.attr_pos = opt.get("attr_layer_pos", "cross2attr")
-            if self.attr_pos not in ("cross2attr", "attr2cross"):
+            if self.attr_pos not in ("cross2attr", "attr2cross", "parallel"):
                 raise ValueError("attr_layer_pos %r is outside the accelerated hot path" % self.attr_pos)
             w["Waq"] = mat(sd[aa + "SDPA.query.weight"]); w["baq"] = f32(aa + "SDPA.query.bias")
             w["Wakv"] = mat(torch.cat([sd[aa + "SDPA.key.weight"], sd[aa + "SDPA.value.weight"]], 0))
             w["bakv"] = torch.cat([f32(aa + "SDPA.key.bias"), f32(aa + "SDPA.value.bias")])
-            w["Wao"] = mat(sd[aa + "dense.weight"]); w["bao"] = f32(aa + "dense.bias")
-            w["lna_g"] = f32(aa + "LayerNorm.weight"); w["lna_b"] = f32(aa + "LayerNorm.bias")
+            if self.attr_pos == "parallel":
+                # Layers.py:188-201: LN(x + dense_x(ctx_video) + dense_a(ctx_concepts)) - the two output projections
+                # as ONE GEMM over the concatenated contexts, K = 2d, with the layer's own LayerNorm as its tail
+                w["Wpo"] = mat(torch.cat([sd[xa + "dense.weight"], sd[aa + "dense.weight"]], 1))
+                w["bpo"] = f32(xa + "dense.bias") + f32(aa + "dense.bias")
+                w["lnp_g"] = f32(L + "LayerNorm.weight"); w["lnp_b"] = f32(L + "LayerNorm.bias")
+            else:
+                w["Wao"] = mat(sd[aa + "dense.weight"]); w["bao"] = f32(aa + "dense.bias")
+                w["lna_g"] = f32(aa + "LayerNorm.weight"); w["lna_b"] = f32(aa + "LayerNorm.bias")
         w["W1"] = mat(sd[L + "ffn.dense1.weight"]); w["b1"] = f32(L + "ffn.dense1.bias")
         w["W2"] = mat(sd[L + "ffn.dense2.weight"]); w["b2"] = f32(L + "ffn.dense2.bias")
         w["ln3_g"] = f32(L + "ffn.LayerNorm.weight"); w["ln3_b"] = f32(L + "ffn.LayerNorm.bias")
@@ -521,7 +529,16 @@ class CareEngine:
         self.gemm(x1, w["Wxq"], w["bxq"], qc, R, d, d)
         check(lib.care_cross_attn_step(ctx, dt, ptr(qc), d, ptr(kv), self.Lm, B, K, self.H, d, ptr(w["hybrid_bias"]),
                                        done, ptr(cx), st), "care_cross_attn_step")
-        self._sublayer_tail(cx, w["Wxo"], w["bxo"], w["ln2_g"], w["ln2_b"], x1, x2, R, d, y32, r1, r2)
+        if self.attr_pos == "parallel":   # Layers.py:188-201
+            qa = self._buf("qa", (R, d), T); cxa = self._buf("ctx_a", (R, d), T)
+            cat = self._buf("ctx_cat", (R, 2 * d), T)
+            self.gemm(x1, w["Waq"], w["baq"], qa, R, d, d)
+            check(lib.care_cross_attn_step(ctx, dt, ptr(qa), d, ptr(akv), akv.shape[1], B, K, self.H, d, None, done,
+                                           ptr(cxa), st), "care_cross_attn_step(attr)")
+            torch.cat([cx, cxa], dim=1, out=cat)
+            self._sublayer_tail(cat, w["Wpo"], w["bpo"], w["lnp_g"], w["lnp_b"], x1, x2, R, 2 * d, y32, r1, r2)
+        else:
+            self._sublayer_tail(cx, w["Wxo"], w["bxo"], w["ln2_g"], w["ln2_b"], x1, x2, R, d, y32, r1, r2)
         if self.attr_pos == "cross2attr":   # Layers.py:217-225
             xa = self._buf("xa", (R, d), T)
             ra = self._buf("ra", (R, d), torch.float32) if self.fused_ln == 2 else None
@@ -706,7 +723,16 @@ class CareEngine:
         self.gemm(x1, w["Wxq"], w["bxq"], qc, N, d, d)
         check(lib.care_group_attn(ctx, dt, ptr(qc), d, ptr(kv), 2 * d, 0, d, n_videos, rpv, self.Lm, self.H, d, None, 0,
                                   ptr(w["hybrid_bias"]), ptr(cx), st), "care_group_attn(cross)")
-        self._sublayer_tail(cx, w["Wxo"], w["bxo"], w["ln2_g"], w["ln2_b"], x1, x2, N, d, y32, r1, r2)
+        if self.attr_pos == "parallel":   # Layers.py:188-201
+            qa = self._buf("sq_qa", (N, d), T); cxa = self._buf("sq_ctx_a", (N, d), T)
+            cat = self._buf("sq_ctx_cat", (N, 2 * d), T)
+            self.gemm(x1, w["Waq"], w["baq"], qa, N, d, d)
+            check(lib.care_group_attn(ctx, dt, ptr(qa), d, ptr(akv), 2 * d, 0, d, n_videos, rpv, akv.shape[1], self.H, d,
+                                      None, 0, None, ptr(cxa), st), "care_group_attn(attr)")
+            torch.cat([cx, cxa], dim=1, out=cat)
+            self._sublayer_tail(cat, w["Wpo"], w["bpo"], w["lnp_g"], w["lnp_b"], x1, x2, N, 2 * d, y32, r1, r2)
+        else:
+            self._sublayer_tail(cx, w["Wxo"], w["bxo"], w["ln2_g"], w["ln2_b"], x1, x2, N, d, y32, r1, r2)
         if self.attr_pos == "cross2attr":
             xa = self._buf("sq_xa", (N, d), T)
             ra = self._buf("sq_ra", (N, d), torch.float32) if self.fused_ln == 2 else None
@@ -764,7 +790,35 @@ class CareEngine:
     # ------------------------------------------------------------------------------------------
     # mask-predict  (reference: models/Translator.py:240-318 + misc/Decoding/na_algorithms.py:146-197)
     # ------------------------------------------------------------------------------------------
-    def mask_predict(self, enc, opt, length_beam_size, length_bias=0, beam_alpha=1.0, trace=None):
+    def _teacher_product(self, teacher, tokens, lengths, probs, R, L, n_len, out):
+        """out[r,p] = probs[r,p] * p_teacher(y_p | y_<p) (scoring_by_teacher, na_algorithms.py:92-126): one
+        teacher-forced pass of the auto-regressive teacher over [<bos>, y_0 .. y_{L-2}], in chunks of videos so that
+        the fp32 logits of a chunk stay below ~2 GB."""
+        t_eng, t_enc, mapping = teacher["engine"], teacher["enc"], teacher.get("mapping")
+        tok = tokens.view(R, L).long()
+        if mapping is not None:
+            tok = mapping[tok]
+        targets = tok.to(torch.int32).contiguous()
+        ids = torch.cat([torch.full((R, 1), BOS, dtype=torch.int64, device=self.device), tok[:, :-1]], dim=1)
+        B = R // n_len
+        per_video = n_len * L * t_eng.ldv * 4
+        step = max(1, min(B, (2 << 30) // per_video))
+        for a in range(0, B, step):
+            b = min(B, a + step)
+            inputs = {k: v[a:b] for k, v in t_enc.items() if k in ("encoder_hidden_states", "semantic_hidden_states",
+                                                                   "semantic_embs")}
+            logits = t_eng.sequence_logits(ids[a * n_len:b * n_len], inputs, decoding_type="ARFormer")
+            rows = slice(a * n_len, b * n_len)
+            check(self.lib.care_nar_teacher_probs(self.ctx, ptr(logits), logits.stride(1), ptr(targets[rows]),
+                                                  ptr(lengths.view(-1)[rows]), (b - a) * n_len, L, t_eng.V,
+                                                  ptr(probs[rows]), ptr(out[rows]), self._stream()),
+                  "care_nar_teacher_probs")
+        return out
+
+    def mask_predict(self, enc, opt, length_beam_size, length_bias=0, beam_alpha=1.0, trace=None, teacher=None):
+        """`teacher` (optional): dict(engine, enc, mapping, masking, final) - the auto-regressive model whose
+        probabilities multiply the student's when positions are re-masked (`masking`, opt masking_decision) and
+        when the length candidates are ranked (`final`, opt no_candidate_decision = False)."""
         lib, ctx = self.lib, self.ctx
         st = self._stream()
         memory = enc["encoder_hidden_states"]
@@ -822,9 +876,13 @@ class CareEngine:
                                  1 if use_ct else 0, st), "care_nar_apply")
         if trace is not None:
             trace.append(dict(c=0, tokens=tokens.cpu().clone(), probs=probs.cpu().clone()))
+        scored = torch.empty((R, L), dtype=torch.float32, device=self.device) if teacher is not None else None
         for c in range(1, T):
             mode = 0 if (use_ct and c == 1) else 1
-            check(lib.care_nar_remask(ctx, ptr(tokens), ptr(probs), ptr(lengths), ptr(table[c]), mode, R, L,
+            worst = probs
+            if teacher is not None and teacher.get("masking") and mode == 1:
+                worst = self._teacher_product(teacher, tokens, lengths, probs, R, L, n, scored)
+            check(lib.care_nar_remask(ctx, ptr(tokens), ptr(worst), ptr(lengths), ptr(table[c]), mode, R, L,
                                       ptr(mask_ind), st), "care_nar_remask")
             one_pass()
             check(lib.care_nar_apply(ctx, ptr(tokens), ptr(probs), ptr(new_idx), ptr(new_prob), ptr(mask_ind),
@@ -835,6 +893,8 @@ class CareEngine:
         out_tok = torch.empty((B, 1, L), dtype=i32, device=self.device)
         out_lp = torch.empty((B, 1, L), dtype=torch.float32, device=self.device)
         best = torch.empty((B,), dtype=i32, device=self.device)
+        if teacher is not None and teacher.get("final", True):
+            probs = self._teacher_product(teacher, tokens, lengths, probs, R, L, n, scored)
         check(lib.care_nar_select(ctx, ptr(tokens), ptr(probs), ptr(lengths), B, n, L, float(beam_alpha), ptr(out_tok),
                                   ptr(out_lp), ptr(best), st), "care_nar_select")
         if trace is not None:

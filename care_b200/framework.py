@@ -59,10 +59,14 @@ class TransformerSeq2Seq(nn.Module):
             raise ValueError("use_attr_type %r is outside the accelerated hot path (CARE: G1Lc = emb_concat, "
                              "CABase: G0L1 = _att)" % opt.get("use_attr_type"))
         if layout.has_attr_attention(opt):
-            if opt.get("attr_layer_pos", "cross2attr") not in ("cross2attr", "attr2cross"):
+            if opt.get("attr_layer_pos", "cross2attr") not in ("cross2attr", "attr2cross", "parallel"):
                 raise ValueError("attr_layer_pos %r is outside the accelerated hot path" % opt.get("attr_layer_pos"))
             if opt.get("add_hybrid_attention_bias", False):
                 raise ValueError("attr_attention with a hybrid attention bias is not a valid reference configuration")
+        elif opt.get("attr_layer_pos", "cross2attr") == "parallel":
+            # Layers.py:107-108: the video cross-attention would lose its residual and LayerNorm with nothing to
+            # replace them (the parallel merge only exists next to an attr_attention)
+            raise ValueError("attr_layer_pos 'parallel' needs the attr_attention layer (use_attr_type '..att')")
         if not opt.get("trainable_pe", False):
             raise ValueError("sinusoidal position embeddings are outside the accelerated hot path")
         # options the engine would silently compute differently from the reference: refuse them loudly

@@ -87,13 +87,19 @@ def param_specs(opt):
     atts = ["intra_attention", "inter_attention"]
     if has_attr_attention(opt):
         atts.append("attr_attention")   # reference: deepcopy of inter_attention, Layers.py:117-119
+    # attr_layer_pos 'parallel' (Layers.py:107-108,121-122): the two cross-attentions have neither a residual nor
+    # a LayerNorm of their own; the layer owns one LayerNorm over x + inter_context + attr_context
+    parallel = has_attr_attention(opt) and opt.get("attr_layer_pos", "cross2attr") == "parallel"
     for att in atts:
         if att != "intra_attention" and opt.get("add_hybrid_attention_bias", False):
             sp[L + att + ".SDPA.hybrid_bias"] = ((opt["num_attention_heads"], hybrid_length(opt)), "zeros")
         for nm_ in ("query", "key", "value"):
             linear(L + att + ".SDPA." + nm_, d, d)
         linear(L + att + ".dense", d, d)
-        ln(L + att + ".LayerNorm")
+        if att == "intra_attention" or not parallel:
+            ln(L + att + ".LayerNorm")
+    if parallel:
+        ln(L + "LayerNorm")
     linear(L + "ffn.dense1", opt["intermediate_size"], d)
     linear(L + "ffn.dense2", d, opt["intermediate_size"])
     ln(L + "ffn.LayerNorm")

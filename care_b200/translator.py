@@ -224,20 +224,56 @@ class Translator_NARFormer(object):
         self.length_bias = opt.get("length_bias", 0)
 
     def translate_batch(self, models, batch, teacher_model_wrapper=None, vocab=None):
-        if teacher_model_wrapper is not None:
-            raise NotImplementedError("teacher rescoring is outside the accelerated hot path")
         model = _single_model(models)
         if batch["feats"][0].shape[0] == 0:
             return [], []
         with torch.no_grad():
-            tokens, lprobs = self.decode_on_device(model, batch["feats"])
+            teacher = self._teacher(model, teacher_model_wrapper, batch["feats"])
+            tokens, lprobs = self.decode_on_device(model, batch["feats"], teacher=teacher)
         return tokens.cpu().tolist(), lprobs.cpu().tolist()
 
-    def decode_on_device(self, model, feats, trace=None):
+    def _teacher(self, model, teacher_model_wrapper, feats):
+        """The auto-regressive teacher that rescores the candidates (reference: models/Translator.py:250-264;
+        flags misc/Decoding/na_algorithms.py:29-32,98-104)."""
+        if teacher_model_wrapper is None:
+            self.vocab_mapping = None
+            return None
+        if not getattr(self, "_mapping_known", False):
+            self.vocab_mapping = get_vocab_mapping(self.opt, teacher_model_wrapper.get_opt())
+            self._mapping_known = True
+        dev = model.engine().device
+        teacher_model = teacher_model_wrapper.captioner.to(dev).eval()
+        mapping = self.vocab_mapping.to(dev) if self.vocab_mapping is not None else None
+        return dict(engine=teacher_model.engine(), enc=teacher_model.encoding_phase(feats), mapping=mapping,
+                    masking=bool(self.opt.get("masking_decision", False)),
+                    final=not self.opt.get("no_candidate_decision", False))
+
+    def decode_on_device(self, model, feats, trace=None, teacher=None):
         """Returns device tensors: ids [B, 1, L] int32 (PAD after each caption's length) and per-token
         log-probabilities [B, 1, L] fp32, L = the longest length candidate of THIS batch (Translator.py:273)."""
         eng = model.engine()
         if eng.max_len != self.max_len:
             raise ValueError("translator max_len %d != model max_len %d" % (self.max_len, eng.max_len))
         enc = model.encoding_phase(feats)
-        return eng.mask_predict(enc, self.opt, self.length_beam_size, self.length_bias, self.beam_alpha, trace=trace)
+        return eng.mask_predict(enc, self.opt, self.length_beam_size, self.length_bias, self.beam_alpha, trace=trace,
+                                teacher=teacher)
+
+
+def get_vocab_mapping(opt, teacher_opt):
+    """student token id -> teacher token id when the two models were trained on different corpora (knowledge
+    distillation changes the vocabulary), None when the vocabularies coincide (reference: models/Translator.py:321-344)."""
+    import pickle
+    if teacher_opt is None:
+        return None
+    with open(opt["info_corpus"], "rb") as f:
+        vocab = pickle.load(f)["info"]["itow"]
+    with open(teacher_opt["info_corpus"], "rb") as f:
+        teacher_vocab = pickle.load(f)["info"]["itow"]
+    if vocab == teacher_vocab:
+        return None
+    teacher_w2ix = {w: i for i, w in teacher_vocab.items()}
+    mapping = torch.zeros(len(vocab), dtype=torch.long)
+    for i, w in vocab.items():
+        mapping[int(i)] = int(teacher_w2ix[w])
+    assert int(mapping[0]) == 0   # <pad> stays <pad>
+    return mapping

@@ -223,6 +223,13 @@ int care_nar_best_logits(care_ctx* ctx, const float* logits, int64_t ldv, int ro
                          float* prob, void* stream);
 int care_nar_best_partials(care_ctx* ctx, const float* partials, int nseg, int rows, int V, int32_t* idx,
                            float* prob, void* stream);
+/* teacher rescoring (scoring_by_teacher, na_algorithms.py:92-126): logits fp32 [R*L, ldv] of the auto-regressive
+ * teacher's teacher-forced pass over [<bos>, y_0 .. y_{L-2}]; targets int32 [R*L] = the student's tokens in the
+ * teacher's vocabulary.  out[r,p] = softmax(logits[r,p])[targets[r,p]] for p < lengths[r], 1 for pad positions,
+ * multiplied by probs_in[r,p] when probs_in != NULL (token_probs * corresponding_probs, :180,194). */
+int care_nar_teacher_probs(care_ctx* ctx, const float* logits, int64_t ldv, const int32_t* targets,
+                           const int32_t* lengths, int R, int L, int V, const float* probs_in, float* out,
+                           void* stream);
 /* write-back (na_algorithms.py:67-82,185-190): where mask_ind (NULL = everywhere) tokens/probs := new, pad
  * positions forced to (<pad>, 1); zero_mask_token: probs := 0 where the new token is <mask> (:64) */
 int care_nar_apply(care_ctx* ctx, int32_t* tokens, float* probs, const int32_t* new_idx, const float* new_prob,

@@ -146,7 +146,7 @@ def decoder_input_keys(opt):
 # --------------------------------------------------------------------------------------
 # decoder  (TransformerDecoder.forward -> DecoderLayer -> MHA -> SDPA -> FFN -> NaiveHead)
 # --------------------------------------------------------------------------------------
-def _attention(sd, p, opt, q_in, kv_in, mask):
+def _attention(sd, p, opt, q_in, kv_in, mask, context_only=False):
     """MultiHeadAttention.forward (models/components/SubLayers.py:40-81, post-LN) around
     ScaledDotProductAttention.forward (models/components/Attention.py:69-131)."""
     H = opt["num_attention_heads"]
@@ -162,7 +162,10 @@ def _attention(sd, p, opt, q_in, kv_in, mask):
     pr = torch.softmax(s, dim=-1)
     ctx = torch.matmul(pr, v).permute(0, 2, 1, 3).contiguous()
     ctx = ctx.view(ctx.shape[0], ctx.shape[1], -1)
-    out = _lin(sd, p + ".dense", ctx) + q_in
+    context = _lin(sd, p + ".dense", ctx)
+    if context_only:   # has_ln = skip_connection = False (Layers.py:107-108): the caller adds and normalises
+        return context
+    out = context + q_in
     return _ln(sd, p + ".LayerNorm", out, opt["layer_norm_eps"])
 
 
@@ -197,11 +200,14 @@ def decoder_hidden(sd, opt, input_ids, inputs, decoding_type=None):
     # (models/components/Layers.py:117-119,140-155,180-225); position per `attr_layer_pos`
     has_attr = opt.get("use_attr", False) and "att" in opt.get("use_attr_type", "att")
     pos = opt.get("attr_layer_pos", "cross2attr")
-    if has_attr and pos == "parallel":
-        raise ValueError("attr_layer_pos='parallel' is outside the restated path")
     if has_attr and pos == "attr2cross":
         x = _attention(sd, lp + ".attr_attention", opt, x, inputs["semantic_embs"], None)
-    x = _attention(sd, lp + ".inter_attention", opt, x, mem, cross_mask)
+    if has_attr and pos == "parallel":   # Layers.py:188-201
+        inter = _attention(sd, lp + ".inter_attention", opt, x, mem, cross_mask, context_only=True)
+        attr = _attention(sd, lp + ".attr_attention", opt, x, inputs["semantic_embs"], None, context_only=True)
+        x = _ln(sd, lp + ".LayerNorm", x + inter + attr, opt["layer_norm_eps"])
+    else:
+        x = _attention(sd, lp + ".inter_attention", opt, x, mem, cross_mask)
     if has_attr and pos == "cross2attr":
         x = _attention(sd, lp + ".attr_attention", opt, x, inputs["semantic_embs"], None)
     h = _lin(sd, lp + ".ffn.dense2", torch.relu(_lin(sd, lp + ".ffn.dense1", x)))
@@ -404,16 +410,41 @@ def _nar_pass(sd, opt, inputs, tokens, pad_mask):
     return idx, max_probs
 
 
-def nar_translate(sd, opt, feats, return_trace=False):
+def _teacher_probs(teacher, t_inputs, opt, tokens, pad_mask, is_last):
+    """Algorithm_Base.scoring_by_teacher (misc/Decoding/na_algorithms.py:92-126): p_teacher(y_t | y_<t) of the
+    student's current tokens from one teacher-forced pass of the auto-regressive teacher; ones when there is no
+    teacher or the decision flags (masking_decision / no_candidate_decision, :29-32) switch the rescoring off."""
+    ones = torch.ones(tokens.shape, dtype=torch.float32)
+    if teacher is None:
+        return ones
+    if is_last and opt.get("no_candidate_decision", False):
+        return ones
+    if not is_last and not opt.get("masking_decision", False):
+        return ones
+    mapping = teacher.get("vocab_mapping")
+    tok = mapping[tokens] if mapping is not None else tokens
+    with_bos = torch.cat([torch.full((tok.shape[0], 1), BOS, dtype=tok.dtype), tok], dim=1)
+    logits = decoding_phase(teacher["sd"], teacher["opt"], with_bos[:, :-1], t_inputs)
+    probs = F.softmax(logits, dim=-1).gather(2, tok.unsqueeze(2)).squeeze(2)
+    probs[pad_mask] = 1.0
+    return probs   # (eos_mask is empty: no <eos> is ever placed, Translator.py:270,282-284)
+
+
+def nar_translate(sd, opt, feats, return_trace=False, teacher=None):
     """Translator_NARFormer.translate_batch (models/Translator.py:240-305) running
-    MaskPredict.generate (misc/Decoding/na_algorithms.py:152-197) with no teacher (teacher
-    rescoring returns ones, :92-104), select_worst (:128-137)."""
+    MaskPredict.generate (misc/Decoding/na_algorithms.py:152-197), select_worst (:128-137).  `teacher`
+    (dict sd / opt / vocab_mapping, optional): the auto-regressive model that rescores the candidates
+    (Translator.py:250-264, na_algorithms.py:92-126)."""
     with torch.no_grad():
         enc = encoding_phase(sd, opt, feats)
         B = feats[0].shape[0]
         beam = length_candidates(opt, enc)
         n_len = beam.shape[1]
         inputs = {k: repeat_rows(enc[k], n_len) for k in decoder_input_keys(opt)}
+        t_inputs = None
+        if teacher is not None:
+            t_enc = encoding_phase(teacher["sd"], teacher["opt"], feats)
+            t_inputs = {k: repeat_rows(t_enc[k], n_len) for k in decoder_input_keys(teacher["opt"])}
         Lmax = int(beam.max())
         tri = torch.triu(torch.ones(Lmax, Lmax, dtype=torch.long), 1)
         length_mask = torch.stack([tri[beam[b] - 1] for b in range(B)], dim=0)
@@ -431,20 +462,22 @@ def nar_translate(sd, opt, feats, return_trace=False):
         else:
             tokens, probs = _nar_pass(sd, opt, inputs, tokens, pad_mask)
         for c in range(1, T):
+            corr = _teacher_probs(teacher, t_inputs, opt, tokens, pad_mask, is_last=False)
             if use_ct and c == 1:
                 mask_ind = tokens == MASK
             else:
                 num_mask = (seq_lens.float() * (1.0 - (c / T))).long()
                 mask_ind = torch.zeros_like(probs)
+                worst = probs * corr
                 for i in range(mask_ind.shape[0]):
-                    ind = probs[i].topk(max(1, int(num_mask[i])), largest=False, sorted=False)[1]
+                    ind = worst[i].topk(max(1, int(num_mask[i])), largest=False, sorted=False)[1]
                     mask_ind[i, ind] = 1
                 mask_ind = mask_ind.bool()
             tokens[mask_ind] = MASK
             new_tokens, new_probs = _nar_pass(sd, opt, inputs, tokens, pad_mask)
             tokens[mask_ind] = new_tokens[mask_ind]
             probs[mask_ind] = new_probs[mask_ind]
-        lprobs = probs.log()
+        lprobs = (probs * _teacher_probs(teacher, t_inputs, opt, tokens, pad_mask, is_last=True)).log()
 
         hyp = tokens.view(B, n_len, Lmax)
         lprobs = lprobs.view(B, n_len, Lmax)

@@ -37,6 +37,7 @@ CASES = [
     # CABase (attr_attention layer, "Cross -> Semantic" and the reverse order)
     ("cab_sharp", "cab", {}, 8, dict(seed=8, perturb=True, sharpen=SHARP)),
     ("cab_attr2cross_sharp", "cab", dict(attr_layer_pos="attr2cross"), 6, dict(seed=9, perturb=True, sharpen=SHARP)),
+    ("cab_parallel_sharp", "cab", dict(attr_layer_pos="parallel"), 6, dict(seed=10, perturb=True, sharpen=SHARP)),
     # round 2: the benchmark's own weights at the headline width (no <eos>: all 29 steps, deep KV cache) ...
     ("cfg4_plain", "cfg4", {}, 8, dict(seed=0)),
     # ... and "trained-like" peaked weights (oracle/weights.py TRAINED: top-1 probability ~0.6, entropy ~1.3 nats,
@@ -111,10 +112,108 @@ ENSEMBLE_CASES = [
 ]
 
 
+def permuted_vocab_mapping(n, seed):
+    """student id -> teacher id for a teacher whose corpus lists the same words in another order; the special
+    tokens keep their ids (Translator.py:344 asserts it for <pad>)."""
+    g = torch.Generator().manual_seed(seed)
+    mapping = torch.arange(n)
+    mapping[6:] = 6 + torch.randperm(n - 6, generator=g)
+    return mapping
+
+
+TEACHER_CASES = [
+    # name, student overrides, teacher weights, student weights, batch, vocabulary mapping seed (None: same corpus)
+    ("cfg5_teacher_sharp", {}, dict(seed=41, perturb=True, sharpen=SHARP), dict(seed=6, perturb=True, sharpen=SHARP), 5, None),
+    ("cfg5_teacher_masking_sharp", dict(masking_decision=True), dict(seed=42, perturb=True, sharpen=SHARP),
+     dict(seed=6, perturb=True, sharpen=SHARP), 4, None),
+    ("cfg5_teacher_mapped_sharp", dict(masking_decision=True), dict(seed=43, perturb=True, sharpen=SHARP),
+     dict(seed=7, perturb=True, sharpen=SHARP), 4, 99),
+]
+
+
+def run_teacher_case(name, over, teacher_w, student_w, bsz, map_seed, feat_seed=11):
+    """Mask-predict with an auto-regressive teacher rescoring the candidates (models/Translator.py:250-264,
+    misc/Decoding/na_algorithms.py:92-126,168,193-195) through the reference's own Translator_NARFormer."""
+    import pickle
+    import tempfile
+    from types import SimpleNamespace
+    opt = make_opt(**{**CONFIGS["cfg5"], **over})
+    t_opt = make_opt(**CONFIGS["cfg2"])
+    tmp = tempfile.mkdtemp()
+    words = {i: "w%d" % i for i in range(opt["vocab_size"])}
+    mapping = permuted_vocab_mapping(opt["vocab_size"], map_seed) if map_seed is not None else None
+    t_words = words if mapping is None else {int(mapping[i]): w for i, w in words.items()}
+    for fn, vocab, o in (("student.pkl", words, opt), ("teacher.pkl", t_words, t_opt)):
+        with open(os.path.join(tmp, fn), "wb") as f:
+            pickle.dump({"info": {"itow": vocab}}, f)
+        o["info_corpus"] = os.path.join(tmp, fn)
+    student = rh.build_reference_model(opt)
+    student.load_state_dict(make_state_dict(opt, **student_w), strict=True)
+    teacher = rh.build_reference_model(t_opt)
+    teacher.load_state_dict(make_state_dict(t_opt, **teacher_w), strict=True)
+    feats = make_feats(opt, bsz, seed=feat_seed)
+    _, get_translator, _ = rh.load_reference()
+    wrapper = SimpleNamespace(captioner=teacher, get_opt=lambda: t_opt)
+    with torch.no_grad():
+        hyps, lprobs = get_translator(dict(opt)).translate_batch([student], {"feats": feats}, vocab=words,
+                                                                 teacher_model_wrapper=wrapper)
+        plain_h, _ = get_translator(dict(opt)).translate_batch([student], {"feats": [f.clone() for f in feats]}, vocab=words)
+    return dict(name=name, overrides=over, teacher_weights=teacher_w, weights=student_w, batch=bsz, map_seed=map_seed,
+                feat_seed=feat_seed, hyps=hyps, scores=lprobs, differs_from_no_teacher=sum(a != b for a, b in zip(hyps, plain_h)))
+
+
+def crit_inputs(opt, bsz, seed):
+    """Synthetic inputs of the evaluation criteria: concept probabilities with saturated tails (clamped to
+    [0.01, 0.99] by the criterion, so ties occur as they do with a trained head), multi-hot labels with 1..24
+    positives, length log-probabilities and a target length distribution."""
+    g = torch.Generator().manual_seed(4242 + seed)
+    n = opt["attribute_prediction_k"]
+    labels = torch.zeros(bsz, n)
+    for v in range(bsz):
+        k = int(torch.randint(1, 25, (1,), generator=g))
+        labels[v, torch.randperm(n, generator=g)[:k]] = 1.0
+    found = (torch.rand(bsz, n, generator=g) < 0.7).float()      # the head "detects" 70 % of the positives
+    preds = torch.sigmoid(3.0 * torch.randn(bsz, n, generator=g) - 2.0 + 5.0 * labels * found)
+    batch = {"preds_attr": preds, "avg_prob_attr": preds.mean(1), "labels_attr": labels}
+    if "length" in opt["crits"]:
+        batch["preds_length"] = torch.log_softmax(torch.randn(bsz, opt["max_len"], generator=g), dim=-1)
+        t = torch.rand(bsz, opt["max_len"], generator=g) * (torch.rand(bsz, opt["max_len"], generator=g) > 0.6)
+        t[:, 7] += 0.1
+        batch["length_target"] = t / t.sum(1, keepdim=True)
+    return batch
+
+
+def run_crit_case(cfg, batches=((16, 0), (7, 1), (32, 2))):
+    """The reference's own evaluation criterion (models/Wrapper.py:421: get_criterion(opt, skip 'lang',
+    calculate_mAP=True)) on synthetic head outputs; records every batch's loss and the final loss-info table."""
+    rh.load_reference()
+    from misc.Crit import get_criterion
+    opt = make_opt(**CONFIGS[cfg])
+    crit = get_criterion(dict(opt), skip_crit_list=["lang"], override_opt={"calculate_mAP": True})
+    losses = [float(crit.get_loss(crit_inputs(opt, b, s))) for b, s in batches]
+    return dict(name="crit_" + cfg, config=cfg, batches=[list(b) for b in batches], losses=losses,
+                loss_info=crit.get_loss_info())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     assert rh.reference_available(), "needs /root/reference"
     only = set(sys.argv[1:])
+    for case in TEACHER_CASES:
+        if only and case[0] not in only:
+            continue
+        rec = run_teacher_case(*case)
+        with open(os.path.join(OUT, "nar_" + rec["name"] + ".json"), "w") as f:
+            json.dump(rec, f)
+        print(rec["name"], "lens", [sum(1 for t in h[0] if t != 0) for h in rec["hyps"]], "videos changed by the teacher:",
+              rec["differs_from_no_teacher"])
+    for cfg in ("cfg2", "cfg5"):
+        if only and ("crit_" + cfg) not in only:
+            continue
+        rec = run_crit_case(cfg)
+        with open(os.path.join(OUT, rec["name"] + ".json"), "w") as f:
+            json.dump(rec, f)
+        print(rec["name"], rec["loss_info"])
     for case in ENSEMBLE_CASES:
         if only and case[0] not in only:
             continue

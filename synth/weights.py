@@ -97,13 +97,17 @@ def make_state_dict(opt, seed=0, perturb=False, sharpen=None):
     atts = ["intra_attention", "inter_attention"]
     if opt.get("use_attr", False) and "att" in opt.get("use_attr_type", "att"):
         atts.append("attr_attention")   # deepcopy of inter_attention (models/components/Layers.py:117-119)
+    parallel = "attr_attention" in atts and opt.get("attr_layer_pos", "cross2attr") == "parallel"   # Layers.py:107-108,121-122
     for att in atts:
         if att != "intra_attention" and opt.get("add_hybrid_attention_bias", False):
             sd[L + att + ".SDPA.hybrid_bias"] = torch.zeros(opt["num_attention_heads"], hybrid_length(opt))
         for nm_ in ("query", "key", "value"):
             _linear(sd, gen, L + att + ".SDPA." + nm_, d, d)
         _linear(sd, gen, L + att + ".dense", d, d)
-        _layernorm(sd, L + att + ".LayerNorm", d)
+        if att == "intra_attention" or not parallel:
+            _layernorm(sd, L + att + ".LayerNorm", d)
+    if parallel:
+        _layernorm(sd, L + "LayerNorm", d)
     _linear(sd, gen, L + "ffn.dense1", opt["intermediate_size"], d)
     _linear(sd, gen, L + "ffn.dense2", d, opt["intermediate_size"])
     _layernorm(sd, L + "ffn.LayerNorm", d)

@@ -17,7 +17,7 @@ from tests.helpers import load_golden, rebuild_case
 pytestmark = pytest.mark.gpu
 
 AR_CASES = ["cfg1_plain", "cfg1_sharp", "cfg2_plain", "cfg2_sharp", "cfg2_sharp_k3_nbest3_a07",
-            "cfg2_sharp_greedy", "cfg3_sharp", "cfg4_sharp", "cab_sharp", "cab_attr2cross_sharp",
+            "cfg2_sharp_greedy", "cfg3_sharp", "cfg4_sharp", "cab_sharp", "cab_attr2cross_sharp", "cab_parallel_sharp",
             "cfg4_plain", "cfg3_trained", "cfg4_trained"]
 
 
@@ -111,8 +111,8 @@ def _prefixes_from_trace(step_rec, B, K):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16-stream", "bf16"])
-@pytest.mark.parametrize("name", ["cfg2_sharp", "cfg1_sharp", "cfg4_sharp", "cab_sharp", "cfg3_trained", "cfg4_trained",
-                                  "cfg4_plain"])
+@pytest.mark.parametrize("name", ["cfg2_sharp", "cfg1_sharp", "cfg4_sharp", "cab_sharp", "cab_parallel_sharp",
+                                  "cfg3_trained", "cfg4_trained", "cfg4_plain"])
 def test_teacher_forced_step_logits(name, precision):
     """Every step's logits from the KV-cached, ancestry-indirected CUDA path against the oracle's
     full-prefix recompute on exactly the prefixes the GPU beam holds at that step.  "bf16-stream" forces the
@@ -162,7 +162,8 @@ def test_teacher_forced_step_logits(name, precision):
 
 
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
-@pytest.mark.parametrize("name", ["cfg2_plain", "cfg2_sharp", "cfg3_sharp", "cab_sharp", "cfg3_trained", "cfg4_trained"])
+@pytest.mark.parametrize("name", ["cfg2_plain", "cfg2_sharp", "cfg3_sharp", "cab_sharp", "cab_parallel_sharp", "cfg3_trained",
+                                  "cfg4_trained"])
 def test_h16_sequences(name, precision):
     """16-bit modes end to end on the small goldens: concept ids equal the fp32 reference's (the encoder runs as
     split products), sequences against the fp32 reference golden; a mismatching video must have a small oracle
@@ -294,26 +295,80 @@ def test_fused_vocab_records_direct():
 
 
 def test_wrapper_checkpoint_roundtrip(tmp_path):
-    """Lightning-layout checkpoint -> load_model -> translate_step, as translate.py drives it."""
+    """Lightning-layout checkpoint -> load_model (reference defaults: data paths rewritten) -> translate_step, as
+    translate.py drives it: the latency branch, then the non-latency branch whose teacher-forced pass feeds the
+    concept criterion (models/Wrapper.py:182-184) - its mAP / F1 table must equal the criterion applied to the
+    oracle's concept probabilities."""
+    import pickle
     import care_b200
     rec = load_golden("cfg2_sharp")
     opt, sd, feats = rebuild_case(rec, batch=4)
-    opt = dict(opt, care_precision="fp32")
+    old_base, new_base = os.path.join(str(tmp_path), "author"), os.path.join(str(tmp_path), "here")
+    os.makedirs(os.path.join(new_base, "MSRVTT"))
+    vocab = {i: "w%d" % i for i in range(opt["vocab_size"])}
+    with open(os.path.join(new_base, "MSRVTT", "info_corpus.pkl"), "wb") as f:
+        pickle.dump({"info": {"itow": vocab}}, f)
+    opt = dict(opt, care_precision="fp32", dataset="MSRVTT",
+               info_corpus=os.path.join(old_base, "MSRVTT", "info_corpus.pkl"),
+               reference=os.path.join(old_base, "MSRVTT", "refs.pkl"),
+               feats_a=[os.path.join(old_base, "MSRVTT", "feats", "audio.hdf5")])
     m = care_b200.Model(opt)
     m.captioner.load_state_dict(sd)
     path = os.path.join(str(tmp_path), "best.ckpt")
     torch.save(m.to_checkpoint(), path)
-    model = care_b200.load_model(path, device=torch.device("cuda"), strict=True)
+    model = care_b200.load_model(path, device=torch.device("cuda"), strict=True, base_data_path=new_base)
+    assert model.get_opt()["feats_a"] == [os.path.join(new_base, "MSRVTT", "feats", "audio.hdf5")]
+    assert model.get_vocab() == vocab          # read through the rewritten info_corpus path
     assert model.get_keys_to_device() == ["feats", "input_ids"]
-    vocab = {i: "w%d" % i for i in range(opt["vocab_size"])}
-    batch = {"feats": [f.cuda() for f in feats], "video_ids": ["video%d" % i for i in range(4)]}
-    out = model.translate_step(batch, vocab, assert_only_a_caption_per_video=True)
+    g = torch.Generator().manual_seed(5)
+    labels = (torch.rand(4, 500, generator=g) < 0.03).float()
+    labels[:, 3] = 1.0
+    batch = {"feats": [f.cuda() for f in feats], "video_ids": ["video%d" % i for i in range(4)],
+             "input_ids": torch.randint(4, opt["vocab_size"], (4, 9), generator=g).cuda(), "labels_attr": labels}
+    out = model.translate_step(batch, vocab, assert_only_a_caption_per_video=True, inference_latency=True)
+    assert model.eval_criterion.get_loss_info()["F1-05"] == 0      # latency branch: criterion untouched
     for i in range(4):
         item = out["video%d" % i][0]
-        words = [("w%d" % t) for t in rec["hyps"][i][0] if t not in (0, 3)]
         ref_caption = care_b200.to_sentence(rec["hyps"][i][0], vocab)
         assert item["caption"] == ref_caption and item["image_id"] == "video%d" % i
         assert abs(item["score"] - rec["scores"][i][0]) < 1e-4 * max(1.0, abs(rec["scores"][i][0]))
+    out2 = model.translate_step(batch, vocab)                      # non-latency branch
+    assert {k: v[0]["caption"] for k, v in out2.items()} == {k: v[0]["caption"] for k, v in out.items()}
+    info = model.eval_criterion.get_loss_info()
+    want = care_b200.get_criterion(opt, skip_crit_list=["lang"], override_opt={"calculate_mAP": True})
+    want.get_loss({"preds_attr": co.encoding_phase(sd, opt, feats)["preds_attr"], "labels_attr": labels})
+    for k, v in want.get_loss_info().items():
+        assert abs(info[k] - v) < 1e-5 * max(1.0, abs(v)), (k, info[k], v)
+    scores, _, preds = model.test_epoch_end([out2], verbose=False, keys_added_to_scores=["beam_size"], analyze=False)
+    assert abs(scores["mAP"] - want.get_loss_info()["mAP"]) < 1e-5 and scores["beam_size"] == opt["beam_size"]
+    assert set(preds) == {"video%d" % i for i in range(4)}
+    assert model.eval_criterion.get_loss_info()["F1-05"] == 0      # recorders reset by the evaluation
+
+
+def test_model_ensemble_wrapper(tmp_path):
+    """ModelEnsemble (models/Wrapper.py:617-714) over two checkpoints: the wrapper's translate_step equals the
+    reference's ensemble golden (mean of the models' log-probabilities)."""
+    import care_b200
+    rec = load_golden("ens2_cfg2_sharp")
+    from tests.helpers import rebuild_ensemble_case
+    opt, sds, feats = rebuild_ensemble_case(rec)
+    opt = dict(opt, **{"feats_%s" % c: ["/data/feats_%s.hdf5" % c] for c in opt["modality"]})
+    paths = []
+    for i, sd in enumerate(sds):
+        m = care_b200.Model(dict(opt, care_precision="fp32"))
+        m.captioner.load_state_dict(sd)
+        paths.append(os.path.join(str(tmp_path), "m%d.ckpt" % i))
+        torch.save(m.to_checkpoint(), paths[-1])
+    model = care_b200.load_model(paths, device=torch.device("cuda"), strict=True, replace_paths=False)
+    assert isinstance(model, care_b200.ModelEnsemble) and isinstance(model.captioner, list) and len(model.captioner) == 2
+    assert not model.need_to_split_feats
+    vocab = {i: "w%d" % i for i in range(opt["vocab_size"])}
+    B = feats[0].shape[0]
+    batch = {"feats": [f.cuda() for f in feats], "video_ids": ["v%d" % i for i in range(B)]}
+    out = model.translate_step(batch, vocab)
+    for i in range(B):
+        assert out["v%d" % i][0]["caption"] == care_b200.to_sentence(rec["hyps"][i][0], vocab)
+        assert abs(out["v%d" % i][0]["score"] - rec["scores"][i][0]) < 1e-4 * max(1.0, abs(rec["scores"][i][0]))
 
 
 def test_no_gpu_no_fallback_message():
@@ -352,6 +407,53 @@ def test_nar_fp32_matches_reference_golden(name):
             assert float(top2[0] - top2[1]) < 1e-3, "video %d differs with a clear candidate margin" % v
     print("\n%s fp32: %d/%d mask-predict outputs identical to the reference" % (name, exact, len(hyps)))
     assert exact >= 0.75 * len(hyps)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("name", ["nar_cfg5_teacher_sharp", "nar_cfg5_teacher_masking_sharp", "nar_cfg5_teacher_mapped_sharp"])
+def test_nar_teacher_rescoring(name, precision, tmp_path):
+    """Mask-predict with an auto-regressive teacher rescoring the candidates (models/Translator.py:250-264,
+    na_algorithms.py:92-126): final rescoring, per-iteration masking decisions, a teacher with another vocabulary
+    order - against the reference's own outputs (fp32 mode: tokens exact unless the oracle's candidate margin is a
+    near-tie; fp16: well-formed and mostly the same length)."""
+    import pickle
+    from types import SimpleNamespace
+    import care_b200
+    from tests.helpers import rebuild_teacher_case
+    rec = load_golden(name)
+    opt, sd, feats, teacher = rebuild_teacher_case(rec)
+    words = {i: "w%d" % i for i in range(opt["vocab_size"])}
+    mapping = teacher["vocab_mapping"]
+    t_words = words if mapping is None else {int(mapping[i]): w for i, w in words.items()}
+    t_opt = dict(teacher["opt"])
+    for fn, vocab, o in (("student.pkl", words, opt), ("teacher.pkl", t_words, t_opt)):
+        with open(os.path.join(str(tmp_path), fn), "wb") as f:
+            pickle.dump({"info": {"itow": vocab}}, f)
+        o["info_corpus"] = os.path.join(str(tmp_path), fn)
+    model = _gpu_model(opt, sd, precision)
+    t_model = _gpu_model(t_opt, teacher["sd"], precision)
+    wrapper = SimpleNamespace(captioner=t_model, get_opt=lambda: t_opt)
+    tr = care_b200.get_translator(opt)
+    hyps, lprobs = tr.translate_batch([model], {"feats": [f.cuda() for f in feats]}, teacher_model_wrapper=wrapper, vocab=words)
+    assert (tr.vocab_mapping is None) == (mapping is None)
+    _, _, otr = co.nar_translate(sd, opt, feats, return_trace=True, teacher=teacher)
+    exact = 0
+    for v in range(len(hyps)):
+        assert len(hyps[v]) == 1 and len(hyps[v][0]) == len(lprobs[v][0])
+        if hyps[v] == rec["hyps"][v]:
+            exact += 1
+            if precision == "fp32":
+                a, b = torch.tensor(lprobs[v][0]), torch.tensor(rec["scores"][v][0])
+                assert (a - b).abs().max().item() < 5e-4 * max(1.0, b.abs().max().item()), (v, a, b)
+        elif precision == "fp32":
+            top2 = otr["avg"][v].topk(2)[0]
+            assert float(top2[0] - top2[1]) < 1e-3, "video %d differs with a clear candidate margin" % v
+    print("\n%s %s: %d/%d teacher-rescored outputs identical to the reference" % (name, precision, exact, len(hyps)))
+    if precision == "fp32":
+        assert exact >= len(hyps) - 1
+    # without the teacher the same model gives other log-probabilities: the rescoring really ran
+    plain_h, plain_p = care_b200.get_translator(opt).translate_batch([model], {"feats": [f.cuda() for f in feats]})
+    assert plain_p != lprobs
 
 
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
