@@ -86,6 +86,14 @@ int care_ctx_create(care_ctx** out, int device) {
                     prop.major, prop.minor);
     return -3;
   }
+  // allocations below go to `device`; the caller's current device is restored before returning (the library
+  // must not change torch's current device as a side effect)
+  int prev_device = -1;
+  CARE_CUDA(cudaGetDevice(&prev_device));
+  struct Restore {
+    int dev;
+    ~Restore() { if (dev >= 0) cudaSetDevice(dev); }
+  } restore{prev_device == device ? -1 : prev_device};
   CARE_CUDA(cudaSetDevice(device));
   care_ctx* c = new care_ctx();
   c->device = device;

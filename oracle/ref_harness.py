@@ -1,5 +1,6 @@
 """Container-only harness that imports the UNMODIFIED reference (yangbang18/CARE) from
-/root/reference and runs its own inference path on CPU.
+/root/reference - or from the archive of its Python packages oracle/_ref/reference_py.zip (oracle/build_ref.py), which is
+how it reaches the GPU box - and runs its own inference path on CPU.
 
 TEST INFRASTRUCTURE ONLY.  Nothing in the product package (care_b200/) may import this
 module.  It exists to (a) generate the golden fixtures under tests/golden/ (see
@@ -15,11 +16,28 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("CARE_REFERENCE_ROOT", "/root/reference")
+# zip of the reference's Python packages made by oracle/build_ref.py (imported through zipimport)
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference_py.zip")
+
+
+def _is_reference(root):
+    return bool(root) and (os.path.isfile(os.path.join(root, "models", "Translator.py")) or
+                           (root.endswith(".zip") and os.path.isfile(root)))
+
+
+def _pick_root():
+    for root in (os.environ.get("CARE_REFERENCE_ROOT"), "/root/reference", _VENDORED):
+        if _is_reference(root):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "Translator.py"))
+    """True in the build container (/root/reference) and wherever oracle/_ref travelled (the GPU box)."""
+    return _is_reference(REFERENCE_ROOT)
 
 
 def _install_stubs():
