@@ -111,6 +111,14 @@ int care_ctx_create(care_ctx** out, int device) {
   // one-time timing (timings taken under a profiler are not representative); CARE_B200_DEBUG=1 logs the choices
   if (const char* e = getenv("CARE_B200_GEMM_2SM")) c->gemm_2sm = atoi(e);
   if (const char* e = getenv("CARE_B200_DEBUG")) c->debug = atoi(e);
+  if (const char* path = getenv("CARE_B200_GEMM_CHOICE_FILE")) {   // GEMM variants picked by an earlier run
+    if (FILE* f = fopen(path, "r")) {
+      unsigned long long key;
+      int choice;
+      while (fscanf(f, "%llu %d", &key, &choice) == 2) c->gemm_choice[(uint64_t)key] = choice;
+      fclose(f);
+    }
+  }
   if (cudaMalloc(&c->self_attn_rows, sizeof(unsigned long long)) != cudaSuccess ||
       cudaMemset(c->self_attn_rows, 0, sizeof(unsigned long long)) != cudaSuccess) {
     care::set_error("care_ctx_create: cannot allocate the ctx counters");

@@ -5,12 +5,12 @@
 // LayerNorm needs all d output columns, but d = 1024 fp32 accumulator columns do not fit one SM's tensor
 // memory twice (512 columns).  So a thread-block CLUSTER of CN = d / 256 CTAs shares one 128-row block: CTA r
 // computes columns [256 r, 256 r + 256) with the mainloop of gemm_tcgen05.cu (TMA producer warp, single-thread
-// tcgen05.mma issuer, accumulator double-buffered in TMEM), and the epilogue makes two passes over its
-// accumulator:
-//   pass 1  v = acc + bias + residual, written back to TMEM in place; per-row (sum, sum of squares) over the
-//           CTA's 256 columns stay in the row's thread and are sent to the other CTAs of the cluster with
-//           st.async into their shared memory (completion counted on an mbarrier there - no cluster-wide
-//           barrier, the producer / MMA warps never stop);
+// tcgen05.mma issuer, accumulator double-buffered in TMEM), and the epilogue (8 warps: one thread per row and
+// column half) makes two passes over its accumulator:
+//   pass 1  v = acc + bias + residual, written back to TMEM in place; the per-row (sum, sum of squares) of the
+//           two column halves meet through shared memory, and the CTA's 256-column partial is sent to the other
+//           CTAs of the cluster with st.async into their shared memory (completion counted on an mbarrier
+//           there - no cluster-wide barrier, the producer / MMA warps never stop);
 //   pass 2  mean / rstd from the CN partial statistics, y = (v - mean) * rstd * gamma + beta, converted and
 //           stored through a swizzled shared-memory transpose as 64-byte row segments.
 // The fp32 pre-LayerNorm tensor of the unfused path (84 MB written and read back per sub-layer at cfg4) never
@@ -35,8 +35,9 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int THREADS = 384;        // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-7, 8-11: two epilogue groups
 constexpr int XP_BYTES = 2048;      // per epilogue warp: one 32-row x 64-byte transposition block
 constexpr int MAX_CN = 4;
-constexpr int STAT_SLOT = BLOCK_M * 8;                          // (sum, sumsq) of 128 rows from one peer CTA
-constexpr int STATS_BYTES = 2 * 2 * (MAX_CN - 1) * STAT_SLOT;   // [group][parity][peer]
+constexpr int STAT_SLOT = BLOCK_M * 8;                          // (sum, sumsq) of 128 rows
+constexpr int N_SLOTS = 2 + (MAX_CN - 1);                       // this CTA's two column halves + one per peer CTA
+constexpr int STATS_BYTES = 2 * N_SLOTS * STAT_SLOT;            // [tile parity][slot]
 constexpr int PARAM_BYTES = 3 * BN * 4;                         // bias | gamma | beta of this CTA's columns
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * XP_BYTES + STATS_BYTES + PARAM_BYTES + BAR_BYTES + 1024;
@@ -147,8 +148,8 @@ gemm_add_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  auto stats_bar = [&](int g, int p) { return bar_base + 8u * (2 * STAGES + 4 + 2 * g + p); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 8);
+  auto stats_bar = [&](int p) { return bar_base + 8u * (2 * STAGES + 4 + p); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 6);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
   float* param_gen = reinterpret_cast<float*>(smem_gen + (param_base - smem_base));
 
@@ -171,9 +172,8 @@ gemm_add_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), EPI_WARPS);
-      mbar_init(stats_bar(a, 0), 1);
-      mbar_init(stats_bar(a, 1), 1);
+      mbar_init(tempty_bar(a), 2 * EPI_WARPS);
+      mbar_init(stats_bar(a), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -238,37 +238,43 @@ gemm_add_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: one thread per row (TMEM lane); two groups of 4 warps take alternate row blocks =====
+    // ===== epilogue: one thread per (row, column half): warps 4-7 take columns [0, 128) of the CTA's 256, warps
+    // 8-11 columns [128, 256) of the SAME tile, so a tile's epilogue has half the latency (what a CTA with a single
+    // row block is exposed to); the accumulator is double-buffered per tile, so the epilogue of tile i still
+    // overlaps the MMAs of tile i+1 =====
     const int grp = (warp - 4) >> 2;
     const int ew = (warp - 4) & 3;   // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
+    constexpr int HALF = BN / 2;
     uint8_t* xp = smem_gen + (xp_base - smem_base) + (warp - 4) * XP_BYTES;
-    const float* bias_s = param_gen;
-    const float* gamma_s = param_gen + BN;
-    const float* beta_s = param_gen + 2 * BN;
+    const float* bias_s = param_gen + grp * HALF;
+    const float* gamma_s = param_gen + BN + grp * HALF;
+    const float* beta_s = param_gen + 2 * BN + grp * HALF;
     const int64_t res_ld = (int64_t)N * (R32 ? 4 : 2);
-    const uint8_t* res_b = reinterpret_cast<const uint8_t*>(residual) + (int64_t)n_blk * BN * (R32 ? 4 : 2);
-    uint8_t* out16_b = reinterpret_cast<uint8_t*>(out16) + (int64_t)n_blk * BN * 2;
-    uint8_t* out32_b = reinterpret_cast<uint8_t*>(out32) + (int64_t)n_blk * BN * 4;
+    const int col_first = n_blk * BN + grp * HALF;
+    const uint8_t* res_b = reinterpret_cast<const uint8_t*>(residual) + (int64_t)col_first * (R32 ? 4 : 2);
+    uint8_t* out16_b = reinterpret_cast<uint8_t*>(out16) + (int64_t)col_first * 2;
+    uint8_t* out32_b = reinterpret_cast<uint8_t*>(out32) + (int64_t)col_first * 4;
     constexpr int NSUB = R32 ? 2 : 1;   // 64-byte sub-blocks of the residual per 32-column chunk
-    uint32_t i = grp;
-    for (int m_blk = cluster_id + grp * n_clusters; m_blk < m_tiles; m_blk += 2 * n_clusters, i += 2) {
-      const uint32_t gcount = i >> 1, par = gcount & 1u, sph = (gcount >> 1) & 1u;
+    const uint32_t my_row = (uint32_t)(ew * 32 + lane);
+    uint32_t tcount = 0;
+    for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters, ++tcount) {
+      const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
       const int row0 = m_blk * BLOCK_M + ew * 32;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + grp * BN;
-      if (ew == 0 && lane == 0) mbar_expect_tx(stats_bar(grp, par), (csize - 1) * STAT_SLOT);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + grp * HALF;
+      if (warp == 4 && lane == 0) mbar_expect_tx(stats_bar(acc), (csize - 1) * STAT_SLOT);
       uint4 gn[NSUB][4];
 #pragma unroll
       for (int sb = 0; sb < NSUB; ++sb) ldg_block(res_b + sb * 64, res_ld, row0, M, lane, gn[sb]);
-      mbar_wait(tfull_bar(grp), gcount & 1u);
+      mbar_wait(tfull_bar(acc), aph);
       tc_fence_after();
       // ---- pass 1: v = acc + bias + residual -> TMEM; row statistics ----
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < HALF / 32; ++c) {
         uint4 rr[NSUB][4];
 #pragma unroll
         for (int sb = 0; sb < NSUB; ++sb) xp_to_rows(xp, lane, gn[sb], rr[sb]);
-        if (c + 1 < BN / 32) {
+        if (c + 1 < HALF / 32) {
 #pragma unroll
           for (int sb = 0; sb < NSUB; ++sb)
             ldg_block(res_b + (c + 1) * 32 * (R32 ? 4 : 2) + sb * 64, res_ld, row0, M, lane, gn[sb]);
@@ -299,18 +305,27 @@ gemm_add_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         tmem_st32(taddr + c * 32, v);
       }
       tmem_st_wait();
-      // ---- exchange the row statistics with the other CTAs of the cluster ----
-      const uint32_t my_row = (uint32_t)(ew * 32 + lane);
-      for (uint32_t dst = 0; dst < csize; ++dst) {
-        if (dst == crank) continue;
-        const uint32_t slot = crank < dst ? crank : crank - 1;
-        const uint32_t local = stats_base + ((grp * 2 + par) * (MAX_CN - 1) + slot) * STAT_SLOT + my_row * 8;
-        st_async_f2(map_to_cta(local, dst), s1, s2, map_to_cta(stats_bar(grp, par), dst));
+      // ---- exchange the row statistics: the two column halves of this CTA through local slots and a named
+      // barrier, then the CTA's 256-column partial to every peer CTA (st.async, counted on the peer's mbarrier) ----
+      uint8_t* table = smem_gen + (stats_base - smem_base) + acc * N_SLOTS * STAT_SLOT;
+      *reinterpret_cast<float2*>(table + grp * STAT_SLOT + my_row * 8) = make_float2(s1, s2);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      {
+        const float2 o = *reinterpret_cast<const float2*>(table + (grp ^ 1) * STAT_SLOT + my_row * 8);
+        s1 += o.x;
+        s2 += o.y;
       }
-      mbar_wait_cluster(stats_bar(grp, par), sph);
-      for (uint32_t slot = 0; slot + 1 < csize; ++slot) {
-        const float2 o = *reinterpret_cast<const float2*>(
-            smem_gen + (stats_base - smem_base) + ((grp * 2 + par) * (MAX_CN - 1) + slot) * STAT_SLOT + my_row * 8);
+      if (grp == 0) {
+        for (uint32_t dst = 0; dst < csize; ++dst) {
+          if (dst == crank) continue;
+          const uint32_t slot = 2 + (crank < dst ? crank : crank - 1);
+          const uint32_t local = stats_base + (acc * N_SLOTS + slot) * STAT_SLOT + my_row * 8;
+          st_async_f2(map_to_cta(local, dst), s1, s2, map_to_cta(stats_bar(acc), dst));
+        }
+      }
+      mbar_wait_cluster(stats_bar(acc), aph);
+      for (uint32_t slot = 2; slot < 1 + csize; ++slot) {
+        const float2 o = *reinterpret_cast<const float2*>(table + slot * STAT_SLOT + my_row * 8);
         s1 += o.x;
         s2 += o.y;
       }
@@ -319,7 +334,7 @@ gemm_add_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       const float rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + eps);
       // ---- pass 2: normalise, scale, store ----
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < HALF / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(taddr + c * 32, v);
         float y[32];
@@ -352,7 +367,7 @@ gemm_add_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(grp));
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
   }
 
