@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--self-compact", type=int, default=None, choices=(0, 1, 2, 3),
                     help="bf16 self-attention: 0 = dense tiles, 1 = per-CTA gather of the live cache slots, "
                          "2 = gathered chunk stream (the library default)")
+    ap.add_argument("--graph-lanes", type=int, default=None,
+                    help="concurrent lanes of a graph-replayed decode (A/B runs; default: the engine's automatic choice)")
     ap.add_argument("--no-latency", action="store_true", help="skip the small-batch latency section (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-fed e2e section (profiling runs)")
     return ap.parse_args()
@@ -319,7 +321,8 @@ def run_care_arm(args):
     opt = make_opt(**CONFIGS[args.config])
     nar = opt["decoding_type"] == "NARFormer"
     sd = make_state_dict(opt, seed=0, perturb=nar)
-    model = care_b200.get_framework(dict(opt, care_precision=args.precision, care_self_compact=args.self_compact))
+    extra = {} if args.graph_lanes is None else {"care_graph_lanes": args.graph_lanes}
+    model = care_b200.get_framework(dict(opt, care_precision=args.precision, care_self_compact=args.self_compact, **extra))
     # (care_self_compact None keeps the library default)
     model.load_state_dict(sd)
     model = model.eval().to(dev)

@@ -32,6 +32,7 @@ _SIGNATURES = {
     "care_ctx_create": (c_int, [POINTER(c_void_p), c_int]),
     "care_ctx_destroy": (None, [c_void_p]),
     "care_ctx_sm_count": (c_int, [c_void_p]),
+    "care_ctx_share_tuning": (c_int, [c_void_p, c_void_p]),
     "care_ctx_launch_count": (c_int64, [c_void_p]),
     "care_ctx_last_kernel": (c_char_p, [c_void_p, c_char_p]),
     "care_ctx_set_early_exit": (c_int, [c_void_p, c_void_p, c_int]),

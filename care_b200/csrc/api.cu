@@ -115,7 +115,7 @@ int care_ctx_create(care_ctx** out, int device) {
     if (FILE* f = fopen(path, "r")) {
       unsigned long long key;
       int choice;
-      while (fscanf(f, "%llu %d", &key, &choice) == 2) c->gemm_choice[(uint64_t)key] = choice;
+      while (fscanf(f, "%llu %d", &key, &choice) == 2) c->tuning->choice[(uint64_t)key] = choice;
       fclose(f);
     }
   }
@@ -157,6 +157,14 @@ const char* care_ctx_last_kernel(const care_ctx* ctx, const char* family) {
   return "";
 }
 
+int care_ctx_share_tuning(care_ctx* ctx, care_ctx* other) {
+  CARE_CHECK_ARG(ctx && other && ctx->device == other->device, "care_ctx_share_tuning: two contexts of one device");
+  ctx->tuning = other->tuning;
+  ctx->gemm_2sm = other->gemm_2sm;
+  ctx->gemm_bn = other->gemm_bn;
+  return 0;
+}
+
 int care_ctx_sm_count(const care_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
 int64_t care_ctx_launch_count(const care_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -196,8 +204,8 @@ int care_ctx_set_option(care_ctx* ctx, const char* name, int value) {
   }
   if (strcmp(name, "gemm_2sm") == 0) {
     ctx->gemm_2sm = value;
-    std::lock_guard<std::mutex> g(ctx->mu);
-    ctx->gemm_choice.clear();
+    std::lock_guard<std::mutex> g(ctx->tuning->mu);
+    ctx->tuning->choice.clear();
     return 0;
   }
   if (strcmp(name, "gemm_bn") == 0) {   // 0: pick the tile width per shape; 64..256 (multiple of 32): force it
@@ -206,8 +214,8 @@ int care_ctx_set_option(care_ctx* ctx, const char* name, int value) {
       return -1;
     }
     ctx->gemm_bn = value;
-    std::lock_guard<std::mutex> g(ctx->mu);
-    ctx->gemm_choice.clear();
+    std::lock_guard<std::mutex> g(ctx->tuning->mu);
+    ctx->tuning->choice.clear();
     return 0;
   }
   care::set_error("care_ctx_set_option: unknown option '%s'", name);

@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -131,7 +132,13 @@ struct care_ctx {
   int gemm_bn = 0;   // > 0: force this tile width in the single-CTA GEMM (A/B runs)
   int debug = 0;
   int vocab_2sm = 1;   // fused vocabulary kernel on CTA pairs when the shape has >= two waves of pair tiles
-  std::unordered_map<uint64_t, int> gemm_choice;
+  // per-shape GEMM variant picks; contexts that must launch identical kernels (the lanes of one decode) share one
+  // table (care_ctx_share_tuning)
+  struct GemmTuning {
+    std::mutex mu;
+    std::unordered_map<uint64_t, int> choice;
+  };
+  std::shared_ptr<GemmTuning> tuning = std::make_shared<GemmTuning>();
   // device-side early exit: kernels without a per-video `done` predicate return at once when
   // *skip_counter >= skip_target (all videos of the batch have finished); NULL disables
   const int32_t* skip_counter = nullptr;

@@ -298,9 +298,9 @@ int gemm_bf16(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t 
                          (uint64_t)(out_dtype & 1);
     int choice = -1;
     {
-      std::lock_guard<std::mutex> g(ctx->mu);
-      auto it = ctx->gemm_choice.find(key);
-      if (it != ctx->gemm_choice.end()) choice = it->second;
+      std::lock_guard<std::mutex> g(ctx->tuning->mu);
+      auto it = ctx->tuning->choice.find(key);
+      if (it != ctx->tuning->choice.end()) choice = it->second;
     }
     if (choice < 0) {
       cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -347,8 +347,8 @@ int gemm_bf16(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t 
                   out_dtype == CARE_F32 ? "f32" : "bf16", best_ms[0] / 3.0f,
                   ok2 ? (std::to_string(best_ms[1] / 3.0f) + " ms").c_str() : "n/a", choice ? "CTA-pair" : "single-CTA");
         {
-          std::lock_guard<std::mutex> g(ctx->mu);
-          ctx->gemm_choice[key] = choice;
+          std::lock_guard<std::mutex> g(ctx->tuning->mu);
+          ctx->tuning->choice[key] = choice;
         }
         // profiling runs replay the choices of an unprofiled run (timings taken under ncu are not representative):
         // CARE_B200_GEMM_CHOICE_FILE names a file that receives "key choice" lines and is read back by care_ctx_create

@@ -88,6 +88,11 @@ class CareEngine:
         self.graph_max_rows = int(opt.get("care_cuda_graph_max_rows", 6144))
         self._graphs = {}
         self._graph_launches = 0
+        # graph-replayed decodes may run as concurrent lanes on separate streams (A/B switch, see _lanes_for);
+        # every lane but the first owns a twin engine (own ctx + workspaces)
+        self.graph_lanes = int(opt.get("care_graph_lanes", os.environ.get("CARE_B200_GRAPH_LANES", "1")))
+        self._twins = []
+        self._lane_streams = []
         self._prepare_weights(state_dict)
 
     def __del__(self):
@@ -270,7 +275,7 @@ class CareEngine:
         stale = [k for k, e in self._ws_epoch_of.items() if e < self._epoch]
         if not stale:
             return
-        self._graphs.clear()   # graphs hold raw pointers into the workspaces
+        (getattr(self, "_owner", None) or self)._graphs.clear()   # graphs hold raw pointers into the workspaces
         for k in stale:
             t = self._ws.pop(k)
             self._ws_bytes -= t.numel() * t.element_size()
@@ -281,6 +286,8 @@ class CareEngine:
         self._ws.clear()
         self._ws_epoch_of.clear()
         self._ws_bytes = 0
+        for t in self._twins:
+            t.free_workspaces()
 
     def copy_stream(self):
         """Side stream for host->device feature copies that overlap the decode."""
@@ -290,7 +297,8 @@ class CareEngine:
 
     def launch_count(self):
         """Kernels launched so far: eager launches counted by the library + launches replayed by graphs."""
-        return int(self.lib.care_ctx_launch_count(self.ctx)) + self._graph_launches
+        eager = sum(int(self.lib.care_ctx_launch_count(e.ctx)) for e in [self] + self._twins)
+        return eager + self._graph_launches
 
     def gemm(self, A, W, bias, C, M, N, K, act=ACT_NONE, lda=None, ldc=None, dt=None):
         out_dt = F32 if C.dtype == torch.float32 else self.dt
@@ -616,66 +624,125 @@ class CareEngine:
                                      ptr(out_score), ptr(out_t), st), "care_beam_finalize")
         return out_tok, out_len, out_score, out_t
 
+    def twin(self):
+        """A second engine over the SAME weights with its own library context and workspaces: lets two halves of a
+        small batch decode concurrently on two streams (see _ar_decode_graph)."""
+        t = object.__new__(CareEngine)
+        t.__dict__.update(self.__dict__)
+        handle = ctypes.c_void_p()
+        check(self.lib.care_ctx_create(ctypes.byref(handle), self.device.index), "care_ctx_create")
+        t.ctx = handle
+        check(self.lib.care_ctx_share_tuning(t.ctx, self.ctx), "care_ctx_share_tuning")
+        t._owner = self
+        if self.opt.get("care_self_compact") is not None:
+            check(self.lib.care_ctx_set_option(t.ctx, b"self_compact", int(self.opt["care_self_compact"])),
+                  "care_ctx_set_option")
+        t._ws, t._ws_epoch_of, t._ws_bytes = {}, {}, 0
+        t._graphs, t._graph_launches, t._twins, t._nseg = {}, 0, [], {}
+        t._copy_stream = None
+        return t
+
+    def _lanes_for(self, B, K):
+        """Concurrent lanes of a graph-replayed decode: independent slices of the batch on separate streams (option
+        care_graph_lanes, default 1).  Measured on B200 (round 2, cfg4): 512 videos 9.35 ms with one lane, 9.84 / 11.2 /
+        11.4 ms with 2 / 3 / 4; 256 videos 7.07 -> 7.84 ms; 64 videos unchanged - the persistent GEMM / vocabulary
+        kernels of one lane already occupy every SM, so lanes serialise and only add their fixed costs.  Kept as an
+        A/B switch."""
+        return max(1, min(self.graph_lanes, B))
+
     def _ar_decode_graph(self, enc, B, K, topk, beam_alpha, bos=BOS):
         """The whole decode (cross K/V projection, beam init, max_len-1 steps, finalisation) as ONE CUDA
         graph per (B, K, topk, alpha): a fixed launch sequence over fixed workspaces with no host
         sync inside, so small batches are not bound by per-launch host overhead.  Inputs are copied
-        into static buffers, outputs are cloned out of them."""
-        lib, ctx = self.lib, self.ctx
+        into static buffers, outputs are cloned out of them.  Larger graph batches run as concurrent lanes
+        (_lanes_for): videos are independent, so every lane is a complete decode of its slice of the batch."""
         Tm = self.max_len - 1
         need = max(K, topk)
-        mem_in = enc["encoder_hidden_states"]
-        gsg_in = enc.get("semantic_hidden_states") if self.use_gsg else None
-        memory = self._buf("g_memory", (B, self.Lm, self.d), self.tdtype)
-        gsg = self._buf("g_gsg", (B, self.d), torch.float32) if gsg_in is not None else None
-        outs = (self._buf("g_out_tok", (B, topk, Tm), torch.int32), self._buf("g_out_len", (B, topk), torch.int32),
-                self._buf("g_out_score", (B, topk), torch.float32), self._buf("g_out_t", (B, topk), torch.int32))
-        memory.copy_(mem_in)
-        if gsg is not None:
-            gsg.copy_(gsg_in)
-        static_enc = {"encoder_hidden_states": memory, "semantic_hidden_states": gsg}
-        if self.attr_pos is not None:
-            sem = self._buf("g_sem", (B, self.n_concepts, self.d), self.tdtype)
-            sem.copy_(enc["semantic_embs"])
-            static_enc["semantic_embs"] = sem
+        n_lanes = self._lanes_for(B, K)
+        while len(self._twins) < n_lanes - 1:
+            self._twins.append(self.twin())
+        engines = [self] + self._twins[:n_lanes - 1]
+        bounds = [(i * B // n_lanes, (i + 1) * B // n_lanes) for i in range(n_lanes)]
+        if n_lanes > 1 and len(self._lane_streams) < n_lanes - 1:
+            self._lane_streams += [torch.cuda.Stream(self.device) for _ in range(n_lanes - 1 - len(self._lane_streams))]
+        lanes = []
+        for eng, (lo, hi) in zip(engines, bounds):
+            n = hi - lo
+            eng._epoch = self._epoch
+            memory = eng._buf("g_memory", (n, self.Lm, self.d), self.tdtype)
+            memory.copy_(enc["encoder_hidden_states"][lo:hi])
+            static_enc = {"encoder_hidden_states": memory, "semantic_hidden_states": None}
+            if self.use_gsg and enc.get("semantic_hidden_states") is not None:
+                gsg = eng._buf("g_gsg", (n, self.d), torch.float32)
+                gsg.copy_(enc["semantic_hidden_states"][lo:hi])
+                static_enc["semantic_hidden_states"] = gsg
+            if self.attr_pos is not None:
+                sem = eng._buf("g_sem", (n, self.n_concepts, self.d), self.tdtype)
+                sem.copy_(enc["semantic_embs"][lo:hi])
+                static_enc["semantic_embs"] = sem
+            outs = (eng._buf("g_out_tok", (n, topk, Tm), torch.int32), eng._buf("g_out_len", (n, topk), torch.int32),
+                    eng._buf("g_out_score", (n, topk), torch.float32), eng._buf("g_out_t", (n, topk), torch.int32))
+            lanes.append(dict(eng=eng, n=n, enc=static_enc, outs=outs))
 
         def body():
-            st = self._stream()
-            kv = self.cross_kv(memory, static=True)
-            akv = self.attr_kv(static_enc, static=True)
-            bufs, bst = self._beam_buffers(B, K, need)
-            check(lib.care_beam_init(ctx, ctypes.byref(bst), bos, st), "care_beam_init")
-            lib.care_ctx_set_early_exit(ctx, ptr(bufs["n_done"]), B)
+            # the current stream is the capturing stream while the graph is recorded: the lanes fork from it
+            main = torch.cuda.current_stream(self.device)
+            streams = [main] + self._lane_streams[:n_lanes - 1]
+            for side in streams[1:]:
+                side.wait_stream(main)
+            for lane, stream in zip(lanes, streams):
+                eng, n = lane["eng"], lane["n"]
+                with torch.cuda.stream(stream):
+                    lane["kv"] = eng.cross_kv(lane["enc"]["encoder_hidden_states"], static=True)
+                    lane["akv"] = eng.attr_kv(lane["enc"], static=True)
+                    lane["bufs"], lane["bst"] = eng._beam_buffers(n, K, need)
+                    check(eng.lib.care_beam_init(eng.ctx, ctypes.byref(lane["bst"]), bos, eng._stream()), "care_beam_init")
+                    eng.lib.care_ctx_set_early_exit(eng.ctx, ptr(lane["bufs"]["n_done"]), n)
             try:
                 for t in range(1, self.max_len):
-                    self.decode_step(t, B, K, static_enc, kv, bufs, bst, akv=akv)
+                    for lane, stream in zip(lanes, streams):
+                        with torch.cuda.stream(stream):
+                            lane["eng"].decode_step(t, lane["n"], K, lane["enc"], lane["kv"], lane["bufs"], lane["bst"],
+                                                    akv=lane["akv"])
             finally:
-                lib.care_ctx_set_early_exit(ctx, None, 0)
-            check(lib.care_beam_finalize(ctx, ctypes.byref(bst), beam_alpha, topk, ptr(outs[0]), ptr(outs[1]),
-                                         ptr(outs[2]), ptr(outs[3]), st), "care_beam_finalize")
+                for lane in lanes:
+                    lane["eng"].lib.care_ctx_set_early_exit(lane["eng"].ctx, None, 0)
+            for lane, stream in zip(lanes, streams):
+                eng, outs = lane["eng"], lane["outs"]
+                with torch.cuda.stream(stream):
+                    check(eng.lib.care_beam_finalize(eng.ctx, ctypes.byref(lane["bst"]), beam_alpha, topk, ptr(outs[0]),
+                                                     ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), eng._stream()),
+                          "care_beam_finalize")
+            for side in streams[1:]:
+                main.wait_stream(side)
 
-        key = (B, K, topk, beam_alpha, bos)
+        def launches():
+            return sum(int(e.lib.care_ctx_launch_count(e.ctx)) for e in engines)
+
+        key = (B, K, topk, beam_alpha, bos, n_lanes)
         entry = self._graphs.get(key)
         if entry is None:
-            before = int(lib.care_ctx_launch_count(ctx))
+            before = launches()
             body()          # eager pass: allocates every workspace, encodes the TMA descriptors, sets attributes
-            n_launch = int(lib.care_ctx_launch_count(ctx)) - before
-            torch.cuda.current_stream(self.device).synchronize()
+            n_launch = launches() - before
+            torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 body()
             # the workspaces the captured launches point into: kept fresh on every replay (see _buf)
-            used = [k for k, e in self._ws_epoch_of.items() if e == self._epoch]
+            used = [[k for k, e in eng._ws_epoch_of.items() if e == self._epoch] for eng in engines]
             self._graphs[key] = (graph, n_launch, used)
             self._graph_launches -= n_launch   # the capture pass went through the library's counter without running
             # the eager pass already produced this call's result
         else:
-            for k in entry[2]:
-                self._ws_epoch_of[k] = self._epoch
+            for eng, keys in zip(engines, entry[2]):
+                for k in keys:
+                    eng._ws_epoch_of[k] = self._epoch
             entry[0].replay()
             self._graph_launches += entry[1]
-        return tuple(o.clone() for o in outs)
-
+        if n_lanes == 1:
+            return tuple(o.clone() for o in lanes[0]["outs"])
+        return tuple(torch.cat([lane["outs"][j] for lane in lanes], dim=0) for j in range(4))
 
     # ------------------------------------------------------------------------------------------
     # full-sequence decoder pass (mask-predict passes and the stateless decoding_phase)

@@ -59,6 +59,10 @@ int care_ctx_sm_count(const care_ctx* ctx);
  * (care_gemm), "vocab" (care_vocab_beam_partials) or "self_attn" (care_self_attn_step); bench.py labels its
  * roofline records with it */
 const char* care_ctx_last_kernel(const care_ctx* ctx, const char* family);
+/* Makes `ctx` use `other`'s table of per-shape GEMM variant picks (and its gemm_2sm / gemm_bn settings): two
+ * contexts of one device that decode slices of the same batch on different streams then launch the same
+ * kernel variant for the same shape, so a video's result does not depend on the slice it fell into. */
+int care_ctx_share_tuning(care_ctx* ctx, care_ctx* other);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches claim) */
 int64_t care_ctx_launch_count(const care_ctx* ctx);
 /* Device-side early exit for a decode loop with no host polling: while `counter` is non-NULL every

@@ -46,6 +46,8 @@ CASES = [
     ("cfg3_trained", "cfg3", {}, 16, dict(seed=33, perturb=True, sharpen=TRAINED)),
     ("cfg4_trained", "cfg4", {}, 16, dict(seed=31, perturb=True, sharpen=TRAINED)),
     ("cfg4_trained_512", "cfg4", {}, 512, dict(seed=31, perturb=True, sharpen=TRAINED), 21),
+    # the same population decoded greedily (beam 1): one decision per step instead of K+1 ranked candidates
+    ("cfg4_trained_512_greedy", "cfg4", dict(beam_size=1), 512, dict(seed=31, perturb=True, sharpen=TRAINED), 21),
 ]
 
 

@@ -7,7 +7,7 @@ reports, against the unrounded fp32 oracle on the same weights and features:
     (the prefixes are the fp32 oracle's own, so errors do not compound through diverging beams);
   * how many captions of a free-running beam search stay identical.
 
-    python -m tests.bf16_budget [cfg4] [n_videos] [preset]
+    python -m tests.bf16_budget [cfg4] [n_videos] [preset] [w_mode] [sites | fine | designs | fp16sites]
 
 Sites
   w      GEMM weight matrices (every nn.Linear weight; embeddings / LayerNorm / biases stay fp32)
@@ -49,8 +49,10 @@ class Emu:
     """Last-position decoder step over the whole prefix with rounding hooks (same math as
     oracle.care_oracle.decoder_hidden restricted to the newest position; CARE / Base tasks)."""
 
-    def __init__(self, sd, opt, sites):
+    def __init__(self, sd, opt, sites, wfmt=None, wskip=()):
         # sites: iterable of site names (bf16) or {site: format} with format in bf16 / fp16 / b2
+        # wfmt / wskip: round the DECODER-side weight matrices to `wfmt` except those whose name contains an entry of
+        # wskip (the encoder / predictor weights stay fp32: the engine multiplies them as split products)
         self.opt = opt
         self.sites = dict(sites) if isinstance(sites, dict) else {s: "bf16" for s in sites}
         self.sd = dict(sd)
@@ -58,6 +60,11 @@ class Emu:
             for k, v in sd.items():
                 if v.dim() == 2 and "embeddings" not in k and "hybrid_bias" not in k:
                     self.sd[k] = r16(v)
+        if wfmt:
+            for k, v in sd.items():
+                if v.dim() == 2 and "embeddings" not in k and "hybrid_bias" not in k and \
+                        not any(x in k for x in tuple(wskip) + ("encoder", "predictor")):
+                    self.sd[k] = r16(v, wfmt)
 
     GROUPS = {"x0": "x", "x1": "x", "x2": "x", "x3": "x", "x0op": "xop", "x1op": "xop", "x2op": "xop", "x3op": "xop",
               "q": "cache", "k": "cache", "v": "cache", "ck": "ckv", "cv": "ckv", "ps": "attn", "cs": "attn",
@@ -257,6 +264,32 @@ def main():
         ]
         if w_mode == "fp32":
             variants = [dict(v, w="bf16") for v in variants]
+    if which == "fp16sites":   # round 2: where the fp16 mode's error comes from, one site at a time
+        dec16 = {s_: "fp16" for s_ in ("mem", "x", "cache", "ckv", "attn", "ffn")}
+        named = [
+            ("decoder weights fp16", {}, "fp16", ()),
+            ("decoder weights fp16 except vocabulary", {}, "fp16", ("tgt_word_prj",)),
+            ("vocabulary weights fp16 only", {}, "fp16", ("decoder",)),
+            ("all activations fp16, weights fp32", dec16, None, ()),
+            ("x3 operand (vocabulary GEMM input)", {"x3op": "fp16"}, None, ()),
+            ("x0..x2 operands (QKV / cross-Q / FFN1 inputs)", {"x0op": "fp16", "x1op": "fp16", "x2op": "fp16"}, None, ()),
+            ("residual stream x0..x3 (operand + residual)", {"x": "fp16"}, None, ()),
+            ("KV cache q / k / v", {"cache": "fp16"}, None, ()),
+            ("cross K / V", {"ckv": "fp16"}, None, ()),
+            ("attention probabilities / contexts / cross-Q", {"attn": "fp16"}, None, ()),
+            ("FFN hidden", {"ffn": "fp16"}, None, ()),
+            ("encoder memory", {"mem": "fp16"}, None, ()),
+            ("ALL (the fp16 mode)", dec16, "fp16", ()),
+            ("ALL, vocabulary GEMM exact", {k: v for k, v in dict(dec16, x0="fp16", x1="fp16", x2="fp16").items() if k != "x"},
+             "fp16", ("tgt_word_prj",)),
+        ]
+        print("%-56s %10s %10s %10s %12s" % ("rounded to fp16", "logit rel", "lp scaled", "lp abs", "exact match"))
+        for name, sites, wfmt, wskip in named:
+            e = teacher_forced_errors(ref, Emu(sd, opt, sites, wfmt, wskip), tf_steps, feats)
+            h, _ = beam_search(Emu(sd, opt, sites, wfmt, wskip), opt, feats)
+            same = sum(int(a == b) for a, b in zip(h, ref_h))
+            print("%-56s %10.2e %10.2e %10.2e %8d/%d" % (name, e[0], e[1], e[2], same, n), flush=True)
+        return
     print("%-56s %10s %10s %10s %12s" % ("sites rounded", "logit rel", "lp scaled", "lp abs", "exact match"))
     for sites in variants:
         e = teacher_forced_errors(ref, Emu(sd, opt, sites), tf_steps, feats)

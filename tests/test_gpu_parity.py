@@ -194,8 +194,9 @@ def test_h16_sequences(name, precision):
             assert abs(scores[v][0] - rec["scores"][v][0]) < 0.05 * max(1.0, abs(rec["scores"][v][0]))
 
 
+@pytest.mark.parametrize("population", ["cfg4_trained_512", "cfg4_trained_512_greedy"])
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
-def test_h16_exact_match_512(precision):
+def test_h16_exact_match_512(precision, population):
     """The north-star population: VATEX-large shape (cfg4), beam 5, 512 videos, trained-like peaked weights
     (oracle/weights.py TRAINED), 16-bit mode against the hypotheses of the UNMODIFIED reference run on the CPU in
     fp32 (tests/golden/cfg4_trained_512.json).  Writes the exact-match rate per oracle-margin bucket to
@@ -203,7 +204,8 @@ def test_h16_exact_match_512(precision):
     the 16-bit rate is asserted at its measured level - see DESIGN.md section 5 for the error budget behind it."""
     import json
     import care_b200
-    rec = load_golden("cfg4_trained_512")
+    rec = load_golden(population)
+    greedy = population.endswith("greedy")
     opt, sd, feats = rebuild_case(rec)
     dev = [f.cuda() for f in feats]
     tr = care_b200.get_translator(opt)
@@ -233,14 +235,15 @@ def test_h16_exact_match_512(precision):
             lens = [len(h[0]) for h in rec["hyps"]]
             assert min(lens) <= 5 and max(lens) >= 25     # the population really spreads over short and long captions
             assert concept_same >= len(hyps) - 3          # split-product encoder: concept ranking as in fp32
-            floor = 0.95 if prec == "fp16" else 0.70
+            # measured (round 2, B200): beam 5 fp16 503/512 (98.2 %), bf16 440/512; greedy fp16 see profiles/
+            floor = (0.97 if greedy else 0.95) if prec == "fp16" else 0.70
             assert sum(same) >= floor * len(hyps), "%s exact-match %d/%d" % (prec, sum(same), len(hyps))
             # a mismatch may only happen where the reference's own decision margin is within the mode's noise
             noise = (1e-3 if prec == "fp16" else 1e-2) * 20.0 * 3
             assert all(same[v] or margins[v] < noise for v in range(len(hyps)))
         del model
     os.makedirs("gpurun_out", exist_ok=True)
-    with open(os.path.join("gpurun_out", "h16_exact_match_%s.json" % precision), "w") as f:
+    with open(os.path.join("gpurun_out", "h16_exact_match_%s%s.json" % (precision, "_greedy" if greedy else "")), "w") as f:
         json.dump(out, f, indent=1)
 
 
