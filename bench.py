@@ -509,7 +509,7 @@ def run_care_arm(args):
         per = [a.elapsed_time(b) for a, b in step_ms[Tm:]]     # first decode = warm-up
         step_lat = {"videos": B, "beam_rows": B * K, "samples": len(per), "mean_ms": sum(per) / len(per),
                     "p50_ms": percentile(per, 0.5), "p99_ms": percentile(per, 0.99), "max_ms": max(per),
-                    "note": "CUDA events around each of the %d beam steps (13 layer launches + fused vocabulary + "
+                    "note": "CUDA events around each of the %d beam steps (10-11 layer launches + fused vocabulary + "
                             "beam update) of the eager decode, 2 decodes after one warm-up" % Tm}
         if world == 1:
             for lb in (1, 64, 512):

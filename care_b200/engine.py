@@ -76,6 +76,7 @@ class CareEngine:
         self.fused_ln = int(default_ln if fl is None else fl) if (self.half and self.d in (512, 768, 1024)) else 0
         if self.fused_ln not in (0, 1, 2):
             raise ValueError("care_fused_ln must be 0, 1 or 2")
+        self.fused_ln_min_rows = int(opt.get("care_fused_ln_min_rows", 2048))
         self._ws = {}
         self._ws_epoch_of = {}
         self._ws_bytes = 0
@@ -306,12 +307,18 @@ class CareEngine:
                                  W.stride(0), ptr(bias), ptr(C), ldc if ldc is not None else C.stride(-2), out_dt,
                                  M, N, K, act, self._stream()), "care_gemm")
 
+    def _fused_for(self, M):
+        return self.fused_ln == 2 or (self.fused_ln == 1 and M >= self.fused_ln_min_rows)
+
     def _sublayer_tail(self, A, W, bias, gamma, beta, res, out, M, K, y32, res32=None, out32=None):
         """out = LayerNorm(A W^T + bias + res) (SubLayers.py:68-79,137-152): one cluster kernel in the 16-bit
         modes, care_gemm -> fp32 y32 -> care_add_ln otherwise.  res32 / out32: the fp32 residual stream
         (care_fused_ln = 2)."""
         d = self.d
-        if self.fused_ln:
+        # the cluster kernel needs a couple of thousand rows to fill the SMs (128-row blocks x d/256 CTAs): below
+        # that the unfused pair with its narrower tiles (or the weight-streaming kernel for a handful of rows) is
+        # faster (measured: 64 videos 5.68 vs 5.89 ms, one video 3.7 vs 4.3 ms per caption)
+        if self._fused_for(M):
             r32 = self.fused_ln == 2
             check(self.lib.care_gemm_add_ln(self.ctx, ptr(A), A.stride(-2), ptr(W), W.stride(0), ptr(bias),
                                             ptr(res32 if r32 else res), F32 if r32 else self.dt, ptr(gamma), ptr(beta),
@@ -472,7 +479,7 @@ class CareEngine:
         st = self._stream()
         R = B * K
         qa = self._buf("qa", (R, d), T); cxa = self._buf("ctx_a", (R, d), T)
-        y32 = None if self.fused_ln else self._buf("y32", (R, d), torch.float32)
+        y32 = None if self._fused_for(R) else self._buf("y32", (R, d), torch.float32)
         self.gemm(x_in, w["Waq"], w["baq"], qa, R, d, d)
         check(lib.care_cross_attn_step(ctx, dt, ptr(qa), d, ptr(akv), akv.shape[1], B, K, self.H, d, None, done,
                                        ptr(cxa), st), "care_cross_attn_step(attr)")
@@ -503,7 +510,7 @@ class CareEngine:
         return bufs, st
 
     def step_hidden(self, t, B, K, enc, kv, bufs, akv=None):
-        """Decoder layer for the newest position of every beam row (13 launches); returns the hidden states
+        """Decoder layer for the newest position of every beam row (10 launches with the fused residual LayerNorm, 13 without); returns the hidden states
         [R, d] the vocabulary projection consumes.  `bufs` holds the shared beam state (tokens, ancestry)."""
         lib, ctx, dt, w, d, T = self.lib, self.ctx, self.dt, self.w, self.d, self.tdtype
         st = self._stream()
@@ -513,7 +520,7 @@ class CareEngine:
         x0 = self._buf("x0", (R, d), T); x1 = self._buf("x1", (R, d), T)
         x2 = self._buf("x2", (R, d), T); x3 = self._buf("x3", (R, d), T)
         cx = self._buf("ctx", (R, d), T); qc = self._buf("qc", (R, d), T)
-        y32 = None if self.fused_ln else self._buf("y32", (R, d), torch.float32)
+        y32 = None if self._fused_for(R) else self._buf("y32", (R, d), torch.float32)
         hb = self._buf("ffn_h", (R, self.F), T)
         # fp32 residual stream (care_fused_ln = 2): r0..r3 next to the 16-bit GEMM operands x0..x3
         r0 = r1 = r2 = r3 = ra = None
@@ -557,7 +564,7 @@ class CareEngine:
         return x3
 
     def decode_step(self, t, B, K, enc, kv, bufs, bst, audit=None, want_logits=False, akv=None):
-        """One beam step (len_input_ids == t) for every video; 14 kernel launches (15 unfused)."""
+        """One beam step (len_input_ids == t) for every video; 12 kernel launches from 2048 beam rows up (fused residual LayerNorm + fused vocabulary), 15 for small batches."""
         lib, ctx, w, d = self.lib, self.ctx, self.w, self.d
         st = self._stream()
         R = B * K
@@ -751,7 +758,7 @@ class CareEngine:
         lib, ctx, dt, w, d, T = self.lib, self.ctx, self.dt, self.w, self.d, self.tdtype
         st = self._stream()
         qa = self._buf("sq_qa", (N, d), T); cxa = self._buf("sq_ctx_a", (N, d), T)
-        y32 = None if self.fused_ln else self._buf("sq_y32", (N, d), torch.float32)
+        y32 = None if self._fused_for(N) else self._buf("sq_y32", (N, d), torch.float32)
         self.gemm(x_in, w["Waq"], w["baq"], qa, N, d, d)
         check(lib.care_group_attn(ctx, dt, ptr(qa), d, ptr(akv), 2 * d, 0, d, n_videos, rpv, akv.shape[1], self.H, d,
                                   None, 0, None, ptr(cxa), st), "care_group_attn(attr)")
@@ -769,7 +776,7 @@ class CareEngine:
         x2 = self._buf("sq_x2", (N, d), T); x3 = self._buf("sq_x3", (N, d), T)
         cx = self._buf("sq_ctx", (N, d), T); qc = self._buf("sq_qc", (N, d), T)
         qkv = self._buf("sq_qkv", (N, 3 * d), T)
-        y32 = None if self.fused_ln else self._buf("sq_y32", (N, d), torch.float32)
+        y32 = None if self._fused_for(N) else self._buf("sq_y32", (N, d), torch.float32)
         hb = self._buf("sq_ffn", (N, self.F), T)
         r0 = r1 = r2 = r3 = ra = None
         if self.fused_ln == 2:
