@@ -111,6 +111,7 @@ int care_ctx_create(care_ctx** out, int device) {
   // one-time timing (timings taken under a profiler are not representative); CARE_B200_DEBUG=1 logs the choices
   if (const char* e = getenv("CARE_B200_GEMM_2SM")) c->gemm_2sm = atoi(e);
   if (const char* e = getenv("CARE_B200_DEBUG")) c->debug = atoi(e);
+  if (const char* e = getenv("CARE_B200_PDL")) c->pdl = atoi(e) != 0;
   if (const char* path = getenv("CARE_B200_GEMM_CHOICE_FILE")) {   // GEMM variants picked by an earlier run
     if (FILE* f = fopen(path, "r")) {
       unsigned long long key;
@@ -200,6 +201,10 @@ int care_ctx_set_option(care_ctx* ctx, const char* name, int value) {
   }
   if (strcmp(name, "gemm_smallm") == 0) {
     ctx->gemm_smallm = value;
+    return 0;
+  }
+  if (strcmp(name, "pdl") == 0) {
+    ctx->pdl = value != 0;
     return 0;
   }
   if (strcmp(name, "gemm_2sm") == 0) {

@@ -206,6 +206,8 @@ __device__ __forceinline__ void attend(const Params& p, int v, int h, int warp, 
 template <int KKW, bool SELF, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int v = blockIdx.x / p.H, h = blockIdx.x - v * p.H;
@@ -290,7 +292,7 @@ static int launch(care_ctx* ctx, const CUtensorMap& tmap, const Params& p, cudaS
     CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  kern<<<p.n_items, WARPS * 32, smem, stream>>>(tmap, p);
+  CARE_CUDA(launch_pdl(ctx, kern, dim3(p.n_items), dim3(WARPS * 32), smem, stream, tmap, p));
   if (SELF) ctx->last_self_attn = "attn_mma_kernel<self>";
   CARE_LAUNCH_CHECK(ctx);
   return 0;
@@ -319,6 +321,8 @@ __global__ void __launch_bounds__(128)
 compact_info_kernel(const uint8_t* __restrict__ anc, int anc_stride, const int32_t* __restrict__ tok_hist,
                     int tok_stride, const int32_t* __restrict__ done, int B, int K, int n_pos,
                     uint32_t* __restrict__ info) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ uint32_t rec_all[4][INFO_WORDS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int v = blockIdx.x * 4 + warp;
@@ -372,6 +376,8 @@ template <int KKW>
 __global__ void __launch_bounds__(128)
 attn_self_compact_kernel(const Params p, const h16* __restrict__ cache, int64_t R,
                          unsigned long long* __restrict__ row_counter, const uint32_t* __restrict__ info) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int WARPS = 4;
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -498,12 +504,13 @@ static int launch_compact(care_ctx* ctx, const Params& p, const void* cache, int
   const uint32_t* info = nullptr;
   if (ctx->compact_info != nullptr && p.n_items / p.H <= ctx->compact_info_videos) {
     const int B = p.n_items / p.H;
-    compact_info_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p.anc, p.anc_stride, p.tok_hist, p.tok_stride, p.done, B, p.K,
-                                                         p.n_pos, ctx->compact_info);
+    CARE_CUDA(launch_pdl(ctx, compact_info_kernel, dim3((B + 3) / 4), dim3(128), 0, stream, p.anc, p.anc_stride, p.tok_hist,
+                         p.tok_stride, p.done, B, p.K, p.n_pos, ctx->compact_info));
     CARE_LAUNCH_CHECK(ctx);
     info = ctx->compact_info;
   }
-  kern<<<p.n_items, 128, smem, stream>>>(p, static_cast<const h16*>(cache), R, ctx->self_attn_rows, info);
+  CARE_CUDA(launch_pdl(ctx, kern, dim3(p.n_items), dim3(128), smem, stream, p, static_cast<const h16*>(cache), R,
+                       ctx->self_attn_rows, info));
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -559,6 +566,8 @@ template <int STAGES>
 __global__ void __launch_bounds__(WARPS * 32, 4)
 attn_self_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Params p, int R, const uint32_t* __restrict__ info,
                         unsigned long long* __restrict__ row_counter, const EarlyExit ee) {
+  pdl_wait();
+  pdl_launch_dependents();
   if (all_done(ee)) return;
   extern __shared__ uint8_t smem_raw[];
   using C = Cfg<STAGES>;
@@ -816,8 +825,8 @@ static int launch_stream_t(care_ctx* ctx, const CUtensorMap& tmap, const Params&
     ctas_per_sm = std::max(n, 1);
   }
   const int grid = std::min((p.n_items + WARPS - 1) / WARPS, ctx->sm_count * ctas_per_sm);
-  kern<<<grid, WARPS * 32, Cfg<STAGES>::SMEM_BYTES, stream>>>(tmap, p, (int)R, ctx->compact_info, ctx->self_attn_rows,
-                                                              early_exit_of(ctx));
+  CARE_CUDA(launch_pdl(ctx, kern, dim3(grid), dim3(WARPS * 32), Cfg<STAGES>::SMEM_BYTES, stream, tmap, p, (int)R,
+                       (const uint32_t*)ctx->compact_info, ctx->self_attn_rows, early_exit_of(ctx)));
   ctx->last_self_attn = "attn_self_stream_kernel";
   CARE_LAUNCH_CHECK(ctx);
   return 0;
@@ -831,8 +840,8 @@ static int launch_stream(care_ctx* ctx, const Params& p, const void* cache, int6
   const uint32_t box[2] = {(uint32_t)DH, 1u};
   int rc = get_tmap_bf16(ctx, cache, 2, gdim, gstr, box, &tmap);
   if (rc) return rc;
-  compact_info_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p.anc, p.anc_stride, p.tok_hist, p.tok_stride, p.done, B, p.K,
-                                                       p.n_pos, ctx->compact_info);
+  CARE_CUDA(launch_pdl(ctx, compact_info_kernel, dim3((B + 3) / 4), dim3(128), 0, stream, p.anc, p.anc_stride, p.tok_hist,
+                       p.tok_stride, p.done, B, p.K, p.n_pos, ctx->compact_info));
   CARE_LAUNCH_CHECK(ctx);
   static const int stages = [] {
     const char* e = getenv("CARE_B200_STREAM_STAGES");

@@ -293,6 +293,8 @@ template <int KB>
 __global__ void __launch_bounds__(UPD_WARPS * 32)
 beam_update_kernel(const care_beam_state st, const SegLayout sl, int step, int max_len, float* __restrict__ cand_val,
                    int32_t* __restrict__ cand_idx) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ uint8_t old_anc_all[UPD_WARPS][8 * 64];
   __shared__ float fin_v_all[UPD_WARPS][KB];
   __shared__ int fin_i_all[UPD_WARPS][KB];
@@ -696,10 +698,14 @@ int care_beam_step_partials(care_ctx* ctx, const care_beam_state* st, const floa
   sl.nseg = nseg;
   vb::seg_layout(ctx, st->B * K, st->V, &sl.n_tiles, &sl.T, &sl.G, &sl.row_shift);
   const int ugrid = (st->B + beam::UPD_WARPS - 1) / beam::UPD_WARPS, uthreads = beam::UPD_WARPS * 32;
-  if (K <= 1) beam::beam_update_kernel<2><<<ugrid, uthreads, 0, s>>>(*st, sl, step, max_len, cand_val, cand_idx);
-  else if (K <= 3) beam::beam_update_kernel<4><<<ugrid, uthreads, 0, s>>>(*st, sl, step, max_len, cand_val, cand_idx);
-  else if (K <= 5) beam::beam_update_kernel<6><<<ugrid, uthreads, 0, s>>>(*st, sl, step, max_len, cand_val, cand_idx);
-  else beam::beam_update_kernel<9><<<ugrid, uthreads, 0, s>>>(*st, sl, step, max_len, cand_val, cand_idx);
+  if (K <= 1)
+    CARE_CUDA(launch_pdl(ctx, beam::beam_update_kernel<2>, dim3(ugrid), dim3(uthreads), 0, s, *st, sl, step, max_len, cand_val, cand_idx));
+  else if (K <= 3)
+    CARE_CUDA(launch_pdl(ctx, beam::beam_update_kernel<4>, dim3(ugrid), dim3(uthreads), 0, s, *st, sl, step, max_len, cand_val, cand_idx));
+  else if (K <= 5)
+    CARE_CUDA(launch_pdl(ctx, beam::beam_update_kernel<6>, dim3(ugrid), dim3(uthreads), 0, s, *st, sl, step, max_len, cand_val, cand_idx));
+  else
+    CARE_CUDA(launch_pdl(ctx, beam::beam_update_kernel<9>, dim3(ugrid), dim3(uthreads), 0, s, *st, sl, step, max_len, cand_val, cand_idx));
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

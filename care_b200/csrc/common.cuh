@@ -11,6 +11,7 @@
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <utility>
 
 #include "../../include/care_b200.h"
 
@@ -131,6 +132,10 @@ struct care_ctx {
   const char* last_self_attn = "";
   int gemm_bn = 0;   // > 0: force this tile width in the single-CTA GEMM (A/B runs)
   int debug = 0;
+  // programmatic dependent launch for the kernels of a decode step: kernel N+1 is scheduled while kernel N drains,
+  // runs its prologue (barrier init, TMEM allocation, descriptor prefetch) and blocks in griddepcontrol.wait
+  // until N has completed and flushed (option "pdl", env CARE_B200_PDL)
+  int pdl = 1;
   int vocab_2sm = 1;   // fused vocabulary kernel on CTA pairs when the shape has >= two waves of pair tiles
   // per-shape GEMM variant picks; contexts that must launch identical kernels (the lanes of one decode) share one
   // table (care_ctx_share_tuning)
@@ -161,9 +166,32 @@ inline EarlyExit early_exit_of(const care_ctx* ctx) { return EarlyExit{ctx->skip
 int get_tmap_bf16(care_ctx* ctx, const void* ptr, int rank, const uint64_t* gdim, const uint64_t* gstride_bytes,
                   const uint32_t* box, CUtensorMap* out);
 
+// Launch through cudaLaunchKernelEx, with the programmatic-stream-serialization attribute when ctx->pdl is set.
+// Every kernel launched through this helper executes pdl_wait() before it touches global memory that an earlier
+// kernel of the stream produces or still reads, and pdl_launch_dependents() only AFTER its own pdl_wait(): a
+// kernel that has started therefore implies that everything before its immediate predecessor has completed.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(const care_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ctx->pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool all_done(const EarlyExit& e) {
   return e.counter != nullptr && *reinterpret_cast<const volatile int32_t*>(e.counter) >= e.target;
 }

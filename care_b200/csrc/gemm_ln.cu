@@ -194,6 +194,8 @@ gemm_add_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();   // prologue (and the LayerNorm parameters: weights) done under the previous kernel's tail
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -404,16 +406,18 @@ static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, c
     configured_all[ctx->device & 63] = true;
   }
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)cn;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.blockDim = dim3(THREADS, 1, 1);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = stream;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = ctx->pdl ? 2 : 1;
   int& max_clusters = max_clusters_all[ctx->device & 63][cn];
   if (max_clusters == 0) {
     cfg.gridDim = dim3((unsigned)(cn * (ctx->sm_count / cn)), 1, 1);

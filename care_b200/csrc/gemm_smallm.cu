@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(WARPS * 32)
 gemm_smallm_kernel(const h16* __restrict__ A, int64_t lda, const h16* __restrict__ W, int64_t ldw,
                    const float* __restrict__ bias, OutT* __restrict__ C, int64_t ldc, int M, int N, int n_store, int K,
                    int relu, const EarlyExit ee) {
+  pdl_wait();
+  pdl_launch_dependents();
   if (all_done(ee)) return;
   __shared__ float red[WARPS][16][COLS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -74,13 +76,13 @@ int gemm_bf16_smallm(care_ctx* ctx, const void* A, int64_t lda, const void* W, i
   const int grid = (n_store + COLS - 1) / COLS;
   const int relu = act == CARE_ACT_RELU ? 1 : 0;
   if (out_dtype == CARE_F32)
-    gemm_smallm_kernel<float><<<grid, WARPS * 32, 0, stream>>>(
-        static_cast<const h16*>(A), lda, static_cast<const h16*>(W), ldw, bias,
-        static_cast<float*>(C), ldc, M, N, n_store, K, relu, early_exit_of(ctx));
+    CARE_CUDA(launch_pdl(ctx, gemm_smallm_kernel<float>, dim3(grid), dim3(WARPS * 32), 0, stream, static_cast<const h16*>(A),
+                         lda, static_cast<const h16*>(W), ldw, bias, static_cast<float*>(C), ldc, M, N, n_store, K, relu,
+                         early_exit_of(ctx)));
   else
-    gemm_smallm_kernel<h16><<<grid, WARPS * 32, 0, stream>>>(
-        static_cast<const h16*>(A), lda, static_cast<const h16*>(W), ldw, bias,
-        static_cast<h16*>(C), ldc, M, N, n_store, K, relu, early_exit_of(ctx));
+    CARE_CUDA(launch_pdl(ctx, gemm_smallm_kernel<h16>, dim3(grid), dim3(WARPS * 32), 0, stream, static_cast<const h16*>(A),
+                         lda, static_cast<const h16*>(W), ldw, bias, static_cast<h16*>(C), ldc, M, N, n_store, K, relu,
+                         early_exit_of(ctx)));
   ctx->last_gemm = "gemm_smallm_kernel";
   CARE_LAUNCH_CHECK(ctx);
   return 0;

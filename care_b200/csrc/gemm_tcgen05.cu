@@ -100,6 +100,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // everything above overlapped the previous kernel's tail (programmatic dependent launch); its outputs - this
+  // kernel's A operand - are complete and visible only from here on
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -269,8 +273,8 @@ static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, c
   }
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + BN - 1) / BN;
   const int grid = std::min(m_tiles * n_tiles, ctx->sm_count);
-  kern<<<grid, GEMM_THREADS, gemm_smem_bytes<BN>(), stream>>>(ta, tb, bias, reinterpret_cast<OutT*>(C), ldc, M, N, n_store, K,
-                                                       act == CARE_ACT_RELU ? 1 : 0, early_exit_of(ctx));
+  CARE_CUDA(launch_pdl(ctx, kern, dim3(grid), dim3(GEMM_THREADS), gemm_smem_bytes<BN>(), stream, ta, tb, bias,
+                       reinterpret_cast<OutT*>(C), ldc, M, N, n_store, K, act == CARE_ACT_RELU ? 1 : 0, early_exit_of(ctx)));
   ctx->last_gemm = sizeof(OutT) == 4 ? "gemm_bf16_tcgen05_kernel<float>" : "gemm_bf16_tcgen05_kernel<h16>";
   CARE_LAUNCH_CHECK(ctx);
   return 0;

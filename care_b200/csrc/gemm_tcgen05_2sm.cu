@@ -124,6 +124,8 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   cluster_sync_all();   // barriers of both CTAs initialised, TMEM allocated in both
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();   // prologue done under the previous kernel's tail; its outputs are visible from here on
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -274,8 +276,8 @@ static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, c
   }
   const int tiles = ((M + PAIR_M - 1) / PAIR_M) * ((N + BN - 1) / BN);
   const int n_clusters = std::min(tiles, ctx->sm_count / 2);
-  kern<<<2 * n_clusters, THREADS, SMEM_BYTES, stream>>>(ta, tb, bias, reinterpret_cast<OutT*>(C), ldc, M, N, n_store, K,
-                                                        act == CARE_ACT_RELU ? 1 : 0, early_exit_of(ctx));
+  CARE_CUDA(launch_pdl(ctx, kern, dim3(2 * n_clusters), dim3(THREADS), SMEM_BYTES, stream, ta, tb, bias,
+                       reinterpret_cast<OutT*>(C), ldc, M, N, n_store, K, act == CARE_ACT_RELU ? 1 : 0, early_exit_of(ctx)));
   ctx->last_gemm = sizeof(OutT) == 4 ? "gemm_bf16_2sm_kernel<float>" : "gemm_bf16_2sm_kernel<h16>";
   CARE_LAUNCH_CHECK(ctx);
   return 0;

@@ -164,6 +164,8 @@ embed_ln_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ 
                 const float* __restrict__ gsg, int rpv, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float eps, int R, int d, T* __restrict__ out,
                 float* __restrict__ out32, const EarlyExit ee) {
+  pdl_wait();   // first kernel of a step: the early-exit counter and the tokens come from the beam kernel just before
+  pdl_launch_dependents();
   if (all_done(ee)) return;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -206,6 +208,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 add_ln_kernel(const float* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
               const float* __restrict__ beta, float eps, int R, int d, T* __restrict__ out, const EarlyExit ee) {
+  pdl_wait();
+  pdl_launch_dependents();
   if (all_done(ee)) return;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -314,13 +318,13 @@ int care_embed_ln(care_ctx* ctx, int dtype, const int32_t* tokens, const int32_t
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = (R + 7) / 8;
   if (dtype == CARE_F32)
-    rw::embed_ln_kernel<float><<<grid, 256, 0, s>>>(tokens, positions, position, word_emb, pos_emb, add_feats, gsg,
-                                                    rows_per_video, gamma, beta, eps, R, d, (float*)out,
-                                                    out32, early_exit_of(ctx));
+    CARE_CUDA(launch_pdl(ctx, rw::embed_ln_kernel<float>, dim3(grid), dim3(256), 0, s, tokens, positions, position, word_emb,
+                         pos_emb, add_feats, gsg, rows_per_video, gamma, beta, eps, R, d, (float*)out, out32,
+                         early_exit_of(ctx)));
   else
-    rw::embed_ln_kernel<h16><<<grid, 256, 0, s>>>(tokens, positions, position, word_emb, pos_emb, add_feats,
-                                                            gsg, rows_per_video, gamma, beta, eps, R, d,
-                                                            (h16*)out, out32, early_exit_of(ctx));
+    CARE_CUDA(launch_pdl(ctx, rw::embed_ln_kernel<h16>, dim3(grid), dim3(256), 0, s, tokens, positions, position, word_emb,
+                         pos_emb, add_feats, gsg, rows_per_video, gamma, beta, eps, R, d, (h16*)out, out32,
+                         early_exit_of(ctx)));
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -333,11 +337,11 @@ int care_add_ln(care_ctx* ctx, int dtype, const float* x, const void* residual, 
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = (R + 7) / 8;
   if (dtype == CARE_F32)
-    rw::add_ln_kernel<float><<<grid, 256, 0, s>>>(x, (const float*)residual, gamma, beta, eps, R, d, (float*)out,
-                                                  early_exit_of(ctx));
+    CARE_CUDA(launch_pdl(ctx, rw::add_ln_kernel<float>, dim3(grid), dim3(256), 0, s, x, (const float*)residual, gamma, beta,
+                         eps, R, d, (float*)out, early_exit_of(ctx)));
   else
-    rw::add_ln_kernel<h16><<<grid, 256, 0, s>>>(x, (const h16*)residual, gamma, beta, eps, R, d,
-                                                          (h16*)out, early_exit_of(ctx));
+    CARE_CUDA(launch_pdl(ctx, rw::add_ln_kernel<h16>, dim3(grid), dim3(256), 0, s, x, (const h16*)residual, gamma, beta, eps,
+                         R, d, (h16*)out, early_exit_of(ctx)));
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -176,6 +176,8 @@ vocab_beam_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();   // prologue done under the previous kernel's tail; its outputs are visible from here on
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -367,6 +369,8 @@ vocab_beam_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -514,7 +518,8 @@ static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
       CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p2::SMEM_BYTES));
       configured = true;
     }
-    kern<<<2 * (int)l.G, VB_THREADS, p2::SMEM_BYTES, stream>>>(ta, tb, partials, nseg, R, V, d, early_exit_of(ctx));
+    CARE_CUDA(launch_pdl(ctx, kern, dim3(2 * (int)l.G), dim3(VB_THREADS), p2::SMEM_BYTES, stream, ta, tb, partials, nseg, R, V,
+                         d, early_exit_of(ctx)));
     ctx->last_vocab = "vocab_beam_2sm_kernel";
   } else {
     auto kern = vocab_beam_tcgen05_kernel<KB>;
@@ -522,7 +527,8 @@ static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
       CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
       configured = true;
     }
-    kern<<<(int)l.G, VB_THREADS, cfg::SMEM_BYTES, stream>>>(ta, tb, partials, nseg, R, V, d, early_exit_of(ctx));
+    CARE_CUDA(launch_pdl(ctx, kern, dim3((int)l.G), dim3(VB_THREADS), cfg::SMEM_BYTES, stream, ta, tb, partials, nseg, R, V, d,
+                         early_exit_of(ctx)));
     ctx->last_vocab = "vocab_beam_tcgen05_kernel";
   }
   CARE_LAUNCH_CHECK(ctx);
