@@ -87,6 +87,11 @@ class CareEngine:
         # launch-bound regime (few rows per step): replay the whole decode as one CUDA graph
         self.use_graphs = bool(opt.get("care_cuda_graph", True))
         self.graph_max_rows = int(opt.get("care_cuda_graph_max_rows", 6144))
+        # larger batches are graphed from the SECOND decode of the same shape on (a one-off shape is not worth a
+        # capture): the replay has no launch gaps and no host polling (the device-side early-exit flag replaces
+        # it) - 4096 videos: 56.2 -> 54.0 ms per batch
+        self.graph_max_rows_repeat = int(opt.get("care_cuda_graph_max_rows_repeat", 32768))
+        self._shapes_seen = {}
         self._graphs = {}
         self._graph_launches = 0
         # graph-replayed decodes may run as concurrent lanes on separate streams (A/B switch, see _lanes_for);
@@ -598,8 +603,12 @@ class CareEngine:
         need = max(K, topk)
         lib, ctx = self.lib, self.ctx
         bos = BOS if bos is None else int(bos)
-        if trace is None and self.use_graphs and B * K <= self.graph_max_rows:
-            return self._ar_decode_graph(enc, B, K, topk, float(beam_alpha), bos)
+        if trace is None and self.use_graphs:
+            shape = (B, K, topk, float(beam_alpha), bos)
+            seen = self._shapes_seen.get(shape, 0)
+            self._shapes_seen[shape] = seen + 1
+            if B * K <= self.graph_max_rows or (seen >= 1 and B * K <= self.graph_max_rows_repeat):
+                return self._ar_decode_graph(enc, B, K, topk, float(beam_alpha), bos)
         st = self._stream()
         kv = self.cross_kv(enc["encoder_hidden_states"])
         akv = self.attr_kv(enc)
