@@ -85,6 +85,8 @@ _SIGNATURES = {
                                          c_void_p, c_int, c_void_p]),
     "care_beam_step_partials": (c_int, [c_void_p, POINTER(BeamState), c_void_p, c_int, c_int, c_int, c_void_p,
                                         c_void_p, c_void_p]),
+    "care_beam_first_step_partials": (c_int, [c_void_p, POINTER(BeamState), c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                              c_void_p]),
     "care_ensemble_logprobs": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "care_beam_step_logprobs": (c_int, [c_void_p, POINTER(BeamState), c_void_p, c_int64, c_int, c_int, c_void_p,
                                         c_void_p, c_void_p]),

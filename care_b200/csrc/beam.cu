@@ -287,6 +287,7 @@ struct SegLayout {
   int nseg, n_tiles;
   int64_t T, G;
   int row_shift;   // log2(rows per row block of the kernel that wrote the records: 7 single-CTA, 8 CTA pair)
+  int rpv;         // record rows per video: K, or 1 for the compact first step (one <bos> row per video, record row v)
 };
 
 template <int KB>
@@ -313,12 +314,13 @@ beam_update_kernel(const care_beam_state st, const SegLayout sl, int step, int m
     const int max_slots = 2 * (int)((sl.n_tiles * sl.G + sl.T - 1) / sl.T + 1);   // upper bound of segments per row
     if (max_slots <= 8) {
       // large batches: a few segments per row -> one lane per row, no cross-lane traffic
-      if (lane < K) {
-        const int r = v * K + lane;
-        const int m_blk = r >> sl.row_shift;
+      if (lane < sl.rpv) {
+        const int r = v * K + lane;            // row of the beam state / merged record
+        const int rr = v * sl.rpv + lane;      // row of the vocabulary kernel's records
+        const int m_blk = rr >> sl.row_shift;
         const int c0 = (int)((((int64_t)m_blk * sl.n_tiles + 1) * sl.G - 1) / sl.T);
         const int c1 = (int)((((int64_t)m_blk * sl.n_tiles + sl.n_tiles) * sl.G - 1) / sl.T);
-        const float* base = sl.partials + (int64_t)r * sl.nseg * (2 + 2 * KB);
+        const float* base = sl.partials + (int64_t)rr * sl.nseg * (2 + 2 * KB);
         const int64_t mlo = (int64_t)m_blk * sl.n_tiles, mhi = mlo + sl.n_tiles;
         float M = -INFINITY, S = 0.f;
         TopList<KB> l;
@@ -353,12 +355,13 @@ beam_update_kernel(const care_beam_state st, const SegLayout sl, int step, int m
     } else {
       // small batches put every tile in its own run (~2 x n_tiles segments per row): the whole warp works on
       // one row at a time
-      for (int b = 0; b < K; ++b) {
+      for (int b = 0; b < sl.rpv; ++b) {
         const int r = v * K + b;
-        const int m_blk = r >> sl.row_shift;
+        const int rr = v * sl.rpv + b;
+        const int m_blk = rr >> sl.row_shift;
         const int c0 = (int)((((int64_t)m_blk * sl.n_tiles + 1) * sl.G - 1) / sl.T);
         const int c1 = (int)((((int64_t)m_blk * sl.n_tiles + sl.n_tiles) * sl.G - 1) / sl.T);
-        const float* base = sl.partials + (int64_t)r * sl.nseg * (2 + 2 * KB);
+        const float* base = sl.partials + (int64_t)rr * sl.nseg * (2 + 2 * KB);
         const int64_t mlo = (int64_t)m_blk * sl.n_tiles, mhi = mlo + sl.n_tiles;
         const int nslot = 2 * (c1 - c0 + 1);
         float M = -INFINITY, S = 0.f;
@@ -434,6 +437,9 @@ beam_update_kernel(const care_beam_state st, const SegLayout sl, int step, int m
   __syncwarp();
 
   // ancestry: new_anc[b'][p] = old_anc[parent(b')][p] for p < step-1, new_anc[b'][step-1] = parent(b')
+  // (a row of NaN logits leaves no candidate: fin_i stays INT_MAX - keep the indices inside the tables)
+  if (lane < nsel && (unsigned)fin_i[lane] >= (unsigned)(K * V)) fin_i[lane] = 0;
+  __syncwarp();
   for (int idx = lane; idx < K * T; idx += 32) {
     const int b = idx / T, pp = idx - b * T;
     const int parent = fin_i[b] / V;
@@ -613,6 +619,7 @@ static int check_state(const care_beam_state* st, const char* who) {
 
 namespace vb {  // vocab_beam.cu
 void seg_layout(const care_ctx* ctx, int R, int V, int* n_tiles, int64_t* T, int64_t* G, int* row_shift);
+int nseg_for(const care_ctx* ctx, int R, int V);
 }
 }  // namespace care
 
@@ -683,20 +690,22 @@ int care_ensemble_logprobs(care_ctx* ctx, const float* const* logits, int n, int
   return 0;
 }
 
-int care_beam_step_partials(care_ctx* ctx, const care_beam_state* st, const float* partials, int nseg, int step,
-                            int max_len, float* cand_val, int32_t* cand_idx, void* stream) {
-  CARE_CHECK_ARG(ctx && partials, "care_beam_step_partials: bad args");
-  if (beam::check_state(st, "care_beam_step_partials")) return -1;
-  CARE_CHECK_ARG(step >= 1 && step <= st->T_max, "care_beam_step_partials: step=%d outside [1,%d]", step, st->T_max);
-  CARE_CHECK_ARG((cand_val == nullptr) == (cand_idx == nullptr),
-                 "care_beam_step_partials: cand_val/cand_idx must go together");
-  CARE_CHECK_ARG(st->scratch != nullptr, "care_beam_step_partials: state.scratch is NULL");
+static int beam_step_partials_impl(care_ctx* ctx, const care_beam_state* st, const float* partials, int nseg, int step,
+                                   int max_len, int rpv, float* cand_val, int32_t* cand_idx, void* stream, const char* who) {
+  CARE_CHECK_ARG(ctx && partials && nseg >= 1, "%s: bad args", who);
+  if (beam::check_state(st, who)) return -1;
+  CARE_CHECK_ARG(step >= 1 && step <= st->T_max, "%s: step=%d outside [1,%d]", who, step, st->T_max);
+  CARE_CHECK_ARG((cand_val == nullptr) == (cand_idx == nullptr), "%s: cand_val/cand_idx must go together", who);
+  CARE_CHECK_ARG(st->scratch != nullptr, "%s: state.scratch is NULL", who);
   cudaStream_t s = (cudaStream_t)stream;
   const int K = st->K;
   beam::SegLayout sl{};
   sl.partials = partials;
   sl.nseg = nseg;
-  vb::seg_layout(ctx, st->B * K, st->V, &sl.n_tiles, &sl.T, &sl.G, &sl.row_shift);
+  sl.rpv = rpv;
+  vb::seg_layout(ctx, st->B * rpv, st->V, &sl.n_tiles, &sl.T, &sl.G, &sl.row_shift);
+  CARE_CHECK_ARG(nseg == vb::nseg_for(ctx, st->B * rpv, st->V), "%s: nseg=%d does not match the %d-row record table", who,
+                 nseg, st->B * rpv);
   const int ugrid = (st->B + beam::UPD_WARPS - 1) / beam::UPD_WARPS, uthreads = beam::UPD_WARPS * 32;
   if (K <= 1)
     CARE_CUDA(launch_pdl(ctx, beam::beam_update_kernel<2>, dim3(ugrid), dim3(uthreads), 0, s, *st, sl, step, max_len, cand_val, cand_idx));
@@ -708,6 +717,18 @@ int care_beam_step_partials(care_ctx* ctx, const care_beam_state* st, const floa
     CARE_CUDA(launch_pdl(ctx, beam::beam_update_kernel<9>, dim3(ugrid), dim3(uthreads), 0, s, *st, sl, step, max_len, cand_val, cand_idx));
   CARE_LAUNCH_CHECK(ctx);
   return 0;
+}
+
+int care_beam_step_partials(care_ctx* ctx, const care_beam_state* st, const float* partials, int nseg, int step,
+                            int max_len, float* cand_val, int32_t* cand_idx, void* stream) {
+  return beam_step_partials_impl(ctx, st, partials, nseg, step, max_len, st ? st->K : 1, cand_val, cand_idx, stream,
+                                 "care_beam_step_partials");
+}
+
+int care_beam_first_step_partials(care_ctx* ctx, const care_beam_state* st, const float* partials, int nseg, int max_len,
+                                  float* cand_val, int32_t* cand_idx, void* stream) {
+  return beam_step_partials_impl(ctx, st, partials, nseg, 1, max_len, 1, cand_val, cand_idx, stream,
+                                 "care_beam_first_step_partials");
 }
 
 int care_beam_finalize(care_ctx* ctx, const care_beam_state* st, double alpha, int n_best, int32_t* out_tokens,

@@ -99,6 +99,8 @@ class CareEngine:
         self.graph_lanes = int(opt.get("care_graph_lanes", os.environ.get("CARE_B200_GRAPH_LANES", "1")))
         self._twins = []
         self._lane_streams = []
+        # step 1 of the beam search on one row per video (all K beams hold <bos>; 16-bit fused path)
+        self.compact_first = bool(opt.get("care_compact_first_step", True))
         self._prepare_weights(state_dict)
 
     def __del__(self):
@@ -258,7 +260,7 @@ class CareEngine:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def _buf(self, name, shape, dtype):
+    def _buf(self, name, shape, dtype, zero=False):
         """Workspace keyed by (name, shape, dtype), kept across calls.  A service that sees many batch
         sizes would otherwise accumulate one workspace set per size: once the sets exceed
         `care_workspace_limit_bytes` (default: half of the device memory), the buffers the current
@@ -271,7 +273,7 @@ class CareEngine:
                 nbytes *= int(n)
             if self._ws_bytes + nbytes > self._ws_limit:
                 self._evict_stale()
-            t = torch.empty(shape, dtype=dtype, device=self.device)
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
             self._ws[key] = t
             self._ws_bytes += nbytes
         self._ws_epoch_of[key] = self._epoch
@@ -514,14 +516,26 @@ class CareEngine:
         st = BeamState(B=B, K=K, T_max=Tm, V=self.V, need=need, **{k: ptr(v) for k, v in bufs.items()})
         return bufs, st
 
-    def step_hidden(self, t, B, K, enc, kv, bufs, akv=None):
-        """Decoder layer for the newest position of every beam row (10 launches with the fused residual LayerNorm, 13 without); returns the hidden states
-        [R, d] the vocabulary projection consumes.  `bufs` holds the shared beam state (tokens, ancestry)."""
+    def step_hidden(self, t, B, K, enc, kv, bufs, akv=None, compact_first=False):
+        """Decoder layer for the newest position of every beam row (10 launches with the fused residual LayerNorm, 13
+        without); returns the hidden states [R, d] the vocabulary projection consumes.  `bufs` holds the shared beam
+        state (tokens, ancestry).
+        compact_first (t == 1 only): before the first step all K beams of a video hold <bos> and identical state, and
+        Beam.advance looks at beam 0 only (Beam.py:56): the layer runs on ONE row per video ([B, d] result).  Its
+        q|k|v land in cache slot 0 of position 0 - the only slot of that position any later step references, because
+        every beam chosen at step 1 descends from beam 0 - and its self-attention over the single <bos> key is the
+        value row itself (a softmax over one key is exactly 1)."""
         lib, ctx, dt, w, d, T = self.lib, self.ctx, self.dt, self.w, self.d, self.tdtype
         st = self._stream()
-        R = B * K
         Tm = self.max_len - 1
-        cache = self._buf("kv_cache", (Tm, R, 3 * d), T)
+        # zero-filled when first allocated: the compact first step writes slot 0 of position 0 only, and the dense
+        # self-attention tile loads every slot of a position (masked keys weigh exactly 0, but 0 x NaN garbage = NaN);
+        # afterwards the other slots hold finite values of an earlier decode at worst
+        cache = self._buf("kv_cache", (Tm, B * K, 3 * d), T, zero=True)
+        if compact_first:
+            assert t == 1
+            K_state, K = K, 1
+        R = B * K
         x0 = self._buf("x0", (R, d), T); x1 = self._buf("x1", (R, d), T)
         x2 = self._buf("x2", (R, d), T); x3 = self._buf("x3", (R, d), T)
         cx = self._buf("ctx", (R, d), T); qc = self._buf("qc", (R, d), T)
@@ -534,13 +548,24 @@ class CareEngine:
             r2 = self._buf("r2", (R, d), torch.float32); r3 = self._buf("r3", (R, d), torch.float32)
         gsg = enc.get("semantic_hidden_states")
         done = ptr(bufs["done"])
-        check(lib.care_embed_ln(ctx, dt, ptr(bufs["cur_tok"]), None, t - 1, ptr(w["word"]), ptr(w["pos"]), None,
-                                ptr(gsg), K, ptr(w["emb_g"]), ptr(w["emb_b"]), self.eps, R, d, ptr(x0), ptr(r0), st),
-              "care_embed_ln")
-        self.gemm(x0, w["Wqkv"], w["bqkv"], cache[t - 1], R, 3 * d, d)
-        check(lib.care_self_attn_step(ctx, dt, ptr(cache), t, B, K, self.H, d, ptr(bufs["anc"]), Tm,
-                                      ptr(bufs["tok_hist"]), done, ptr(cx), st), "care_self_attn_step")
-        self._sublayer_tail(cx, w["Wo"], w["bo"], w["ln1_g"], w["ln1_b"], x0, x1, R, d, y32, r0, r1)
+        if compact_first:
+            tok0 = self._buf("first_tok", (B,), torch.int32)
+            tok0.copy_(bufs["cur_tok"].view(B, K_state)[:, 0])
+            slot0 = cache[0].view(B, K_state, 3 * d)[:, 0, :]          # [B, 3d], row stride K * 3d
+            check(lib.care_embed_ln(ctx, dt, ptr(tok0), None, 0, ptr(w["word"]), ptr(w["pos"]), None, ptr(gsg), 1,
+                                    ptr(w["emb_g"]), ptr(w["emb_b"]), self.eps, R, d, ptr(x0), ptr(r0), st),
+                  "care_embed_ln")
+            self.gemm(x0, w["Wqkv"], w["bqkv"], slot0, R, 3 * d, d)
+            cx_in = slot0[:, 2 * d:]                                   # the value rows: attention over one key
+        else:
+            check(lib.care_embed_ln(ctx, dt, ptr(bufs["cur_tok"]), None, t - 1, ptr(w["word"]), ptr(w["pos"]), None,
+                                    ptr(gsg), K, ptr(w["emb_g"]), ptr(w["emb_b"]), self.eps, R, d, ptr(x0), ptr(r0), st),
+                  "care_embed_ln")
+            self.gemm(x0, w["Wqkv"], w["bqkv"], cache[t - 1], R, 3 * d, d)
+            check(lib.care_self_attn_step(ctx, dt, ptr(cache), t, B, K, self.H, d, ptr(bufs["anc"]), Tm,
+                                          ptr(bufs["tok_hist"]), done, ptr(cx), st), "care_self_attn_step")
+            cx_in = cx
+        self._sublayer_tail(cx_in, w["Wo"], w["bo"], w["ln1_g"], w["ln1_b"], x0, x1, R, d, y32, r0, r1)
         if self.attr_pos == "attr2cross":   # Layers.py:180-187
             xa = self._buf("xa", (R, d), T)
             ra = self._buf("ra", (R, d), torch.float32) if self.fused_ln == 2 else None
@@ -573,8 +598,21 @@ class CareEngine:
         lib, ctx, w, d = self.lib, self.ctx, self.w, self.d
         st = self._stream()
         R = B * K
-        x3 = self.step_hidden(t, B, K, enc, kv, bufs, akv)
         fused = self.fused_vocab and not want_logits
+        if t == 1 and fused and audit is None and K > 1 and self.compact_first:
+            # step 1 on one row per video (see step_hidden): the vocabulary kernel and the beam kernel take B rows
+            x3 = self.step_hidden(t, B, K, enc, kv, bufs, akv, compact_first=True)
+            nseg = self._nseg.get(B)
+            if nseg is None:
+                nseg = self._nseg[B] = int(lib.care_vocab_beam_nseg(ctx, B, self.V))
+            kb = 2 if K <= 1 else 4 if K <= 3 else 6 if K <= 5 else 9
+            part = self._buf("vocab_partials", (B, nseg, 2 + 2 * kb), torch.float32)
+            check(lib.care_vocab_beam_partials(ctx, ptr(x3), d, ptr(w["Wvocab"]), w["Wvocab"].stride(0), B, self.V, d,
+                                               K, ptr(part), nseg, st), "care_vocab_beam_partials")
+            check(lib.care_beam_first_step_partials(ctx, ctypes.byref(bst), ptr(part), nseg, self.max_len, None, None,
+                                                    st), "care_beam_first_step_partials")
+            return None
+        x3 = self.step_hidden(t, B, K, enc, kv, bufs, akv)
         logits = None if fused else self._buf("logits", (R, self.ldv), torch.float32)
         cv = ci = None
         if audit is not None:

@@ -301,6 +301,13 @@ int care_vocab_beam_partials(care_ctx* ctx, const void* x, int64_t ldx, const vo
                              int V, int d, int K, float* partials, int nseg, void* stream);
 int care_beam_step_partials(care_ctx* ctx, const care_beam_state* st, const float* partials, int nseg,
                             int step, int max_len, float* cand_val, int32_t* cand_idx, void* stream);
+/* The same for step 1 computed on ONE row per video: before the first step all K beams of a video hold <bos> and
+ * identical state, Beam.advance looks at beam 0 only (Beam.py:56), and every new beam's ancestor at position 0 is
+ * slot 0 - so the decoder layer and the vocabulary kernel need B rows, not B*K.  partials: the records of
+ * care_vocab_beam_partials run on those B rows (record row v = video v, nseg = care_vocab_beam_nseg(ctx, B, V)). */
+int care_beam_first_step_partials(care_ctx* ctx, const care_beam_state* st, const float* partials,
+                                  int nseg, int max_len, float* cand_val, int32_t* cand_idx,
+                                  void* stream);
 
 /* Hypothesis extraction (Translator.py:211-220, Beam.py:91-105,119-132): rank finished items by
  * score / t^alpha (double), stable, and back-walk the n_best first.  out_tokens int32

@@ -374,6 +374,35 @@ def test_model_ensemble_wrapper(tmp_path):
         assert abs(out["v%d" % i][0]["score"] - rec["scores"][i][0]) < 1e-4 * max(1.0, abs(rec["scores"][i][0]))
 
 
+def test_first_step_on_one_row_per_video_is_exact_and_ignores_stale_cache_memory():
+    """Step 1 runs on ONE row per video in the 16-bit fused path (all K beams hold <bos>; engine.step_hidden
+    compact_first): identical captions to the full-row first step, also when the KV-cache workspace is carved out of
+    memory full of NaN bit patterns (only slot 0 of position 0 is written; the dense self-attention tile loads every
+    slot of a position and 0 x NaN would poison the context)."""
+    import care_b200
+    rec = load_golden("cfg2_sharp")
+    opt, sd, feats = rebuild_case(rec)
+    dev = [f.cuda() for f in feats]
+    tr = care_b200.get_translator(opt)
+    full = _gpu_model(dict(opt, care_compact_first_step=False), sd, "fp16")
+    h_full, s_full = tr.translate_batch([full], {"feats": dev})
+    assert not full.engine().compact_first
+    del full
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    junk = [torch.full((32 << 20,), float("nan"), device="cuda", dtype=torch.float16) for _ in range(4)]
+    torch.cuda.synchronize()
+    del junk                                   # back to the caching allocator: the next engine's workspaces reuse it
+    compact = _gpu_model(opt, sd, "fp16")
+    h_c, s_c = tr.translate_batch([compact], {"feats": dev})
+    assert compact.engine().compact_first
+    assert h_c == h_full
+    for a, b in zip(s_c, s_full):
+        assert abs(a[0] - b[0]) < 2e-3 * max(1.0, abs(b[0]))     # one-row and K-row first steps take different GEMM tiles
+    h_again, _ = tr.translate_batch([compact], {"feats": dev})    # graph replay
+    assert h_again == h_c
+
+
 def test_no_gpu_no_fallback_message():
     from care_b200 import _lib
     assert os.path.isfile(_lib.LIB_PATH)
