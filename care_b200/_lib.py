@@ -25,6 +25,12 @@ class BeamState(Structure):
     ]
 
 
+class NextStep(Structure):
+    """Mirror of `care_next_step` (include/care_b200.h)."""
+    _fields_ = [("word_emb", c_void_p), ("pos_emb", c_void_p), ("gsg", c_void_p), ("gamma", c_void_p), ("beta", c_void_p),
+                ("eps", c_float), ("d", c_int32), ("x0", c_void_p), ("x0_f32", c_void_p)]
+
+
 _SIGNATURES = {
     "care_version": (c_int, []),
     "care_h16_dtype": (c_int, []),
@@ -33,6 +39,7 @@ _SIGNATURES = {
     "care_ctx_destroy": (None, [c_void_p]),
     "care_ctx_sm_count": (c_int, [c_void_p]),
     "care_ctx_share_tuning": (c_int, [c_void_p, c_void_p]),
+    "care_ctx_set_next_step": (c_int, [c_void_p, POINTER(NextStep)]),
     "care_ctx_launch_count": (c_int64, [c_void_p]),
     "care_ctx_last_kernel": (c_char_p, [c_void_p, c_char_p]),
     "care_ctx_set_early_exit": (c_int, [c_void_p, c_void_p, c_int]),

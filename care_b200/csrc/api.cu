@@ -112,6 +112,7 @@ int care_ctx_create(care_ctx** out, int device) {
   if (const char* e = getenv("CARE_B200_GEMM_2SM")) c->gemm_2sm = atoi(e);
   if (const char* e = getenv("CARE_B200_DEBUG")) c->debug = atoi(e);
   if (const char* e = getenv("CARE_B200_PDL")) c->pdl = atoi(e) != 0;
+  if (const char* e = getenv("CARE_B200_FUSE_INFO")) c->fuse_info = atoi(e) != 0;
   if (const char* path = getenv("CARE_B200_GEMM_CHOICE_FILE")) {   // GEMM variants picked by an earlier run
     if (FILE* f = fopen(path, "r")) {
       unsigned long long key;
@@ -158,6 +159,13 @@ const char* care_ctx_last_kernel(const care_ctx* ctx, const char* family) {
   return "";
 }
 
+int care_ctx_set_next_step(care_ctx* ctx, const care_next_step* next) {
+  CARE_CHECK_ARG(ctx != nullptr, "care_ctx_set_next_step: ctx is NULL");
+  ctx->next_armed = next != nullptr;
+  if (next != nullptr) ctx->next = *next;
+  return 0;
+}
+
 int care_ctx_share_tuning(care_ctx* ctx, care_ctx* other) {
   CARE_CHECK_ARG(ctx && other && ctx->device == other->device, "care_ctx_share_tuning: two contexts of one device");
   ctx->tuning = other->tuning;
@@ -201,6 +209,10 @@ int care_ctx_set_option(care_ctx* ctx, const char* name, int value) {
   }
   if (strcmp(name, "gemm_smallm") == 0) {
     ctx->gemm_smallm = value;
+    return 0;
+  }
+  if (strcmp(name, "fuse_info") == 0) {
+    ctx->fuse_info = value != 0;
     return 0;
   }
   if (strcmp(name, "pdl") == 0) {

@@ -9,7 +9,7 @@
 #include <cfloat>
 #include <climits>
 
-#include "common.cuh"
+#include "step_prologue.cuh"
 
 namespace care {
 namespace beam {
@@ -290,12 +290,31 @@ struct SegLayout {
   int rpv;         // record rows per video: K, or 1 for the compact first step (one <bos> row per video, record row v)
 };
 
+// Prologue of the NEXT decode step, run by the video's warp once its beams are chosen (both optional):
+//   x0 != NULL:   the decoder input rows of the K new tokens, LN(word[tok] + pos[step] + gsg[v]) - what embed_ln_kernel
+//                 would compute in a launch of its own at the start of step + 1;
+//   info != NULL: the live-slot record of the video for a prefix of step + 1 positions - what compact_info_kernel
+//                 would compute before the next self-attention.
+struct NextStep {
+  const float* word;
+  const float* pos;
+  const float* gsg;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int d;
+  h16* x0;
+  float* x0_32;
+  uint32_t* info;
+};
+
 template <int KB>
 __global__ void __launch_bounds__(UPD_WARPS * 32)
 beam_update_kernel(const care_beam_state st, const SegLayout sl, int step, int max_len, float* __restrict__ cand_val,
-                   int32_t* __restrict__ cand_idx) {
+                   int32_t* __restrict__ cand_idx, const NextStep ns) {
   pdl_wait();
   pdl_launch_dependents();
+  __shared__ uint32_t info_rec_all[UPD_WARPS][attn_mma::INFO_WORDS];
   __shared__ uint8_t old_anc_all[UPD_WARPS][8 * 64];
   __shared__ float fin_v_all[UPD_WARPS][KB];
   __shared__ int fin_i_all[UPD_WARPS][KB];
@@ -461,6 +480,7 @@ beam_update_kernel(const care_beam_state st, const SegLayout sl, int step, int m
     cand_val[(int64_t)v * nsel + lane] = fin_v[lane];
     cand_idx[(int64_t)v * nsel + lane] = fin_i[lane];
   }
+  int vdone = 0;
   if (lane == 0) {
     int count = st.fin_count[v];
     bool done = false;
@@ -491,6 +511,24 @@ beam_update_kernel(const care_beam_state st, const SegLayout sl, int step, int m
       st.done[v] = 1;
       atomicAdd(st.n_done, 1);
     }
+    vdone = done ? 1 : 0;
+  }
+  vdone = __shfl_sync(0xffffffffu, vdone, 0);
+  if (vdone) return;
+  // ---- prologue of step + 1 for a video that goes on ----
+  if (ns.x0 != nullptr) {
+    for (int b = 0; b < K; ++b) {
+      const int fi = fin_i[b];
+      const int tok = fi - (fi / V) * V;
+      const int64_t row = (int64_t)v * K + b;
+      rw::warp_embed_ln_row<h16>(tok, step, ns.word, ns.pos, nullptr, ns.gsg ? ns.gsg + (int64_t)v * ns.d : nullptr,
+                                 ns.gamma, ns.beta, ns.eps, ns.d, lane, ns.x0 + row * ns.d,
+                                 ns.x0_32 ? ns.x0_32 + row * ns.d : nullptr);
+    }
+  }
+  if (ns.info != nullptr) {
+    __syncwarp();   // this warp's ancestry / token writes above are visible to all of its lanes
+    attn_mma::warp_compact_record(st.anc, T, st.tok_hist, (T + 1) * K, v, K, step + 1, lane, info_rec_all[warp], ns.info);
   }
 }
 
@@ -632,6 +670,8 @@ int care_beam_init(care_ctx* ctx, const care_beam_state* st, int bos, void* stre
   if (beam::check_state(st, "care_beam_init")) return -1;
   const int64_t n = (int64_t)st->B * (st->T_max + 1) * st->K;
   const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
+  ctx->info_ready_npos = -1;
+  ctx->next_armed = false;
   beam::beam_init_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*st, bos);
   CARE_LAUNCH_CHECK(ctx);
   return 0;
@@ -650,12 +690,14 @@ static int beam_step_impl(care_ctx* ctx, const care_beam_state* st, const float*
   cudaStream_t s = (cudaStream_t)stream;
   const int K = st->K, R = st->B * st->K;
   const int ugrid = (st->B + beam::UPD_WARPS - 1) / beam::UPD_WARPS, uthreads = beam::UPD_WARPS * 32;
+  ctx->info_ready_npos = -1;   // the ancestry changes: records written for it are stale
+  ctx->next_armed = false;
 #define CARE_BEAM_GO(KB_)                                                                                  \
   do {                                                                                                     \
     beam::beam_row_kernel<KB_><<<R, beam::ROW_THREADS, 0, s>>>(*st, logits, ldv, step, normalized);        \
     CARE_LAUNCH_CHECK(ctx);                                                                                \
     beam::beam_update_kernel<KB_><<<ugrid, uthreads, 0, s>>>(*st, beam::SegLayout{}, step, max_len, cand_val, \
-                                                              cand_idx);                                   \
+                                                              cand_idx, beam::NextStep{});                 \
   } while (0)
   if (K <= 1) CARE_BEAM_GO(2);
   else if (K <= 3) CARE_BEAM_GO(4);
@@ -704,17 +746,39 @@ static int beam_step_partials_impl(care_ctx* ctx, const care_beam_state* st, con
   sl.nseg = nseg;
   sl.rpv = rpv;
   vb::seg_layout(ctx, st->B * rpv, st->V, &sl.n_tiles, &sl.T, &sl.G, &sl.row_shift);
+  // the next step's prologue rides along: its input rows when the caller armed them (care_ctx_set_next_step), the
+  // live-slot record when the next self-attention will be the chunk stream over this ctx's record table
+  beam::NextStep ns{};
+  const bool has_next = step + 1 < max_len;
+  if (ctx->next_armed) {
+    ctx->next_armed = false;
+    if (has_next) {
+      const care_next_step& n = ctx->next;
+      CARE_CHECK_ARG(n.word_emb && n.pos_emb && n.gamma && n.beta && n.x0 && n.d > 0 && n.d % 128 == 0 && n.d <= 1024,
+                     "%s: bad care_next_step", who);
+      ns.word = n.word_emb; ns.pos = n.pos_emb; ns.gsg = n.gsg; ns.gamma = n.gamma; ns.beta = n.beta;
+      ns.eps = n.eps; ns.d = n.d; ns.x0 = static_cast<h16*>(n.x0); ns.x0_32 = n.x0_f32;
+    }
+  }
+  ctx->info_ready_npos = -1;
+  if (has_next && ctx->fuse_info && ctx->compact_info != nullptr && st->B <= ctx->compact_info_videos && step + 1 <= 64 && st->K <= 8 &&
+      (ctx->self_compact == 3 || (ctx->self_compact == 2 && step + 1 >= 6))) {
+    ns.info = ctx->compact_info;
+    ctx->info_ready_npos = step + 1;
+    ctx->info_ready_B = st->B;
+    ctx->info_ready_anc = st->anc;
+  }
   CARE_CHECK_ARG(nseg == vb::nseg_for(ctx, st->B * rpv, st->V), "%s: nseg=%d does not match the %d-row record table", who,
                  nseg, st->B * rpv);
   const int ugrid = (st->B + beam::UPD_WARPS - 1) / beam::UPD_WARPS, uthreads = beam::UPD_WARPS * 32;
   if (K <= 1)
-    CARE_CUDA(launch_pdl(ctx, beam::beam_update_kernel<2>, dim3(ugrid), dim3(uthreads), 0, s, *st, sl, step, max_len, cand_val, cand_idx));
+    CARE_CUDA(launch_pdl(ctx, beam::beam_update_kernel<2>, dim3(ugrid), dim3(uthreads), 0, s, *st, sl, step, max_len, cand_val, cand_idx, ns));
   else if (K <= 3)
-    CARE_CUDA(launch_pdl(ctx, beam::beam_update_kernel<4>, dim3(ugrid), dim3(uthreads), 0, s, *st, sl, step, max_len, cand_val, cand_idx));
+    CARE_CUDA(launch_pdl(ctx, beam::beam_update_kernel<4>, dim3(ugrid), dim3(uthreads), 0, s, *st, sl, step, max_len, cand_val, cand_idx, ns));
   else if (K <= 5)
-    CARE_CUDA(launch_pdl(ctx, beam::beam_update_kernel<6>, dim3(ugrid), dim3(uthreads), 0, s, *st, sl, step, max_len, cand_val, cand_idx));
+    CARE_CUDA(launch_pdl(ctx, beam::beam_update_kernel<6>, dim3(ugrid), dim3(uthreads), 0, s, *st, sl, step, max_len, cand_val, cand_idx, ns));
   else
-    CARE_CUDA(launch_pdl(ctx, beam::beam_update_kernel<9>, dim3(ugrid), dim3(uthreads), 0, s, *st, sl, step, max_len, cand_val, cand_idx));
+    CARE_CUDA(launch_pdl(ctx, beam::beam_update_kernel<9>, dim3(ugrid), dim3(uthreads), 0, s, *st, sl, step, max_len, cand_val, cand_idx, ns));
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

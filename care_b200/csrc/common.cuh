@@ -136,6 +136,17 @@ struct care_ctx {
   // runs its prologue (barrier init, TMEM allocation, descriptor prefetch) and blocks in griddepcontrol.wait
   // until N has completed and flushed (option "pdl", env CARE_B200_PDL)
   int pdl = 1;
+  // one-shot request armed by care_ctx_set_next_step: the next beam step also computes the following step's input rows
+  care_next_step next = {};
+  bool next_armed = false;
+  // the live-slot record table already holds the records for (n_pos, B, anc): written by the last beam step
+  // the beam kernel also writes the next step's live-slot records (option "fuse_info", env CARE_B200_FUSE_INFO).  Off
+  // by default: measured neutral to slightly slower (4096 videos 51.2 -> 51.9 ms) - the one-warp-per-video beam kernel
+  // is the latency-bound one, and with graphs + programmatic dependent launch a separate small launch costs little
+  int fuse_info = 0;
+  int info_ready_npos = -1;
+  int info_ready_B = 0;
+  const void* info_ready_anc = nullptr;
   int vocab_2sm = 1;   // fused vocabulary kernel on CTA pairs when the shape has >= two waves of pair tiles
   // per-shape GEMM variant picks; contexts that must launch identical kernels (the lanes of one decode) share one
   // table (care_ctx_share_tuning)

@@ -1,13 +1,10 @@
 // Row-wise HBM-bound kernels: feature cast, encoder LayerNorm(+temporal mean), HighWay+BN tail,
 // decoder input embedding + LayerNorm, residual + LayerNorm.  One warp per row, 16-byte accesses,
 // LayerNorm statistics in fp32 with a two-pass (mean, then centred variance) reduction.
-#include "common.cuh"
+#include "step_prologue.cuh"
 
 namespace care {
 namespace rw {
-
-constexpr int MAX_D = 1024;           // per-lane register budget: MAX_D / 32 / 4 float4 chunks
-constexpr int MAX_CHUNKS = MAX_D / 128;
 
 // ---------------------------------------------------------------------------------------------
 // dst[r] = [hi | lo | hi * 2^-11] (TERMS == 3) or [hi] (TERMS == 1) of src[r], each part `cols_pad` wide (zero
@@ -49,40 +46,6 @@ __global__ void split_f32_h16_kernel(const float* __restrict__ src, int64_t ld_s
       Act<h16>::store8(o + 2 * cols_pad, v);
     }
   }
-}
-
-// LayerNorm of a row held as `nch` float4 chunks per lane (chunk c covers columns c*128 + lane*4 .. +3).
-__device__ __forceinline__ void warp_layernorm(float (&x)[MAX_CHUNKS][4], int nch, int d, int lane,
-                                               const float* __restrict__ gamma, const float* __restrict__ beta,
-                                               float eps) {
-  float s = 0.f;
-#pragma unroll
-  for (int c = 0; c < MAX_CHUNKS; ++c)
-    if (c < nch)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) s += x[c][j];
-  const float mean = warp_sum(s) / (float)d;
-  float q = 0.f;
-#pragma unroll
-  for (int c = 0; c < MAX_CHUNKS; ++c)
-    if (c < nch)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float t = x[c][j] - mean;
-        q += t * t;
-      }
-  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)d + eps);
-#pragma unroll
-  for (int c = 0; c < MAX_CHUNKS; ++c)
-    if (c < nch) {
-      const int col = c * 128 + lane * 4;
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + col));
-      x[c][0] = (x[c][0] - mean) * rstd * g.x + b.x;
-      x[c][1] = (x[c][1] - mean) * rstd * g.y + b.y;
-      x[c][2] = (x[c][2] - mean) * rstd * g.z + b.z;
-      x[c][3] = (x[c][3] - mean) * rstd * g.w + b.w;
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -169,38 +132,10 @@ embed_ln_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ 
   if (all_done(ee)) return;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= R) return;
-  const int nch = d / 128;
-  const int tok = tokens[row];
-  const int p = positions ? positions[row] : position;
   const int vid = row / rpv;
-  float r[MAX_CHUNKS][4];
-#pragma unroll
-  for (int c = 0; c < MAX_CHUNKS; ++c)
-    if (c < nch) {
-      const int col = c * 128 + lane * 4;
-      float w[4], q[4];
-      Act<float>::load4(word + (int64_t)tok * d + col, w);
-      Act<float>::load4(pos + (int64_t)p * d + col, q);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) r[c][j] = w[j] + q[j];
-      if (add) {
-        Act<float>::load4(add + (int64_t)vid * d + col, q);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) r[c][j] += q[j];
-      }
-      if (gsg) {
-        Act<float>::load4(gsg + (int64_t)vid * d + col, q);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) r[c][j] += q[j];
-      }
-    }
-  warp_layernorm(r, nch, d, lane, gamma, beta, eps);
-#pragma unroll
-  for (int c = 0; c < MAX_CHUNKS; ++c)
-    if (c < nch) {
-      Act<T>::store4(out + (int64_t)row * d + c * 128 + lane * 4, r[c]);
-      if (out32 != nullptr) Act<float>::store4(out32 + (int64_t)row * d + c * 128 + lane * 4, r[c]);
-    }
+  warp_embed_ln_row<T>(tokens[row], positions ? positions[row] : position, word, pos,
+                       add ? add + (int64_t)vid * d : nullptr, gsg ? gsg + (int64_t)vid * d : nullptr, gamma, beta, eps, d,
+                       lane, out + (int64_t)row * d, out32 ? out32 + (int64_t)row * d : nullptr);
 }
 
 // out = LN(x + residual)   (SubLayers.py:74-79, 148-150)

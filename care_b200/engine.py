@@ -21,7 +21,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_RELU, BF16, F16, F32, BeamState, check, ptr
+from ._lib import ACT_NONE, ACT_RELU, BF16, F16, F32, BeamState, NextStep, check, ptr
 
 PAD, UNK, BOS, EOS, MASK, VIS = 0, 1, 2, 3, 4, 5  # reference: config/Constants.py:1-6
 
@@ -99,6 +99,13 @@ class CareEngine:
         self.graph_lanes = int(opt.get("care_graph_lanes", os.environ.get("CARE_B200_GRAPH_LANES", "1")))
         self._twins = []
         self._lane_streams = []
+        # A/B switch: the beam kernel of step t also writes step t+1's decoder input rows (no embed_ln launch).  Off by
+        # default - measured slower (4096 videos 51.2 -> 51.8 ms, 512 videos 8.90 -> 9.29 ms): one warp per video
+        # embeds its K rows one after the other, where embed_ln_kernel has a warp per row
+        self.fuse_next_step = bool(int(opt.get("care_fuse_next_step", os.environ.get("CARE_B200_FUSE_NEXT", "0"))))
+        if opt.get("care_fuse_info") is not None:
+            check(self.lib.care_ctx_set_option(self.ctx, b"fuse_info", int(opt["care_fuse_info"])), "care_ctx_set_option")
+        self._x0_ready = None      # (t, R): x0 of step t was written by the previous step's beam kernel
         # step 1 of the beam search on one row per video (all K beams hold <bos>; 16-bit fused path)
         self.compact_first = bool(opt.get("care_compact_first_step", True))
         self._prepare_weights(state_dict)
@@ -558,9 +565,12 @@ class CareEngine:
             self.gemm(x0, w["Wqkv"], w["bqkv"], slot0, R, 3 * d, d)
             cx_in = slot0[:, 2 * d:]                                   # the value rows: attention over one key
         else:
-            check(lib.care_embed_ln(ctx, dt, ptr(bufs["cur_tok"]), None, t - 1, ptr(w["word"]), ptr(w["pos"]), None,
-                                    ptr(gsg), K, ptr(w["emb_g"]), ptr(w["emb_b"]), self.eps, R, d, ptr(x0), ptr(r0), st),
-                  "care_embed_ln")
+            if self._x0_ready == (t, R):
+                self._x0_ready = None      # written by the beam kernel of step t - 1 (care_ctx_set_next_step)
+            else:
+                check(lib.care_embed_ln(ctx, dt, ptr(bufs["cur_tok"]), None, t - 1, ptr(w["word"]), ptr(w["pos"]), None,
+                                        ptr(gsg), K, ptr(w["emb_g"]), ptr(w["emb_b"]), self.eps, R, d, ptr(x0), ptr(r0),
+                                        st), "care_embed_ln")
             self.gemm(x0, w["Wqkv"], w["bqkv"], cache[t - 1], R, 3 * d, d)
             check(lib.care_self_attn_step(ctx, dt, ptr(cache), t, B, K, self.H, d, ptr(bufs["anc"]), Tm,
                                           ptr(bufs["tok_hist"]), done, ptr(cx), st), "care_self_attn_step")
@@ -593,11 +603,25 @@ class CareEngine:
         self._sublayer_tail(hb, w["W2"], w["b2"], w["ln3_g"], w["ln3_b"], x2, x3, R, self.F, y32, r2, r3)
         return x3
 
+    def _arm_next_step(self, t, B, K, enc):
+        """Asks the beam kernel of step t for step t+1's decoder input rows (x0 of the full K-row layout)."""
+        if not self.fuse_next_step or t + 1 >= self.max_len:
+            return
+        w, d, R = self.w, self.d, B * K
+        x0 = self._buf("x0", (R, d), self.tdtype)
+        r0 = self._buf("r0", (R, d), torch.float32) if self.fused_ln == 2 else None
+        nxt = NextStep(ptr(w["word"]), ptr(w["pos"]), ptr(enc.get("semantic_hidden_states")), ptr(w["emb_g"]),
+                       ptr(w["emb_b"]), self.eps, d, ptr(x0), ptr(r0))
+        check(self.lib.care_ctx_set_next_step(self.ctx, ctypes.byref(nxt)), "care_ctx_set_next_step")
+        self._x0_ready = (t + 1, R)
+
     def decode_step(self, t, B, K, enc, kv, bufs, bst, audit=None, want_logits=False, akv=None):
         """One beam step (len_input_ids == t) for every video; 12 kernel launches from 2048 beam rows up (fused residual LayerNorm + fused vocabulary), 15 for small batches."""
         lib, ctx, w, d = self.lib, self.ctx, self.w, self.d
         st = self._stream()
         R = B * K
+        if t == 1:
+            self._x0_ready = None     # a decode that stopped early may have left a request behind
         fused = self.fused_vocab and not want_logits
         if t == 1 and fused and audit is None and K > 1 and self.compact_first:
             # step 1 on one row per video (see step_hidden): the vocabulary kernel and the beam kernel take B rows
@@ -609,6 +633,7 @@ class CareEngine:
             part = self._buf("vocab_partials", (B, nseg, 2 + 2 * kb), torch.float32)
             check(lib.care_vocab_beam_partials(ctx, ptr(x3), d, ptr(w["Wvocab"]), w["Wvocab"].stride(0), B, self.V, d,
                                                K, ptr(part), nseg, st), "care_vocab_beam_partials")
+            self._arm_next_step(t, B, K, enc)
             check(lib.care_beam_first_step_partials(ctx, ctypes.byref(bst), ptr(part), nseg, self.max_len, None, None,
                                                     st), "care_beam_first_step_partials")
             return None
@@ -625,6 +650,8 @@ class CareEngine:
             part = self._buf("vocab_partials", (R, nseg, 2 + 2 * kb), torch.float32)
             check(lib.care_vocab_beam_partials(ctx, ptr(x3), d, ptr(w["Wvocab"]), w["Wvocab"].stride(0), R, self.V, d,
                                                K, ptr(part), nseg, st), "care_vocab_beam_partials")
+            if audit is None:
+                self._arm_next_step(t, B, K, enc)
             check(lib.care_beam_step_partials(ctx, ctypes.byref(bst), ptr(part), nseg, t, self.max_len, ptr(cv),
                                               ptr(ci), st), "care_beam_step_partials")
             return None

@@ -59,6 +59,25 @@ int care_ctx_sm_count(const care_ctx* ctx);
  * (care_gemm), "vocab" (care_vocab_beam_partials) or "self_attn" (care_self_attn_step); bench.py labels its
  * roofline records with it */
 const char* care_ctx_last_kernel(const care_ctx* ctx, const char* family);
+/* Inputs of the NEXT decode step that the beam kernel can produce while it still holds the chosen tokens: the
+ * decoder input rows x0[v*K + b] = LN(word[tok] + pos[step] + gsg[v]) (Embeddings.py:134-188; what care_embed_ln
+ * computes in a launch of its own).  care_ctx_set_next_step arms ONE request: the next care_beam_step_partials /
+ * care_beam_first_step_partials call on this ctx also writes x0 (T16 [B*K, d], plus the fp32 copy x0_f32 when not
+ * NULL) for every video that goes on, and the caller skips care_embed_ln at the start of that step.  NULL disarms.
+ * Independently of this, the same kernel writes the live-slot records of the chunk-stream self-attention
+ * (care_ctx_set_option "self_compact") for the next step, so that step launches no record kernel. */
+typedef struct care_next_step {
+  const float* word_emb;
+  const float* pos_emb;
+  const float* gsg;      /* fp32 [B, d] or NULL */
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int32_t d;
+  void* x0;
+  float* x0_f32;         /* or NULL */
+} care_next_step;
+int care_ctx_set_next_step(care_ctx* ctx, const care_next_step* next);
 /* Makes `ctx` use `other`'s table of per-shape GEMM variant picks (and its gemm_2sm / gemm_bn settings): two
  * contexts of one device that decode slices of the same batch on different streams then launch the same
  * kernel variant for the same shape, so a video's result does not depend on the slice it fell into. */
@@ -77,6 +96,10 @@ int care_ctx_set_early_exit(care_ctx* ctx, const int32_t* counter, int target);
  * (M, N, K, out dtype) by timing both variants ONCE, on the first care_gemm call with that shape - the
  * only place the library waits on the stream (never while the stream is being captured). */
 int care_ctx_set_option(care_ctx* ctx, const char* name, int value);
+/* "pdl": 1 (default) = the kernels of a decode step are launched with programmatic stream serialization: kernel
+ * N+1 is scheduled while kernel N drains, runs its prologue and blocks in griddepcontrol.wait until N has completed.
+ * "fuse_info": 1 = the beam kernel also writes the next step's live-slot records (0, the default: a kernel of its
+ * own before the self-attention; measured neutral to slightly slower when fused). */
 /* "vocab_2sm": 1 (default) = the fused vocabulary kernel runs on CTA pairs when the shape has at least two
  * waves of 256 x 256 tiles, 0 = single-CTA tiles only.
  * "gemm_smallm": 1 (default) = GEMMs with M <= 16 rows (batch-1 / latency mode) use a weight-streaming

@@ -403,6 +403,31 @@ def test_first_step_on_one_row_per_video_is_exact_and_ignores_stale_cache_memory
     assert h_again == h_c
 
 
+@pytest.mark.parametrize("name,stream", [("cfg2_sharp", False), ("cfg4_trained", True), ("cab_sharp", False)])
+def test_next_step_prologue_in_the_beam_kernel_changes_nothing(name, stream):
+    """The beam kernel of step t writes step t+1's decoder input rows (care_ctx_set_next_step) and, for the chunk-stream
+    self-attention, its live-slot records: same arithmetic as care_embed_ln / the record kernel, so captions AND scores
+    are bit-identical to the run with the stand-alone launches - which it saves (one or two launches per step).  Both
+    switches are off by default: measured neutral to slower."""
+    import care_b200
+    rec = load_golden(name)
+    opt, sd, feats = rebuild_case(rec)
+    if stream:
+        opt = dict(opt, care_self_compact=3)      # the live-slot stream kernel for every shape
+    dev = [f.cuda() for f in feats]
+    tr = care_b200.get_translator(opt)
+    out, launches = {}, {}
+    for fuse in (False, True):
+        m = _gpu_model(dict(opt, care_fuse_next_step=fuse, care_fuse_info=int(fuse), care_cuda_graph=False), sd, "fp16")
+        n0 = m.engine().launch_count()
+        out[fuse] = tr.translate_batch([m], {"feats": dev})
+        launches[fuse] = m.engine().launch_count() - n0
+    assert out[True][0] == out[False][0]
+    assert out[True][1] == out[False][1]
+    assert launches[True] < launches[False]
+    print("\n%s: launches per decode %d -> %d" % (name, launches[False], launches[True]))
+
+
 def test_no_gpu_no_fallback_message():
     from care_b200 import _lib
     assert os.path.isfile(_lib.LIB_PATH)
