@@ -267,6 +267,14 @@ gemm_add_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       uint4 gn[NSUB][4];
 #pragma unroll
       for (int sb = 0; sb < NSUB; ++sb) ldg_block(res_b + sb * 64, res_ld, row0, M, lane, gn[sb]);
+      // the rest of this thread's residual row slice -> L2 while the MMAs of the tile still run (the row was usually
+      // evicted by the attention kernel that ran in between); one 128-byte line per request
+      if (row0 + lane < M) {
+        const uint8_t* rp = res_b + (int64_t)(row0 + lane) * res_ld;
+#pragma unroll
+        for (int off = 128; off < HALF * (R32 ? 4 : 2); off += 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + off));
+      }
       mbar_wait(tfull_bar(acc), aph);
       tc_fence_after();
       // ---- pass 1: v = acc + bias + residual -> TMEM; row statistics ----

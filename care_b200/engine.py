@@ -76,7 +76,7 @@ class CareEngine:
         self.fused_ln = int(default_ln if fl is None else fl) if (self.half and self.d in (512, 768, 1024)) else 0
         if self.fused_ln not in (0, 1, 2):
             raise ValueError("care_fused_ln must be 0, 1 or 2")
-        self.fused_ln_min_rows = int(opt.get("care_fused_ln_min_rows", 2048))
+        self.fused_ln_min_rows = int(opt.get("care_fused_ln_min_rows", os.environ.get("CARE_B200_FUSED_LN_MIN_ROWS", 2048)))
         self._ws = {}
         self._ws_epoch_of = {}
         self._ws_bytes = 0
