@@ -173,6 +173,76 @@ gemm_f32_small_kernel(const float* __restrict__ A, int64_t lda, const float* __r
   }
 }
 
+// Same product on 32x32 tiles (2x2 outputs per thread): a few hundred rows of a ranking head (512 videos x 500
+// concepts, K = 4096) are only 64 tiles of 64x64 - 64 CTAs walking 256 k-tiles one after the other on 148 SMs, bound by
+// the latency of each k-tile, not by FFMA issue.  256 tiles put several CTAs on every SM.  Same k order per output:
+// bit-identical to the other two kernels.
+constexpr int TB = 32;
+template <typename OutT>
+__global__ void __launch_bounds__(THREADS)
+gemm_f32_tiny_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ W, int64_t ldw,
+                     const float* __restrict__ bias, OutT* __restrict__ C, int64_t ldc, int M, int N, int n_store, int K,
+                     int relu, const EarlyExit ee) {
+  if (all_done(ee)) return;
+  __shared__ __align__(16) float As[2][BK][TB + 4];
+  __shared__ __align__(16) float Ws[2][BK][TB + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * TB, n0 = blockIdx.x * TB;
+  const bool loads_a = tid < 128;                 // threads 0..127 move A's k-tile, 128..255 W's: one float4 each
+  const int lrow = (tid & 127) >> 2, lk = (tid & 3) * 4;
+  const int tx = tid & 15, ty = tid >> 4;         // 16 x 16 threads, 2 x 2 outputs each
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  float4 r4;
+  auto gload = [&](int k0) {
+    const int gk = k0 + lk;
+    r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (loads_a) {
+      const int gm = m0 + lrow;
+      if (gm < M && gk < K) r4 = *reinterpret_cast<const float4*>(A + (int64_t)gm * lda + gk);
+    } else {
+      const int gn = n0 + lrow;
+      if (gn < N && gk < K) r4 = *reinterpret_cast<const float4*>(W + (int64_t)gn * ldw + gk);
+    }
+  };
+  auto sstore = [&](int buf) {
+    float(*dst)[TB + 4] = loads_a ? As[buf] : Ws[buf];
+    dst[lk + 0][lrow] = r4.x; dst[lk + 1][lrow] = r4.y; dst[lk + 2][lrow] = r4.z; dst[lk + 3][lrow] = r4.w;
+  };
+  const int k_tiles = (K + BK - 1) / BK;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < k_tiles; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < k_tiles) gload((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float2 a2 = *reinterpret_cast<const float2*>(&As[buf][k][ty * 2]);
+      const float2 w2 = *reinterpret_cast<const float2*>(&Ws[buf][k][tx * 2]);
+      acc[0][0] = fmaf(a2.x, w2.x, acc[0][0]); acc[0][1] = fmaf(a2.x, w2.y, acc[0][1]);
+      acc[1][0] = fmaf(a2.y, w2.x, acc[1][0]); acc[1][1] = fmaf(a2.y, w2.y, acc[1][1]);
+    }
+    if (kt + 1 < k_tiles) {
+      sstore(buf ^ 1);
+      __syncthreads();
+    }
+  }
+  const int col = n0 + tx * 2;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int row = m0 + ty * 2 + i;
+    if (row >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (col + j >= n_store) continue;
+      float x = acc[i][j];
+      if (bias != nullptr && col + j < N) x += __ldg(bias + col + j);
+      if (col + j >= N) x = 0.f;
+      C[(int64_t)row * ldc + col + j] = Act<OutT>::from_float(relu ? fmaxf(x, 0.f) : x);
+    }
+  }
+}
+
 int gemm_f32(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
              int64_t ldc, int out_dtype, int M, int N, int K, int act, cudaStream_t stream) {
   CARE_CHECK_ARG(lda % 4 == 0 && ldw % 4 == 0 && K % 4 == 0,
@@ -188,6 +258,20 @@ int gemm_f32(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t l
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   if ((int)(grid.x * grid.y) * 4 <= ctx->sm_count) {   // too few large tiles to fill the machine
     dim3 sgrid((N + SB - 1) / SB, (M + SB - 1) / SB);
+    if ((int)(sgrid.x * sgrid.y) < ctx->sm_count) {     // ... and too few 64x64 tiles as well
+      dim3 tgrid((N + TB - 1) / TB, (M + TB - 1) / TB);
+      if (out_dtype == CARE_F32)
+        gemm_f32_tiny_kernel<float><<<tgrid, THREADS, 0, stream>>>((const float*)A, lda, (const float*)W, ldw, bias,
+                                                                  (float*)C, ldc, M, N, n_pad, K, act == CARE_ACT_RELU,
+                                                                  early_exit_of(ctx));
+      else
+        gemm_f32_tiny_kernel<h16><<<tgrid, THREADS, 0, stream>>>((const float*)A, lda, (const float*)W, ldw, bias,
+                                                                (h16*)C, ldc, M, N, n_pad, K, act == CARE_ACT_RELU,
+                                                                early_exit_of(ctx));
+      ctx->last_gemm = "gemm_f32_tiny_kernel";
+      CARE_LAUNCH_CHECK(ctx);
+      return 0;
+    }
     if (out_dtype == CARE_F32)
       gemm_f32_small_kernel<float><<<sgrid, THREADS, 0, stream>>>((const float*)A, lda, (const float*)W, ldw, bias,
                                                                  (float*)C, ldc, M, N, n_pad, K,
