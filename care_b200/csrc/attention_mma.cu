@@ -56,7 +56,8 @@ constexpr int COMB_LD = 72;   // floats per row of the merge buffer (64 + pad: <
 template <int KKW, bool SELF, int WARPS>
 __device__ __forceinline__ void attend(const Params& p, int v, int h, int warp, int lane, uint32_t (&qa)[4][2],
                                        uint32_t k_s, uint32_t v_s, int n_keys, int rows_pad, uint32_t bar_k,
-                                       uint32_t bar_v, const uint32_t* mw, float* stat, float* comb) {
+                                       uint32_t bar_v, const uint32_t* mw, float* stat, float* comb,
+                                       const float (&bq)[2 * KKW][2]) {
   const int K = p.K;
   const int g = lane >> 2, tig = lane & 3;
   if (g >= K) {
@@ -104,8 +105,8 @@ __device__ __forceinline__ void attend(const Params& p, int v, int h, int warp, 
         float x = s[2 * i + half][e] * 0.125f;   // / sqrt(64), Attention.py:84
         if (SELF) {
           if (!((mw[g * 8 + ((j >> 5) & 7)] >> (j & 31)) & 1u)) x = -1e9f;
-        } else if (p.bias != nullptr && j < n_keys) {
-          x += __ldg(p.bias + (int64_t)h * p.Lm + j);
+        } else {
+          x += bq[2 * i + half][e];   // hybrid attention bias of key j, fetched while the K tile was in flight
         }
         if (kk >= kk1 || j >= n_keys) x = -INFINITY;
         s[2 * i + half][e] = x;
@@ -276,8 +277,24 @@ attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       }
     }
   }
+  // cross: the hybrid attention bias of this thread's keys (Attention.py:104-111), loaded now so that its latency
+  // hides behind the K tile's instead of sitting between the two MMA phases
+  float bq[2 * KKW][2];
+  {
+    const int n_kk = p.rows_pad >> 4;
+    const int kk0 = (warp * n_kk) / WARPS;
+#pragma unroll
+    for (int i = 0; i < KKW; ++i)
+#pragma unroll
+      for (int half = 0; half < 2; ++half)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = (kk0 + i) * 16 + half * 8 + 2 * tig + e;
+          bq[2 * i + half][e] = (!SELF && p.bias != nullptr && j < n_keys) ? __ldg(p.bias + (int64_t)h * p.Lm + j) : 0.f;
+        }
+  }
   __syncthreads();   // mbarrier init + mask words visible to every warp
-  attend<KKW, SELF, WARPS>(p, v, h, warp, lane, qa, k_s, v_s, n_keys, p.rows_pad, bar_k, bar_v, mw, stat, comb);
+  attend<KKW, SELF, WARPS>(p, v, h, warp, lane, qa, k_s, v_s, n_keys, p.rows_pad, bar_k, bar_v, mw, stat, comb, bq);
 }
 
 template <int KKW, bool SELF, int WARPS>
@@ -442,7 +459,8 @@ attn_self_compact_kernel(const Params p, const h16* __restrict__ cache, int64_t 
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
-  attend<KKW, true, WARPS>(p, v, h, warp, lane, qa, k_s, v_s, n_live, rows_pad, 0u, 0u, mw, stat, comb);
+  const float no_bias[2 * KKW][2] = {};
+  attend<KKW, true, WARPS>(p, v, h, warp, lane, qa, k_s, v_s, n_live, rows_pad, 0u, 0u, mw, stat, comb, no_bias);
 }
 
 template <int KKW>
