@@ -90,7 +90,8 @@ class CareEngine:
         # larger batches are graphed from the SECOND decode of the same shape on (a one-off shape is not worth a
         # capture): the replay has no launch gaps and no host polling (the device-side early-exit flag replaces
         # it) - 4096 videos: 56.2 -> 54.0 ms per batch
-        self.graph_max_rows_repeat = int(opt.get("care_cuda_graph_max_rows_repeat", 32768))
+        self.graph_max_rows_repeat = int(opt.get("care_cuda_graph_max_rows_repeat",
+                                                 os.environ.get("CARE_B200_GRAPH_REPEAT_ROWS", 32768)))
         self._shapes_seen = {}
         self._graphs = {}
         self._graph_launches = 0

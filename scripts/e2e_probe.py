@@ -118,12 +118,3 @@ time.sleep(0.3)
 sustained(20, 4, "+ nvidia-smi -lms 50")
 p.terminate()
 p.wait()
-sys.path.insert(0, ROOT)
-import bench  # noqa: E402
-eng = model.engine()
-timed = bench.TimedLib(eng.lib, bench.kernel_work_table(2))
-eng.lib = timed
-timed.on = True
-sustained(20, 4, "+ per-kernel events")
-timed.on = False
-sustained(20, 4, "+ TimedLib proxy off")

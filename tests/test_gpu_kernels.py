@@ -625,6 +625,53 @@ def test_fused_vocab_beam_matches_unfused(env, B, K, V, d):
         assert torch.isfinite(lse).all() and live.shape[0] == B
 
 
+def test_nar_teacher_probs(env):
+    """care_nar_teacher_probs (scoring_by_teacher, na_algorithms.py:92-126) against torch softmax + gather."""
+    lib, h, L = env
+    R, Lc, V, ldv = 13, 9, 1037, 1040
+    g = torch.Generator(device="cuda").manual_seed(4)
+    logits = torch.randn(R * Lc, ldv, device="cuda", generator=g) * 3.0
+    targets = torch.randint(0, V, (R * Lc,), device="cuda", generator=g, dtype=torch.int32)
+    lengths = torch.randint(1, Lc + 1, (R,), device="cuda", generator=g, dtype=torch.int32)
+    probs_in = torch.rand(R * Lc, device="cuda", generator=g)
+    ref = torch.softmax(logits[:, :V], dim=-1).gather(1, targets.long().unsqueeze(1)).squeeze(1).view(R, Lc)
+    pad = torch.arange(Lc, device="cuda").unsqueeze(0) >= lengths.unsqueeze(1)
+    ref[pad] = 1.0
+    for pin in (None, probs_in):
+        out = torch.full((R * Lc,), float("nan"), device="cuda")
+        L.check(lib.care_nar_teacher_probs(h, logits.data_ptr(), ldv, targets.data_ptr(), lengths.data_ptr(), R, Lc, V,
+                                           None if pin is None else pin.data_ptr(), out.data_ptr(), _stream()), "teacher")
+        torch.cuda.synchronize()
+        want = ref.reshape(-1) * (1.0 if pin is None else pin)
+        assert (out - want).abs().max().item() < 1e-6
+
+
+def test_contexts_share_gemm_tuning(env):
+    """care_ctx_share_tuning: a second context of the device adopts the first one's per-shape GEMM variant picks, so
+    both launch the same kernel for the same shape (care_ctx_last_kernel) and produce identical bits."""
+    lib, h, L = env
+    h2 = ctypes.c_void_p()
+    L.check(lib.care_ctx_create(ctypes.byref(h2), 0), "ctx")
+    try:
+        L.check(lib.care_ctx_share_tuning(h2, h), "share")
+        M, N, K = 20480, 1024, 1024
+        g = torch.Generator(device="cuda").manual_seed(9)
+        A = torch.randn(M, K, device="cuda", generator=g).to(TH)
+        W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(TH)
+        outs, names = [], []
+        for ctx in (h, h2):
+            C = torch.empty(M, N, device="cuda", dtype=TH)
+            L.check(lib.care_gemm(ctx, H16, A.data_ptr(), K, W.data_ptr(), K, None, C.data_ptr(), N, H16, M, N, K, 0,
+                                  _stream()), "gemm")
+            torch.cuda.synchronize()
+            outs.append(C)
+            names.append(lib.care_ctx_last_kernel(ctx, b"gemm"))
+        assert names[0] == names[1]
+        assert torch.equal(outs[0], outs[1])
+    finally:
+        lib.care_ctx_destroy(h2)
+
+
 def test_early_exit_flag_skips_gemm_and_ln(env):
     """care_ctx_set_early_exit: once *counter >= target the GEMM / LayerNorm kernels return without
     touching their outputs; below the target, or with the flag cleared, they run normally."""
