@@ -112,6 +112,7 @@ int care_ctx_create(care_ctx** out, int device) {
   if (const char* e = getenv("CARE_B200_GEMM_2SM")) c->gemm_2sm = atoi(e);
   if (const char* e = getenv("CARE_B200_DEBUG")) c->debug = atoi(e);
   if (const char* e = getenv("CARE_B200_PDL")) c->pdl = atoi(e) != 0;
+  if (const char* e = getenv("CARE_B200_GEMM_LN_MC")) c->gemm_ln_multicast = atoi(e) != 0;
   if (const char* e = getenv("CARE_B200_FUSE_INFO")) c->fuse_info = atoi(e) != 0;
   if (const char* path = getenv("CARE_B200_GEMM_CHOICE_FILE")) {   // GEMM variants picked by an earlier run
     if (FILE* f = fopen(path, "r")) {
@@ -209,6 +210,10 @@ int care_ctx_set_option(care_ctx* ctx, const char* name, int value) {
   }
   if (strcmp(name, "gemm_smallm") == 0) {
     ctx->gemm_smallm = value;
+    return 0;
+  }
+  if (strcmp(name, "gemm_ln_multicast") == 0) {
+    ctx->gemm_ln_multicast = value != 0;
     return 0;
   }
   if (strcmp(name, "fuse_info") == 0) {

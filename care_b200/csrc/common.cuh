@@ -147,6 +147,11 @@ struct care_ctx {
   int info_ready_npos = -1;
   int info_ready_B = 0;
   const void* info_ready_anc = nullptr;
+  // care_gemm_add_ln: A tile fetched once per cluster and multicast (option "gemm_ln_multicast", env CARE_B200_GEMM_LN_MC).
+  // Off by default: measured neutral (49 vs 49 us at 20480 x 1024 x 1024) - the 128 x 256 single-CTA mainloop is bound by
+  // shared-memory bandwidth (48 KB of operands read by the MMAs plus 48 KB written by TMA per 512 MMA cycles = 192 B/clk
+  // against 128 B/clk), not by L2; only CTA pairs (cta_group::2, half the B operand per SM) lift that
+  int gemm_ln_multicast = 0;
   int vocab_2sm = 1;   // fused vocabulary kernel on CTA pairs when the shape has >= two waves of pair tiles
   // per-shape GEMM variant picks; contexts that must launch identical kernels (the lanes of one decode) share one
   // table (care_ctx_share_tuning)

@@ -92,6 +92,22 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
   } while (!done);
 }
 
+// this CTA's slice of the A tile, delivered to the same offset (and counted on the same barrier offset) in every CTA of mask
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                      uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the barrier at this offset in every CTA of mask
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+
 // [32 rows x 64 bytes] transposition block: physical offset of 16-byte chunk c16 of row r; conflict-free both
 // for "lane = row" accesses and for the coalesced mapping (4 lanes per row)
 __device__ __forceinline__ uint32_t xp_off(int r, int c16) { return (uint32_t)(r * 64 + ((c16 ^ ((r >> 1) & 3)) << 4)); }
@@ -129,7 +145,12 @@ __device__ __forceinline__ void xp_store_rows(uint8_t* xp, int lane, const uint4
   }
 }
 
-template <bool R32>
+// MC (A/B switch, off by default): the A tile (the same 128 rows for every CTA of the cluster) is fetched ONCE per
+// cluster: CTA r loads rows [r * 128 / CN, (r + 1) * 128 / CN) and multicasts them into all CN shared memories (36 KB
+// instead of 48 KB from L2 per k-block and CTA at CN = 4); a stage is refilled only when the MMA threads of ALL the CTAs
+// have released it (multicast tcgen05.commit, empty barriers count CN arrivals).  Measured neutral: the mainloop is
+// bound by shared-memory bandwidth (operand reads + TMA fills), not by L2.
+template <bool R32, bool MC>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_add_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                    const float* __restrict__ bias, const void* __restrict__ residual, const float* __restrict__ gamma,
@@ -168,7 +189,7 @@ gemm_add_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), MC ? csize : 1u);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -205,10 +226,16 @@ gemm_add_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
-          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_wait_cluster(empty_bar(s), ph ^ 1u);
           mbar_expect_tx(full_bar(s), STAGE_BYTES);
           const uint32_t a_dst = smem_base + s * STAGE_BYTES;
-          tma_load_2d(a_dst, &tma_a, full_bar(s), kb * BLOCK_K, m_blk * BLOCK_M);
+          if constexpr (MC) {
+            const int slice_rows = BLOCK_M / (int)csize;
+            tma_load_2d_multicast(a_dst + crank * (uint32_t)(slice_rows * BLOCK_K * 2), &tma_a, full_bar(s), kb * BLOCK_K,
+                                  m_blk * BLOCK_M + (int)crank * slice_rows, (uint16_t)((1u << csize) - 1u));
+          } else {
+            tma_load_2d(a_dst, &tma_a, full_bar(s), kb * BLOCK_K, m_blk * BLOCK_M);
+          }
           tma_load_2d(a_dst + A_BYTES, &tma_b, full_bar(s), kb * BLOCK_K, n_blk * BN);
         }
       }
@@ -234,7 +261,8 @@ gemm_add_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
             tc_mma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          tc_commit(empty_bar(s));
+          if constexpr (MC) tc_commit_multicast(empty_bar(s), (uint16_t)((1u << csize) - 1u));
+          else tc_commit(empty_bar(s));
         }
         tc_commit(tfull_bar(acc));
       }
@@ -401,13 +429,13 @@ static int get_tmap(care_ctx* ctx, const void* ptr, uint64_t rows, uint64_t cols
   return get_tmap_bf16(ctx, ptr, 2, gdim, gstride, box, out);
 }
 
-template <bool R32>
+template <bool R32, bool MC>
 static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const void* residual,
                   const float* gamma, const float* beta, float eps, void* out16, float* out32, int M, int N, int K,
                   cudaStream_t stream) {
   static bool configured_all[64] = {false};
   static int max_clusters_all[64][MAX_CN + 1] = {{0}};
-  auto kern = gemm_add_ln_kernel<R32>;
+  auto kern = gemm_add_ln_kernel<R32, MC>;
   const int cn = N / BN;
   if (!configured_all[ctx->device & 63]) {
     CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -464,12 +492,18 @@ extern "C" int care_gemm_add_ln(care_ctx* ctx, const void* A, int64_t lda, const
                    reinterpret_cast<uintptr_t>(out16) | reinterpret_cast<uintptr_t>(out32)) & 15) == 0,
                  "care_gemm_add_ln: pointers must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
+  const int cn = N / gln::BN;
+  // the A tile is multicast inside the cluster when its 128 rows split evenly over the CTAs (d = 512, 1024)
+  const bool mc = ctx->gemm_ln_multicast && (tc::BLOCK_M % cn) == 0;
   CUtensorMap ta, tb;
-  int rc = gln::get_tmap(ctx, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, tc::BLOCK_M, &ta);
+  int rc = gln::get_tmap(ctx, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, mc ? tc::BLOCK_M / cn : tc::BLOCK_M, &ta);
   if (rc) return rc;
   rc = gln::get_tmap(ctx, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)gln::BN, &tb);
   if (rc) return rc;
-  if (residual_dtype == CARE_F32)
-    return gln::launch<true>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, out32, M, N, K, s);
-  return gln::launch<false>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, nullptr, M, N, K, s);
+  if (residual_dtype == CARE_F32) {
+    if (mc) return gln::launch<true, true>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, out32, M, N, K, s);
+    return gln::launch<true, false>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, out32, M, N, K, s);
+  }
+  if (mc) return gln::launch<false, true>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, nullptr, M, N, K, s);
+  return gln::launch<false, false>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, nullptr, M, N, K, s);
 }

@@ -98,6 +98,8 @@ int care_ctx_set_early_exit(care_ctx* ctx, const int32_t* counter, int target);
 int care_ctx_set_option(care_ctx* ctx, const char* name, int value);
 /* "pdl": 1 (default) = the kernels of a decode step are launched with programmatic stream serialization: kernel
  * N+1 is scheduled while kernel N drains, runs its prologue and blocks in griddepcontrol.wait until N has completed.
+ * "gemm_ln_multicast": 1 = care_gemm_add_ln fetches the A tile once per cluster and multicasts it (0, the default:
+ * every CTA loads it; measured neutral - the mainloop is bound by shared-memory bandwidth, not by L2).
  * "fuse_info": 1 = the beam kernel also writes the next step's live-slot records (0, the default: a kernel of its
  * own before the self-attention; measured neutral to slightly slower when fused). */
 /* "vocab_2sm": 1 (default) = the fused vocabulary kernel runs on CTA pairs when the shape has at least two

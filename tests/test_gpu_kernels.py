@@ -343,14 +343,16 @@ def test_embed_ln_and_add_ln(env, dt, T):
     assert (out.float() - ref).abs().max().item() < tol * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("multicast", [0, 1])
 @pytest.mark.parametrize("resid32", [False, True])
 @pytest.mark.parametrize("M,N,K", [(2560, 1024, 1024), (20480, 1024, 4096), (333, 1024, 1024), (5, 512, 512),
                                    (1000, 768, 3072), (4097, 512, 2048), (128, 1024, 64), (20480, 1024, 1024)])
-def test_gemm_add_ln_fused(env, M, N, K, resid32):
+def test_gemm_add_ln_fused(env, M, N, K, resid32, multicast):
     """care_gemm_add_ln (cluster of N/256 CTAs per row block, statistics through distributed shared memory)
     against fp32 torch: layer_norm(A W^T + bias + residual) on the same 16-bit operands; and against the
     unfused care_gemm + care_add_ln pair."""
     lib, h, L = env
+    L.check(lib.care_ctx_set_option(h, b"gemm_ln_multicast", multicast), "option")   # A tile multicast in the cluster
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     A = torch.randn(M, K, device="cuda", generator=g).to(TH)
     W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(TH)
@@ -367,6 +369,7 @@ def test_gemm_add_ln_fused(env, M, N, K, resid32):
                                      F32 if resid32 else H16, gamma.data_ptr(), beta.data_ptr(), eps, out16.data_ptr(),
                                      None if out32 is None else out32.data_ptr(), M, N, K, _stream()), "gemm_add_ln")
     torch.cuda.synchronize()
+    L.check(lib.care_ctx_set_option(h, b"gemm_ln_multicast", 0), "option")
     ref = torch.nn.functional.layer_norm(A.float() @ W.float().t() + bias + res.float(), (N,), gamma, beta, eps)
     tol = 2e-3 if TH == torch.float16 else 1.6e-2      # one 16-bit rounding of an O(1..4) value
     assert torch.isfinite(out16.float()).all()
