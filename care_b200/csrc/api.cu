@@ -113,6 +113,7 @@ int care_ctx_create(care_ctx** out, int device) {
   if (const char* e = getenv("CARE_B200_DEBUG")) c->debug = atoi(e);
   if (const char* e = getenv("CARE_B200_PDL")) c->pdl = atoi(e) != 0;
   if (const char* e = getenv("CARE_B200_GEMM_LN_MC")) c->gemm_ln_multicast = atoi(e) != 0;
+  if (const char* e = getenv("CARE_B200_GEMM_LN_PAIR")) c->gemm_ln_pair = atoi(e);
   if (const char* e = getenv("CARE_B200_FUSE_INFO")) c->fuse_info = atoi(e) != 0;
   if (const char* path = getenv("CARE_B200_GEMM_CHOICE_FILE")) {   // GEMM variants picked by an earlier run
     if (FILE* f = fopen(path, "r")) {
@@ -172,6 +173,7 @@ int care_ctx_share_tuning(care_ctx* ctx, care_ctx* other) {
   ctx->tuning = other->tuning;
   ctx->gemm_2sm = other->gemm_2sm;
   ctx->gemm_bn = other->gemm_bn;
+  ctx->gemm_ln_pair = other->gemm_ln_pair;
   return 0;
 }
 
@@ -214,6 +216,12 @@ int care_ctx_set_option(care_ctx* ctx, const char* name, int value) {
   }
   if (strcmp(name, "gemm_ln_multicast") == 0) {
     ctx->gemm_ln_multicast = value != 0;
+    return 0;
+  }
+  if (strcmp(name, "gemm_ln_pair") == 0) {
+    ctx->gemm_ln_pair = value;
+    std::lock_guard<std::mutex> g(ctx->tuning->mu);
+    ctx->tuning->choice.clear();
     return 0;
   }
   if (strcmp(name, "fuse_info") == 0) {

@@ -152,6 +152,10 @@ struct care_ctx {
   // shared-memory bandwidth (48 KB of operands read by the MMAs plus 48 KB written by TMA per 512 MMA cycles = 192 B/clk
   // against 128 B/clk), not by L2; only CTA pairs (cta_group::2, half the B operand per SM) lift that
   int gemm_ln_multicast = 0;
+  // care_gemm_add_ln on CTA pairs (gemm_add_ln_pair_kernel: clusters of 2 * d/256 CTAs over 256-row blocks): 0 = single-CTA
+  // clusters only, 1 = pairs whenever such a cluster fits the device, 2 (default) = pick per (M, N, K) by timing both once
+  // (option "gemm_ln_pair", env CARE_B200_GEMM_LN_PAIR)
+  int gemm_ln_pair = 2;
   int vocab_2sm = 1;   // fused vocabulary kernel on CTA pairs when the shape has >= two waves of pair tiles
   // per-shape GEMM variant picks; contexts that must launch identical kernels (the lanes of one decode) share one
   // table (care_ctx_share_tuning)

@@ -145,6 +145,154 @@ __device__ __forceinline__ void xp_store_rows(uint8_t* xp, int lane, const uint4
   }
 }
 
+// One 128-row x 256-column accumulator tile through the two epilogue passes (see the file header).  Called by the
+// 8 epilogue warps of a CTA: thread = (row, column half grp).  ln_rank / ln_size: which of the row's d / 256 column
+// blocks this CTA holds; the CTA holding block j is cluster rank j * peer_stride + peer_offset.
+struct EpiCtx {
+  const uint8_t* res_b;   // residual, already offset to this thread group's first column
+  int64_t res_ld;         // bytes
+  uint8_t* out16_b;
+  uint8_t* out32_b;
+  const float* bias_s;
+  const float* gamma_s;
+  const float* beta_s;
+  uint8_t* xp;            // this warp's transposition block
+  int M, N;
+  float eps;
+  uint32_t ln_rank, ln_size, peer_stride, peer_offset;
+};
+
+template <bool R32>
+__device__ __forceinline__ void ln_epilogue_tile(const EpiCtx& e, uint32_t taddr, int row0, uint32_t tfull, uint32_t stats,
+                                                 uint32_t table_addr, uint8_t* table_gen, uint32_t aph, int grp, int lane,
+                                                 uint32_t my_row) {
+  constexpr int HALF = BN / 2;
+  constexpr int NSUB = R32 ? 2 : 1;   // 64-byte sub-blocks of the residual per 32-column chunk
+  const uint8_t* res_b = e.res_b;
+  const int64_t res_ld = e.res_ld;
+  uint8_t* out16_b = e.out16_b;
+  uint8_t* out32_b = e.out32_b;
+  const float* bias_s = e.bias_s;
+  const float* gamma_s = e.gamma_s;
+  const float* beta_s = e.beta_s;
+  uint8_t* xp = e.xp;
+  const int M = e.M, N = e.N;
+  const float eps = e.eps;
+  const uint32_t ln_rank = e.ln_rank, ln_size = e.ln_size, peer_stride = e.peer_stride, peer_offset = e.peer_offset;
+  uint4 gn[NSUB][4];
+#pragma unroll
+  for (int sb = 0; sb < NSUB; ++sb) ldg_block(res_b + sb * 64, res_ld, row0, M, lane, gn[sb]);
+  // the rest of this thread's residual row slice -> L2 while the MMAs of the tile still run (the row was usually
+  // evicted by the attention kernel that ran in between); one 128-byte line per request
+  if (row0 + lane < M) {
+    const uint8_t* rp = res_b + (int64_t)(row0 + lane) * res_ld;
+#pragma unroll
+    for (int off = 128; off < HALF * (R32 ? 4 : 2); off += 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + off));
+  }
+  mbar_wait(tfull, aph);
+  tc_fence_after();
+  // ---- pass 1: v = acc + bias + residual -> TMEM; row statistics ----
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < HALF / 32; ++c) {
+    uint4 rr[NSUB][4];
+#pragma unroll
+    for (int sb = 0; sb < NSUB; ++sb) xp_to_rows(xp, lane, gn[sb], rr[sb]);
+    if (c + 1 < HALF / 32) {
+#pragma unroll
+      for (int sb = 0; sb < NSUB; ++sb)
+        ldg_block(res_b + (c + 1) * 32 * (R32 ? 4 : 2) + sb * 64, res_ld, row0, M, lane, gn[sb]);
+    }
+    uint32_t v[32];
+    tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 bq = *reinterpret_cast<const float4*>(bias_s + c * 32 + q * 4);
+      float r0, r1, r2, r3;
+      if constexpr (R32) {
+        const uint4 u = rr[q >> 2][q & 3];
+        r0 = __uint_as_float(u.x); r1 = __uint_as_float(u.y); r2 = __uint_as_float(u.z); r3 = __uint_as_float(u.w);
+      } else {
+        const uint4 u = rr[0][q >> 1];
+        const uint32_t w0 = (q & 1) ? u.z : u.x, w1 = (q & 1) ? u.w : u.y;
+        r0 = h16_lo(w0); r1 = h16_hi(w0); r2 = h16_lo(w1); r3 = h16_hi(w1);
+      }
+      const float x0 = __uint_as_float(v[4 * q]) + bq.x + r0;
+      const float x1 = __uint_as_float(v[4 * q + 1]) + bq.y + r1;
+      const float x2 = __uint_as_float(v[4 * q + 2]) + bq.z + r2;
+      const float x3 = __uint_as_float(v[4 * q + 3]) + bq.w + r3;
+      s1 += (x0 + x1) + (x2 + x3);
+      s2 = fmaf(x0, x0, s2); s2 = fmaf(x1, x1, s2); s2 = fmaf(x2, x2, s2); s2 = fmaf(x3, x3, s2);
+      v[4 * q] = __float_as_uint(x0); v[4 * q + 1] = __float_as_uint(x1);
+      v[4 * q + 2] = __float_as_uint(x2); v[4 * q + 3] = __float_as_uint(x3);
+    }
+    tmem_st32(taddr + c * 32, v);
+  }
+  tmem_st_wait();
+  // ---- exchange the row statistics: the two column halves of this CTA through local slots and a named
+  // barrier, then the CTA's 256-column partial to every peer CTA (st.async, counted on the peer's mbarrier) ----
+  uint8_t* table = table_gen;
+  *reinterpret_cast<float2*>(table + grp * STAT_SLOT + my_row * 8) = make_float2(s1, s2);
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  {
+    const float2 o = *reinterpret_cast<const float2*>(table + (grp ^ 1) * STAT_SLOT + my_row * 8);
+    s1 += o.x;
+    s2 += o.y;
+  }
+  if (grp == 0) {
+    for (uint32_t dst = 0; dst < ln_size; ++dst) {
+      if (dst == ln_rank) continue;
+      const uint32_t slot = 2 + (ln_rank < dst ? ln_rank : ln_rank - 1);
+      const uint32_t local = table_addr + slot * STAT_SLOT + my_row * 8;
+      const uint32_t peer = dst * peer_stride + peer_offset;   // cluster rank of the CTA holding column block dst
+      st_async_f2(map_to_cta(local, peer), s1, s2, map_to_cta(stats, peer));
+    }
+  }
+  mbar_wait_cluster(stats, aph);
+  for (uint32_t slot = 2; slot < 1 + ln_size; ++slot) {
+    const float2 o = *reinterpret_cast<const float2*>(table + slot * STAT_SLOT + my_row * 8);
+    s1 += o.x;
+    s2 += o.y;
+  }
+  const float inv_n = 1.0f / (float)N;
+  const float mean = s1 * inv_n;
+  const float rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + eps);
+  // ---- pass 2: normalise, scale, store ----
+#pragma unroll 1
+  for (int c = 0; c < HALF / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld32(taddr + c * 32, v);
+    float y[32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 gq = *reinterpret_cast<const float4*>(gamma_s + c * 32 + q * 4);
+      const float4 eq = *reinterpret_cast<const float4*>(beta_s + c * 32 + q * 4);
+      y[4 * q] = fmaf((__uint_as_float(v[4 * q]) - mean) * rstd, gq.x, eq.x);
+      y[4 * q + 1] = fmaf((__uint_as_float(v[4 * q + 1]) - mean) * rstd, gq.y, eq.y);
+      y[4 * q + 2] = fmaf((__uint_as_float(v[4 * q + 2]) - mean) * rstd, gq.z, eq.z);
+      y[4 * q + 3] = fmaf((__uint_as_float(v[4 * q + 3]) - mean) * rstd, gq.w, eq.w);
+    }
+    uint4 pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      pk[j] = make_uint4(pack_h16(y[8 * j], y[8 * j + 1]), pack_h16(y[8 * j + 2], y[8 * j + 3]),
+                         pack_h16(y[8 * j + 4], y[8 * j + 5]), pack_h16(y[8 * j + 6], y[8 * j + 7]));
+    xp_store_rows(xp, lane, pk, out16_b + c * 64, (int64_t)N * 2, row0, M);
+    if constexpr (R32) {
+#pragma unroll
+      for (int sb = 0; sb < 2; ++sb) {
+        uint4 pf[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          pf[j] = make_uint4(__float_as_uint(y[16 * sb + 4 * j]), __float_as_uint(y[16 * sb + 4 * j + 1]),
+                             __float_as_uint(y[16 * sb + 4 * j + 2]), __float_as_uint(y[16 * sb + 4 * j + 3]));
+        xp_store_rows(xp, lane, pf, out32_b + c * 128 + sb * 64, (int64_t)N * 4, row0, M);
+      }
+    }
+  }
+}
+
 // MC (A/B switch, off by default): the A tile (the same 128 rows for every CTA of the cluster) is fetched ONCE per
 // cluster: CTA r loads rows [r * 128 / CN, (r + 1) * 128 / CN) and multicasts them into all CN shared memories (36 KB
 // instead of 48 KB from L2 per k-block and CTA at CN = 4); a stage is refilled only when the MMA threads of ALL the CTAs
@@ -284,7 +432,6 @@ gemm_add_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     const uint8_t* res_b = reinterpret_cast<const uint8_t*>(residual) + (int64_t)col_first * (R32 ? 4 : 2);
     uint8_t* out16_b = reinterpret_cast<uint8_t*>(out16) + (int64_t)col_first * 2;
     uint8_t* out32_b = reinterpret_cast<uint8_t*>(out32) + (int64_t)col_first * 4;
-    constexpr int NSUB = R32 ? 2 : 1;   // 64-byte sub-blocks of the residual per 32-column chunk
     const uint32_t my_row = (uint32_t)(ew * 32 + lane);
     uint32_t tcount = 0;
     for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters, ++tcount) {
@@ -292,117 +439,9 @@ gemm_add_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       const int row0 = m_blk * BLOCK_M + ew * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + grp * HALF;
       if (warp == 4 && lane == 0) mbar_expect_tx(stats_bar(acc), (csize - 1) * STAT_SLOT);
-      uint4 gn[NSUB][4];
-#pragma unroll
-      for (int sb = 0; sb < NSUB; ++sb) ldg_block(res_b + sb * 64, res_ld, row0, M, lane, gn[sb]);
-      // the rest of this thread's residual row slice -> L2 while the MMAs of the tile still run (the row was usually
-      // evicted by the attention kernel that ran in between); one 128-byte line per request
-      if (row0 + lane < M) {
-        const uint8_t* rp = res_b + (int64_t)(row0 + lane) * res_ld;
-#pragma unroll
-        for (int off = 128; off < HALF * (R32 ? 4 : 2); off += 128)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + off));
-      }
-      mbar_wait(tfull_bar(acc), aph);
-      tc_fence_after();
-      // ---- pass 1: v = acc + bias + residual -> TMEM; row statistics ----
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < HALF / 32; ++c) {
-        uint4 rr[NSUB][4];
-#pragma unroll
-        for (int sb = 0; sb < NSUB; ++sb) xp_to_rows(xp, lane, gn[sb], rr[sb]);
-        if (c + 1 < HALF / 32) {
-#pragma unroll
-          for (int sb = 0; sb < NSUB; ++sb)
-            ldg_block(res_b + (c + 1) * 32 * (R32 ? 4 : 2) + sb * 64, res_ld, row0, M, lane, gn[sb]);
-        }
-        uint32_t v[32];
-        tmem_ld32(taddr + c * 32, v);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 bq = *reinterpret_cast<const float4*>(bias_s + c * 32 + q * 4);
-          float r0, r1, r2, r3;
-          if constexpr (R32) {
-            const uint4 u = rr[q >> 2][q & 3];
-            r0 = __uint_as_float(u.x); r1 = __uint_as_float(u.y); r2 = __uint_as_float(u.z); r3 = __uint_as_float(u.w);
-          } else {
-            const uint4 u = rr[0][q >> 1];
-            const uint32_t w0 = (q & 1) ? u.z : u.x, w1 = (q & 1) ? u.w : u.y;
-            r0 = h16_lo(w0); r1 = h16_hi(w0); r2 = h16_lo(w1); r3 = h16_hi(w1);
-          }
-          const float x0 = __uint_as_float(v[4 * q]) + bq.x + r0;
-          const float x1 = __uint_as_float(v[4 * q + 1]) + bq.y + r1;
-          const float x2 = __uint_as_float(v[4 * q + 2]) + bq.z + r2;
-          const float x3 = __uint_as_float(v[4 * q + 3]) + bq.w + r3;
-          s1 += (x0 + x1) + (x2 + x3);
-          s2 = fmaf(x0, x0, s2); s2 = fmaf(x1, x1, s2); s2 = fmaf(x2, x2, s2); s2 = fmaf(x3, x3, s2);
-          v[4 * q] = __float_as_uint(x0); v[4 * q + 1] = __float_as_uint(x1);
-          v[4 * q + 2] = __float_as_uint(x2); v[4 * q + 3] = __float_as_uint(x3);
-        }
-        tmem_st32(taddr + c * 32, v);
-      }
-      tmem_st_wait();
-      // ---- exchange the row statistics: the two column halves of this CTA through local slots and a named
-      // barrier, then the CTA's 256-column partial to every peer CTA (st.async, counted on the peer's mbarrier) ----
-      uint8_t* table = smem_gen + (stats_base - smem_base) + acc * N_SLOTS * STAT_SLOT;
-      *reinterpret_cast<float2*>(table + grp * STAT_SLOT + my_row * 8) = make_float2(s1, s2);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      {
-        const float2 o = *reinterpret_cast<const float2*>(table + (grp ^ 1) * STAT_SLOT + my_row * 8);
-        s1 += o.x;
-        s2 += o.y;
-      }
-      if (grp == 0) {
-        for (uint32_t dst = 0; dst < csize; ++dst) {
-          if (dst == crank) continue;
-          const uint32_t slot = 2 + (crank < dst ? crank : crank - 1);
-          const uint32_t local = stats_base + (acc * N_SLOTS + slot) * STAT_SLOT + my_row * 8;
-          st_async_f2(map_to_cta(local, dst), s1, s2, map_to_cta(stats_bar(acc), dst));
-        }
-      }
-      mbar_wait_cluster(stats_bar(acc), aph);
-      for (uint32_t slot = 2; slot < 1 + csize; ++slot) {
-        const float2 o = *reinterpret_cast<const float2*>(table + slot * STAT_SLOT + my_row * 8);
-        s1 += o.x;
-        s2 += o.y;
-      }
-      const float inv_n = 1.0f / (float)N;
-      const float mean = s1 * inv_n;
-      const float rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + eps);
-      // ---- pass 2: normalise, scale, store ----
-#pragma unroll 1
-      for (int c = 0; c < HALF / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c * 32, v);
-        float y[32];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 gq = *reinterpret_cast<const float4*>(gamma_s + c * 32 + q * 4);
-          const float4 eq = *reinterpret_cast<const float4*>(beta_s + c * 32 + q * 4);
-          y[4 * q] = fmaf((__uint_as_float(v[4 * q]) - mean) * rstd, gq.x, eq.x);
-          y[4 * q + 1] = fmaf((__uint_as_float(v[4 * q + 1]) - mean) * rstd, gq.y, eq.y);
-          y[4 * q + 2] = fmaf((__uint_as_float(v[4 * q + 2]) - mean) * rstd, gq.z, eq.z);
-          y[4 * q + 3] = fmaf((__uint_as_float(v[4 * q + 3]) - mean) * rstd, gq.w, eq.w);
-        }
-        uint4 pk[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          pk[j] = make_uint4(pack_h16(y[8 * j], y[8 * j + 1]), pack_h16(y[8 * j + 2], y[8 * j + 3]),
-                             pack_h16(y[8 * j + 4], y[8 * j + 5]), pack_h16(y[8 * j + 6], y[8 * j + 7]));
-        xp_store_rows(xp, lane, pk, out16_b + c * 64, (int64_t)N * 2, row0, M);
-        if constexpr (R32) {
-#pragma unroll
-          for (int sb = 0; sb < 2; ++sb) {
-            uint4 pf[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              pf[j] = make_uint4(__float_as_uint(y[16 * sb + 4 * j]), __float_as_uint(y[16 * sb + 4 * j + 1]),
-                                 __float_as_uint(y[16 * sb + 4 * j + 2]), __float_as_uint(y[16 * sb + 4 * j + 3]));
-            xp_store_rows(xp, lane, pf, out32_b + c * 128 + sb * 64, (int64_t)N * 4, row0, M);
-          }
-        }
-      }
+      EpiCtx ectx{res_b, res_ld, out16_b, out32_b, bias_s, gamma_s, beta_s, xp, M, N, eps, crank, csize, 1u, 0u};
+      ln_epilogue_tile<R32>(ectx, taddr, row0, tfull_bar(acc), stats_bar(acc), stats_base + acc * N_SLOTS * STAT_SLOT,
+                            smem_gen + (stats_base - smem_base) + acc * N_SLOTS * STAT_SLOT, aph, grp, lane, my_row);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -419,6 +458,207 @@ gemm_add_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   __syncwarp();
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same operation on CTA PAIRS (tcgen05.mma.cta_group::2).  The single-CTA mainloop above moves 48 KB of operands
+// into an SM per k-block and is bound by shared-memory bandwidth (TMA fill + MMA operand reads); as in
+// gemm_tcgen05_2sm.cu a pair of SMs shares one 256-row x 256-column tile, each CTA staging its own 128 rows of A and
+// only HALF of the W tile (32 KB per k-block).  A cluster is now 2 * d/256 CTAs = d/256 pairs over one 256-row block:
+// pair j (cluster ranks 2j, 2j+1) holds columns [256 j, 256 j + 256); CTA 2j + h holds rows [128 h, 128 h + 128) of
+// the block in its own tensor memory, so its epilogue is the one above, with the row statistics exchanged between
+// the CTAs of equal h (ranks h, h + 2, h + 4, ...).
+// Barriers: full[s] in the pair's leader (even rank; both CTAs' TMA bytes complete there), empty[s] / tfull[a] in both
+// CTAs (multicast tcgen05.commit from the leader's MMA thread), tempty[a] in the leader (16 arrivals: 8 epilogue
+// warps of each CTA), stats[a] per CTA as above.
+constexpr int P_STAGES = 6;
+constexpr int P_B_BYTES = (BN / 2) * BLOCK_K * 2;
+constexpr int P_STAGE_BYTES = A_BYTES + P_B_BYTES;   // 32 KB per CTA and k-block
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 8 * XP_BYTES + STATS_BYTES + PARAM_BYTES + BAR_BYTES + 1024;
+static_assert(P_SMEM_BYTES <= 227 * 1024, "shared memory budget (pair kernel)");
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the lowest CTA-rank bit of a shared-window address -> pair leader
+
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mma_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_pair_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
+}
+
+template <bool R32>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_add_ln_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                        const float* __restrict__ bias, const void* __restrict__ residual, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, float eps, h16* __restrict__ out16, float* __restrict__ out32,
+                        int M, int N, int K, const EarlyExit ee) {
+  if (all_done(ee)) return;   // uniform over the grid
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - raw_addr);
+  const uint32_t xp_base = smem_base + P_STAGES * P_STAGE_BYTES;
+  const uint32_t stats_base = xp_base + 8 * XP_BYTES;
+  const uint32_t param_base = stats_base + STATS_BYTES;
+  const uint32_t bar_base = param_base + PARAM_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (P_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * P_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * P_STAGES + 2 + a); };
+  auto stats_bar = [&](int p) { return bar_base + 8u * (2 * P_STAGES + 4 + p); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * P_STAGES + 6);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  float* param_gen = reinterpret_cast<float*>(smem_gen + (param_base - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
+  const uint32_t half = crank & 1u;        // which 128 rows of the pair's 256
+  const int n_blk = (int)(crank >> 1);     // the pair's column block
+  const uint32_t cn = csize >> 1;
+  const int cluster_id = blockIdx.x / csize, n_clusters = gridDim.x / csize;
+  constexpr int PAIR_M = 2 * BLOCK_M;
+  const int m_tiles = (M + PAIR_M - 1) / PAIR_M;
+  const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  const uint16_t pair_mask = (uint16_t)(3u << (crank & ~1u));
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < P_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4 * EPI_WARPS);   // 8 epilogue warps of each CTA of the pair
+      mbar_init(stats_bar(a), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < BN; i += THREADS) {
+    const int col = n_blk * BN + i;
+    param_gen[i] = (bias != nullptr && col < N) ? __ldg(bias + col) : 0.f;
+    param_gen[BN + i] = col < N ? __ldg(gamma + col) : 0.f;
+    param_gen[2 * BN + i] = col < N ? __ldg(beta + col) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  // barriers of every CTA of the cluster initialised and tensor memory allocated before any peer signals into them
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (every CTA): own 128 rows of A, own half of the pair's W tile =====
+      uint32_t it = 0;
+      for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters) {
+        const int a_row = m_blk * PAIR_M + (int)half * BLOCK_M;
+        const int b_row = n_blk * BN + (int)half * (BN / 2);
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % P_STAGES;
+          const uint32_t ph = (it / P_STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          if (half == 0) mbar_expect_tx(full_bar(s), 2 * P_STAGE_BYTES);   // both CTAs' bytes land on the leader
+          const uint32_t a_dst = smem_base + s * P_STAGE_BYTES;
+          tma_load_2d_pair(a_dst, &tma_a, full_bar(s), kb * BLOCK_K, a_row);
+          tma_load_2d_pair(a_dst + A_BYTES, &tma_b, full_bar(s), kb * BLOCK_K, b_row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && half == 0) {
+      // ===== MMA issuer (pair leader): M = 256 across the pair, N = 256, K = 16 =====
+      constexpr uint32_t idesc = instr_desc_bf16(PAIR_M, BN);
+      uint32_t it = 0, tcount = 0;
+      for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters, ++tcount) {
+        const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % P_STAGES;
+          const uint32_t ph = (it / P_STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + s * P_STAGE_BYTES;
+          const uint64_t adesc = sw128_kmajor_desc(a_addr);
+          const uint64_t bdesc = sw128_kmajor_desc(a_addr + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            mma_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          commit_pair(empty_bar(s), pair_mask);
+        }
+        commit_pair(tfull_bar(acc), pair_mask);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (every CTA): its 128 rows x 256 columns, exactly as in the single-CTA kernel =====
+    const int grp = (warp - 4) >> 2;
+    const int ew = (warp - 4) & 3;
+    constexpr int HALF = BN / 2;
+    uint8_t* xp = smem_gen + (xp_base - smem_base) + (warp - 4) * XP_BYTES;
+    const float* bias_s = param_gen + grp * HALF;
+    const float* gamma_s = param_gen + BN + grp * HALF;
+    const float* beta_s = param_gen + 2 * BN + grp * HALF;
+    const int64_t res_ld = (int64_t)N * (R32 ? 4 : 2);
+    const int col_first = n_blk * BN + grp * HALF;
+    const uint8_t* res_b = reinterpret_cast<const uint8_t*>(residual) + (int64_t)col_first * (R32 ? 4 : 2);
+    uint8_t* out16_b = reinterpret_cast<uint8_t*>(out16) + (int64_t)col_first * 2;
+    uint8_t* out32_b = reinterpret_cast<uint8_t*>(out32) + (int64_t)col_first * 4;
+    const uint32_t my_row = (uint32_t)(ew * 32 + lane);
+    uint32_t tcount = 0;
+    for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters, ++tcount) {
+      const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+      const int row0 = m_blk * PAIR_M + (int)half * BLOCK_M + ew * 32;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + grp * HALF;
+      if (warp == 4 && lane == 0) mbar_expect_tx(stats_bar(acc), (cn - 1) * STAT_SLOT);
+      EpiCtx ectx{res_b, res_ld, out16_b, out32_b, bias_s, gamma_s, beta_s, xp, M, N, eps, (uint32_t)n_blk, cn, 2u, half};
+      ln_epilogue_tile<R32>(ectx, taddr, row0, tfull_bar(acc), stats_bar(acc), stats_base + acc * N_SLOTS * STAT_SLOT,
+                            smem_gen + (stats_base - smem_base) + acc * N_SLOTS * STAT_SLOT, aph, grp, lane, my_row);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_pair_leader(tempty_bar(acc));   // local for the leader, remote for its peer
+    }
+  }
+
+  // no CTA leaves (or frees tensor memory) while a peer may still send statistics or commits into it
+  tc_fence_before();
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
 }
 
 static int get_tmap(care_ctx* ctx, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
@@ -472,6 +712,81 @@ static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, c
   return 0;
 }
 
+template <bool R32>
+static int launch_pair(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const void* residual,
+                       const float* gamma, const float* beta, float eps, void* out16, float* out32, int M, int N, int K,
+                       cudaStream_t stream) {
+  static bool configured_all[64] = {false};
+  static int max_clusters_all[64][MAX_CN + 1] = {{0}};   // -1: a cluster of 2 * cn CTAs does not fit this device
+  auto kern = gemm_add_ln_pair_kernel<R32>;
+  const int cn = N / BN;
+  if (!configured_all[ctx->device & 63]) {
+    CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+    configured_all[ctx->device & 63] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)(2 * cn);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.blockDim = dim3(THREADS, 1, 1);
+  cfg.dynamicSmemBytes = P_SMEM_BYTES;
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = ctx->pdl ? 2 : 1;
+  int& max_clusters = max_clusters_all[ctx->device & 63][cn];
+  if (max_clusters == 0) {
+    cfg.gridDim = dim3((unsigned)(2 * cn * (ctx->sm_count / (2 * cn))), 1, 1);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+      (void)cudaGetLastError();
+      n = -1;
+    }
+    max_clusters = n;
+  }
+  if (max_clusters < 0) return 1;   // caller falls back to the single-CTA clusters
+  const int m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int clusters = std::min(m_tiles, max_clusters);
+  cfg.gridDim = dim3((unsigned)(clusters * 2 * cn), 1, 1);
+  CARE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, bias, residual, gamma, beta, eps, reinterpret_cast<h16*>(out16), out32,
+                               M, N, K, early_exit_of(ctx)));
+  ctx->last_gemm = R32 ? "gemm_add_ln_pair_kernel<f32 residual>" : "gemm_add_ln_pair_kernel<h16 residual>";
+  CARE_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+// one launch of the variant `pair` (0: single-CTA clusters, 1: CTA pairs); returns 1 when the pair kernel cannot run
+static int run_variant(care_ctx* ctx, int pair, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                       const void* residual, int residual_dtype, const float* gamma, const float* beta, float eps,
+                       void* out16, float* out32, int M, int N, int K, cudaStream_t s) {
+  const int cn = N / BN;
+  CUtensorMap ta, tb;
+  if (pair) {
+    int rc = get_tmap(ctx, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BLOCK_M, &ta);
+    if (rc) return rc;
+    rc = get_tmap(ctx, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(BN / 2), &tb);
+    if (rc) return rc;
+    if (residual_dtype == CARE_F32)
+      return launch_pair<true>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, out32, M, N, K, s);
+    return launch_pair<false>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, nullptr, M, N, K, s);
+  }
+  // the A tile is multicast inside the cluster when its 128 rows split evenly over the CTAs (d = 512, 1024)
+  const bool mc = ctx->gemm_ln_multicast && (BLOCK_M % cn) == 0;
+  int rc = get_tmap(ctx, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, mc ? BLOCK_M / cn : BLOCK_M, &ta);
+  if (rc) return rc;
+  rc = get_tmap(ctx, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)BN, &tb);
+  if (rc) return rc;
+  if (residual_dtype == CARE_F32) {
+    if (mc) return launch<true, true>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, out32, M, N, K, s);
+    return launch<true, false>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, out32, M, N, K, s);
+  }
+  if (mc) return launch<false, true>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, nullptr, M, N, K, s);
+  return launch<false, false>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, nullptr, M, N, K, s);
+}
+
 }  // namespace gln
 }  // namespace care
 
@@ -492,18 +807,71 @@ extern "C" int care_gemm_add_ln(care_ctx* ctx, const void* A, int64_t lda, const
                    reinterpret_cast<uintptr_t>(out16) | reinterpret_cast<uintptr_t>(out32)) & 15) == 0,
                  "care_gemm_add_ln: pointers must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
-  const int cn = N / gln::BN;
-  // the A tile is multicast inside the cluster when its 128 rows split evenly over the CTAs (d = 512, 1024)
-  const bool mc = ctx->gemm_ln_multicast && (tc::BLOCK_M % cn) == 0;
-  CUtensorMap ta, tb;
-  int rc = gln::get_tmap(ctx, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, mc ? tc::BLOCK_M / cn : tc::BLOCK_M, &ta);
-  if (rc) return rc;
-  rc = gln::get_tmap(ctx, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)gln::BN, &tb);
-  if (rc) return rc;
-  if (residual_dtype == CARE_F32) {
-    if (mc) return gln::launch<true, true>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, out32, M, N, K, s);
-    return gln::launch<true, false>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, out32, M, N, K, s);
+  auto run = [&](int pair) {
+    return gln::run_variant(ctx, pair, A, lda, W, ldw, bias, residual, residual_dtype, gamma, beta, eps, out16, out32, M, N,
+                            K, s);
+  };
+  int pair = ctx->gemm_ln_pair;
+  if (pair == 2) {
+    // per-shape choice between the single-CTA clusters and the CTA-pair clusters, measured once (as care_gemm does)
+    const uint64_t key = (1ull << 63) ^ ((uint64_t)(uint32_t)M << 40) ^ ((uint64_t)(uint32_t)N << 20) ^
+                         ((uint64_t)(uint32_t)K << 1) ^ (uint64_t)(residual_dtype == CARE_F32 ? 1 : 0);
+    int choice = -1;
+    {
+      std::lock_guard<std::mutex> g(ctx->tuning->mu);
+      auto it = ctx->tuning->choice.find(key);
+      if (it != ctx->tuning->choice.end()) choice = it->second;
+    }
+    if (choice < 0) {
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(s, &cap);
+      if (cap != cudaStreamCaptureStatusNone) {
+        choice = M >= 2048 ? 1 : 0;   // cannot time inside a capture; not cached
+      } else {
+        float ms[2] = {0.f, 0.f};
+        bool ok = true;
+        cudaEvent_t e0, e1;
+        CARE_CUDA(cudaEventCreate(&e0));
+        CARE_CUDA(cudaEventCreate(&e1));
+        for (int v = 0; v < 2 && ok; ++v) {
+          for (int rep = 0; rep < 4; ++rep) {   // rep 0 = warm-up
+            if (rep == 1) cudaEventRecord(e0, s);
+            const int rc = run(v);
+            if (rc == 1) { ok = false; break; }
+            if (rc != 0) {
+              cudaEventDestroy(e0);
+              cudaEventDestroy(e1);
+              return rc;
+            }
+          }
+          if (!ok) break;
+          cudaEventRecord(e1, s);
+          cudaEventSynchronize(e1);
+          cudaEventElapsedTime(&ms[v], e0, e1);
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        choice = (ok && ms[1] < ms[0]) ? 1 : 0;
+        if (ctx->debug)
+          fprintf(stderr, "[care_b200] gemm_add_ln M=%d N=%d K=%d: single-CTA clusters %.3f ms, CTA pairs %.3f ms -> %s\n", M,
+                  N, K, ms[0] / 3.0f, ms[1] / 3.0f, choice ? "pairs" : "single");
+        {
+          std::lock_guard<std::mutex> g(ctx->tuning->mu);
+          ctx->tuning->choice[key] = choice;
+        }
+        if (const char* path = getenv("CARE_B200_GEMM_CHOICE_FILE")) {
+          if (FILE* f = fopen(path, "a")) {
+            fprintf(f, "%llu %d\n", (unsigned long long)key, choice);
+            fclose(f);
+          }
+        }
+      }
+    }
+    pair = choice;
   }
-  if (mc) return gln::launch<false, true>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, nullptr, M, N, K, s);
-  return gln::launch<false, false>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, nullptr, M, N, K, s);
+  if (pair == 1) {
+    const int rc = run(1);
+    if (rc != 1) return rc;
+  }
+  return run(0);
 }

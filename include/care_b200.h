@@ -100,6 +100,9 @@ int care_ctx_set_option(care_ctx* ctx, const char* name, int value);
  * N+1 is scheduled while kernel N drains, runs its prologue and blocks in griddepcontrol.wait until N has completed.
  * "gemm_ln_multicast": 1 = care_gemm_add_ln fetches the A tile once per cluster and multicasts it (0, the default:
  * every CTA loads it; measured neutral - the mainloop is bound by shared-memory bandwidth, not by L2).
+ * "gemm_ln_pair": care_gemm_add_ln on CTA pairs (tcgen05 cta_group::2; clusters of 2 * N/256 CTAs over 256-row blocks):
+ * 0 = single-CTA clusters only, 1 = pairs whenever such a cluster fits the device, 2 (default) = choose per (M, N, K) by
+ * timing both once, as "gemm_2sm" does.
  * "fuse_info": 1 = the beam kernel also writes the next step's live-slot records (0, the default: a kernel of its
  * own before the self-attention; measured neutral to slightly slower when fused). */
 /* "vocab_2sm": 1 (default) = the fused vocabulary kernel runs on CTA pairs when the shape has at least two

@@ -31,7 +31,9 @@ def main():
     h = ctypes.c_void_p()
     _lib.check(lib.care_ctx_create(ctypes.byref(h), 0), "ctx")
     st = torch.cuda.current_stream().cuda_stream
-    for M, N, K in [(20480, 1024, 1024), (20480, 1024, 4096), (2560, 1024, 1024), (2560, 1024, 4096), (10240, 1024, 1024)]:
+    for M, N, K in [(20480, 1024, 1024), (20480, 1024, 4096), (2560, 1024, 1024), (2560, 1024, 4096), (10240, 1024, 1024),
+                    (20480, 512, 512), (20480, 768, 768),
+                    (20480, 1024, 64), (20480, 1024, 256), (2560, 1024, 64)]   # K = 64: the epilogue alone:
         nbuf = 6 if M > 4096 else 24
         A = [torch.randn(M, K, device="cuda").half() for _ in range(nbuf)]
         res = [torch.randn(M, N, device="cuda").half() for _ in range(nbuf)]
@@ -63,9 +65,12 @@ def main():
 
         unfused(0)
         flops = 2.0 * M * N * K
-        for name, fn in (("gemm + add_ln", unfused), ("fused (16-bit residual)", fused), ("fused (fp32 residual)", fused32)):
+        for name, fn, pair in (("gemm + add_ln", unfused, 0), ("fused (16-bit residual)", fused, 0),
+                               ("fused, CTA pairs (16-bit residual)", fused, 1), ("fused (fp32 residual)", fused32, 0),
+                               ("fused, CTA pairs (fp32 residual)", fused32, 1)):
+            _lib.check(lib.care_ctx_set_option(h, b"gemm_ln_pair", pair), "option")
             ms = timed(fn)
-            print("M=%5d N=%d K=%d  %-26s %.3f ms  %.0f TFLOP/s" % (M, N, K, name, ms, flops / ms / 1e9), flush=True)
+            print("M=%5d N=%d K=%d  %-36s %.3f ms  %.0f TFLOP/s" % (M, N, K, name, ms, flops / ms / 1e9), flush=True)
 
 
 if __name__ == "__main__":

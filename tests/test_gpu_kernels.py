@@ -343,16 +343,19 @@ def test_embed_ln_and_add_ln(env, dt, T):
     assert (out.float() - ref).abs().max().item() < tol * ref.abs().max().item()
 
 
-@pytest.mark.parametrize("multicast", [0, 1])
+@pytest.mark.parametrize("variant", ["single", "multicast", "pair"])
 @pytest.mark.parametrize("resid32", [False, True])
 @pytest.mark.parametrize("M,N,K", [(2560, 1024, 1024), (20480, 1024, 4096), (333, 1024, 1024), (5, 512, 512),
-                                   (1000, 768, 3072), (4097, 512, 2048), (128, 1024, 64), (20480, 1024, 1024)])
-def test_gemm_add_ln_fused(env, M, N, K, resid32, multicast):
-    """care_gemm_add_ln (cluster of N/256 CTAs per row block, statistics through distributed shared memory)
-    against fp32 torch: layer_norm(A W^T + bias + residual) on the same 16-bit operands; and against the
-    unfused care_gemm + care_add_ln pair."""
+                                   (1000, 768, 3072), (4097, 512, 2048), (128, 1024, 64), (20480, 1024, 1024),
+                                   (257, 1024, 512), (9999, 768, 768)])
+def test_gemm_add_ln_fused(env, M, N, K, resid32, variant):
+    """care_gemm_add_ln (cluster of N/256 CTAs per 128-row block, or of N/256 CTA pairs per 256-row block; statistics
+    through distributed shared memory) against fp32 torch: layer_norm(A W^T + bias + residual) on the same 16-bit
+    operands; and against the unfused care_gemm + care_add_ln pair."""
     lib, h, L = env
+    multicast = 1 if variant == "multicast" else 0
     L.check(lib.care_ctx_set_option(h, b"gemm_ln_multicast", multicast), "option")   # A tile multicast in the cluster
+    L.check(lib.care_ctx_set_option(h, b"gemm_ln_pair", 1 if variant == "pair" else 0), "option")
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     A = torch.randn(M, K, device="cuda", generator=g).to(TH)
     W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(TH)
@@ -369,7 +372,10 @@ def test_gemm_add_ln_fused(env, M, N, K, resid32, multicast):
                                      F32 if resid32 else H16, gamma.data_ptr(), beta.data_ptr(), eps, out16.data_ptr(),
                                      None if out32 is None else out32.data_ptr(), M, N, K, _stream()), "gemm_add_ln")
     torch.cuda.synchronize()
+    ran = lib.care_ctx_last_kernel(h, b"gemm").decode()
     L.check(lib.care_ctx_set_option(h, b"gemm_ln_multicast", 0), "option")
+    L.check(lib.care_ctx_set_option(h, b"gemm_ln_pair", 2), "option")
+    assert ("pair" in ran) == (variant == "pair"), ran
     ref = torch.nn.functional.layer_norm(A.float() @ W.float().t() + bias + res.float(), (N,), gamma, beta, eps)
     tol = 2e-3 if TH == torch.float16 else 1.6e-2      # one 16-bit rounding of an O(1..4) value
     assert torch.isfinite(out16.float()).all()
