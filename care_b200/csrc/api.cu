@@ -113,6 +113,9 @@ int care_ctx_create(care_ctx** out, int device) {
   if (const char* e = getenv("CARE_B200_DEBUG")) c->debug = atoi(e);
   if (const char* e = getenv("CARE_B200_PDL")) c->pdl = atoi(e) != 0;
   if (const char* e = getenv("CARE_B200_GEMM_LN_MC")) c->gemm_ln_multicast = atoi(e) != 0;
+  if (const char* e = getenv("CARE_B200_VOCAB_SPLIT")) c->vocab_split = atoi(e);
+  if (const char* e = getenv("CARE_B200_VOCAB_SPLIT_TILES")) c->vocab_split_tiles = atoi(e);
+  if (const char* e = getenv("CARE_B200_L2_HINTS")) c->l2_hints = atoi(e);
   if (const char* e = getenv("CARE_B200_GEMM_LN_PAIR")) c->gemm_ln_pair = atoi(e);
   if (const char* e = getenv("CARE_B200_FUSE_INFO")) c->fuse_info = atoi(e) != 0;
   if (const char* path = getenv("CARE_B200_GEMM_CHOICE_FILE")) {   // GEMM variants picked by an earlier run
@@ -216,6 +219,18 @@ int care_ctx_set_option(care_ctx* ctx, const char* name, int value) {
   }
   if (strcmp(name, "gemm_ln_multicast") == 0) {
     ctx->gemm_ln_multicast = value != 0;
+    return 0;
+  }
+  if (strcmp(name, "vocab_split") == 0) {
+    ctx->vocab_split = value;
+    return 0;
+  }
+  if (strcmp(name, "vocab_split_tiles") == 0) {
+    ctx->vocab_split_tiles = value;
+    return 0;
+  }
+  if (strcmp(name, "l2_hints") == 0) {
+    ctx->l2_hints = value;
     return 0;
   }
   if (strcmp(name, "gemm_ln_pair") == 0) {

@@ -45,6 +45,7 @@ struct Params {
   unsigned long long* row_counter;   // self: statistics, K/V cache rows read per video (head 0 counts)
   h16* out;       // [R, d]
   int n_items;              // B * H
+  int l2_hints;             // ctx->l2_hints (bit 1: K/V tiles and cache rows are loaded evict_first)
 };
 
 
@@ -245,11 +246,12 @@ attn_mma_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const uint32_t bytes = (uint32_t)n_keys * 128u;
     mbar_expect_tx(bar_k, bytes);
+    const uint64_t pol_kv = l2_policy((p.l2_hints & 2) ? 2 : 0);
     if (SELF) tma_load_3d(k_s, &tmap, bar_k, p.k_col + h * DH, v * K, 0);
-    else tma_load_2d(k_s, &tmap, bar_k, p.k_col + h * DH, v * p.Lm);
+    else tma_load_2d_hint(k_s, &tmap, bar_k, p.k_col + h * DH, v * p.Lm, pol_kv);
     mbar_expect_tx(bar_v, bytes);
     if (SELF) tma_load_3d(v_s, &tmap, bar_v, p.v_col + h * DH, v * K, 0);
-    else tma_load_2d(v_s, &tmap, bar_v, p.v_col + h * DH, v * p.Lm);
+    else tma_load_2d_hint(v_s, &tmap, bar_v, p.v_col + h * DH, v * p.Lm, pol_kv);
   }
 
   const int g = lane >> 2, tig = lane & 3;   // g = beam (MMA row), tig = column pair
@@ -522,6 +524,8 @@ struct Cfg {
 
 __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, uint32_t bar, int col, int r0, int r1,
                                             int r2, int r3) {
+  // no L2 eviction hint here (the cross-attention K/V tiles carry one): the 64-bit policy operand costs the two
+  // registers this 128-register kernel does not have (24 bytes of spills when it was tried)
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
@@ -855,6 +859,7 @@ int cross_step(care_ctx* ctx, const void* q, int64_t ldq, const void* kv, int Lm
   p.done = done;
   p.out = static_cast<h16*>(ctx_out);
   p.n_items = B * H;
+  p.l2_hints = ctx->l2_hints;
   if (Lm <= 32) return launch<2, false, 1>(ctx, tmap, p, stream);   // e.g. the 30 concept embeddings (attr_attention)
   if (Lm <= 64) return launch<2, false, 2>(ctx, tmap, p, stream);
   return launch<2, false, 4>(ctx, tmap, p, stream);   // Lm <= 128: 8 steps of 16 keys over 4 warps
@@ -890,6 +895,7 @@ int self_step(care_ctx* ctx, const void* cache, int n_pos, int B, int K, int H, 
   p.row_counter = ctx->self_attn_rows;
   p.out = static_cast<h16*>(ctx_out);
   p.n_items = B * H;
+  p.l2_hints = ctx->l2_hints;
   // short prefixes: nearly every slot is still live and the dense TMA tile is cheaper than the per-item bookkeeping
   // (and few (video, head) items - latency mode - leave most of the stream kernel's warps without work)
   // (3 = the stream kernel for every shape: tests)

@@ -287,6 +287,7 @@ struct SegLayout {
   int nseg, n_tiles;
   int64_t T, G;
   int row_shift;   // log2(rows per row block of the kernel that wrote the records: 7 single-CTA, 8 CTA pair)
+  int split;       // segment g of a run = column half g of its tiles (both exist) instead of its tiles of parity g
   int rpv;         // record rows per video: K, or 1 for the compact first step (one <bos> row per video, record row v)
 };
 
@@ -318,6 +319,7 @@ beam_update_kernel(const care_beam_state st, const SegLayout sl, int step, int m
   __shared__ uint8_t old_anc_all[UPD_WARPS][8 * 64];
   __shared__ float fin_v_all[UPD_WARPS][KB];
   __shared__ int fin_i_all[UPD_WARPS][KB];
+  __shared__ float row_rec_all[UPD_WARPS][8][2 + 2 * KB];   // merged (max, sum-exp, top-KB) record of each beam row
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int v = blockIdx.x * UPD_WARPS + warp;
   if (v >= st.B) return;
@@ -327,119 +329,105 @@ beam_update_kernel(const care_beam_state st, const SegLayout sl, int step, int m
   int* fin_i = fin_i_all[warp];
   const int K = st.K, V = st.V, T = st.T_max;
   const int nsel = K + 1;
+  // everything the bookkeeping below needs from the beam state is requested now, under the record merge
+  for (int idx = lane; idx < K * T; idx += 32) old_anc[idx] = st.anc[(int64_t)v * K * T + idx];
+  __shared__ int row_tok_all[UPD_WARPS][8];
+  __shared__ float row_score_all[UPD_WARPS][8];
+  if (lane < K && step > 1) {
+    row_tok_all[warp][lane] = st.cur_tok[v * K + lane];
+    row_score_all[warp][lane] = st.scores[v * K + lane];
+  }
+  int fin_count0 = 0;
+  if (lane == 0) fin_count0 = st.fin_count[v];
 
+  const float* rec_base = st.scratch + (int64_t)v * K * (2 + 2 * KB);   // one record per row, rows of this video
   if (sl.partials != nullptr) {
-    // merge the row's segment records into one (max, sum-exp, top-KB) record
+    // merge the row's segment records into one (max, sum-exp, top-KB) record, kept in shared memory
+    rec_base = &row_rec_all[warp][0][0];
     const int max_slots = 2 * (int)((sl.n_tiles * sl.G + sl.T - 1) / sl.T + 1);   // upper bound of segments per row
-    if (max_slots <= 8) {
-      // large batches: a few segments per row -> one lane per row, no cross-lane traffic
-      if (lane < sl.rpv) {
-        const int r = v * K + lane;            // row of the beam state / merged record
-        const int rr = v * sl.rpv + lane;      // row of the vocabulary kernel's records
-        const int m_blk = rr >> sl.row_shift;
-        const int c0 = (int)((((int64_t)m_blk * sl.n_tiles + 1) * sl.G - 1) / sl.T);
-        const int c1 = (int)((((int64_t)m_blk * sl.n_tiles + sl.n_tiles) * sl.G - 1) / sl.T);
-        const float* base = sl.partials + (int64_t)rr * sl.nseg * (2 + 2 * KB);
-        const int64_t mlo = (int64_t)m_blk * sl.n_tiles, mhi = mlo + sl.n_tiles;
-        float M = -INFINITY, S = 0.f;
-        TopList<KB> l;
-        l.init();
-        for (int sidx = 0; sidx < 2 * (c1 - c0 + 1); ++sidx) {
-          const int c = c0 + (sidx >> 1), g = sidx & 1;
-          const int64_t start = (int64_t)c * sl.T / sl.G, end = (int64_t)(c + 1) * sl.T / sl.G;
-          const int64_t lo = start > mlo ? start : mlo, hi = end < mhi ? end : mhi;
-          if (!(lo + ((g - (lo - start)) & 1) < hi)) continue;
-          const float* rec = base + sidx * (2 + 2 * KB);
-          const float m = rec[0];
-          if (m > M) {
-            S *= __expf(M - m);
-            M = m;
-          }
-          S += rec[1] * __expf(rec[0] - M);
-#pragma unroll
-          for (int q = 0; q < KB; ++q) {
-            const int idx = reinterpret_cast<const int*>(rec)[2 + KB + q];
-            if (idx != INT_MAX) l.insert(rec[2 + q], idx);
-          }
+    // large batches have a few segments per row: one lane per row.  Small batches put every tile in its own short run
+    // (up to ~2 x n_tiles segments per row): four lanes per row, all rows of the video at once
+    const int lpr = max_slots <= 8 ? 1 : 4;
+    const int b = lane / lpr, sub = lane - b * lpr;
+    float M = -INFINITY, S = 0.f;
+    TopList<KB> l;
+    l.init();
+    if (b < sl.rpv) {
+      const int rr = v * sl.rpv + b;         // row of the vocabulary kernel's records
+      const int m_blk = rr >> sl.row_shift;
+      const int c0 = (int)((((int64_t)m_blk * sl.n_tiles + 1) * sl.G - 1) / sl.T);
+      const int c1 = (int)((((int64_t)m_blk * sl.n_tiles + sl.n_tiles) * sl.G - 1) / sl.T);
+      const float* base = sl.partials + (int64_t)rr * sl.nseg * (2 + 2 * KB);
+      const int64_t mlo = (int64_t)m_blk * sl.n_tiles, mhi = mlo + sl.n_tiles;
+      const int nslot = 2 * (c1 - c0 + 1);
+      for (int sidx = sub; sidx < nslot; sidx += lpr) {
+        const int c = c0 + (sidx >> 1), g = sidx & 1;
+        // segment 2*(c - c0) + g exists iff epilogue group g of run c saw a tile of this m-block
+        const int64_t start = (int64_t)c * sl.T / sl.G, end = (int64_t)(c + 1) * sl.T / sl.G;
+        const int64_t lo = start > mlo ? start : mlo, hi = end < mhi ? end : mhi;
+        if (!(lo + (sl.split ? 0 : ((g - (lo - start)) & 1)) < hi)) continue;
+        const float* rec = base + sidx * (2 + 2 * KB);
+        const float m = rec[0];
+        if (m == -INFINITY) continue;   // a column half past the last vocabulary column
+        if (m > M) {
+          S *= __expf(M - m);
+          M = m;
         }
-        float* out = st.scratch + (int64_t)r * (2 + 2 * KB);
-        out[0] = M;
-        out[1] = S;
+        S += rec[1] * __expf(rec[0] - M);
 #pragma unroll
         for (int q = 0; q < KB; ++q) {
-          out[2 + q] = l.v[q];
-          reinterpret_cast<int*>(out)[2 + KB + q] = l.i[q];
-        }
-      }
-    } else {
-      // small batches put every tile in its own run (~2 x n_tiles segments per row): the whole warp works on
-      // one row at a time
-      for (int b = 0; b < sl.rpv; ++b) {
-        const int r = v * K + b;
-        const int rr = v * sl.rpv + b;
-        const int m_blk = rr >> sl.row_shift;
-        const int c0 = (int)((((int64_t)m_blk * sl.n_tiles + 1) * sl.G - 1) / sl.T);
-        const int c1 = (int)((((int64_t)m_blk * sl.n_tiles + sl.n_tiles) * sl.G - 1) / sl.T);
-        const float* base = sl.partials + (int64_t)rr * sl.nseg * (2 + 2 * KB);
-        const int64_t mlo = (int64_t)m_blk * sl.n_tiles, mhi = mlo + sl.n_tiles;
-        const int nslot = 2 * (c1 - c0 + 1);
-        float M = -INFINITY, S = 0.f;
-        TopList<KB> l;
-        l.init();
-        for (int sidx = lane; sidx < nslot; sidx += 32) {
-          const int c = c0 + (sidx >> 1), g = sidx & 1;
-          // segment 2*(c - c0) + g exists iff epilogue group g of run c saw a tile of this m-block
-          const int64_t start = (int64_t)c * sl.T / sl.G, end = (int64_t)(c + 1) * sl.T / sl.G;
-          const int64_t lo = start > mlo ? start : mlo, hi = end < mhi ? end : mhi;
-          if (!(lo + ((g - (lo - start)) & 1) < hi)) continue;
-          const float* rec = base + sidx * (2 + 2 * KB);
-          const float m = rec[0];
-          if (m > M) {
-            S *= __expf(M - m);
-            M = m;
-          }
-          S += rec[1] * __expf(rec[0] - M);
-  #pragma unroll
-          for (int q = 0; q < KB; ++q) {
-            const int idx = reinterpret_cast<const int*>(rec)[2 + KB + q];
-            if (idx != INT_MAX) l.insert(rec[2 + q], idx);
-          }
-        }
-        const float Mw = warp_max(M);
-        const float Sw = warp_sum(M == -INFINITY ? 0.f : S * __expf(M - Mw));
-        float mv[KB];
-        int mi[KB];
-        warp_merge<KB>(l, mv, mi);
-        if (lane == 0) {
-          float* out = st.scratch + (int64_t)r * (2 + 2 * KB);
-          out[0] = Mw;
-          out[1] = Sw;
-  #pragma unroll
-          for (int q = 0; q < KB; ++q) {
-            out[2 + q] = mv[q];
-            reinterpret_cast<int*>(out)[2 + KB + q] = mi[q];
-          }
+          const int idx = reinterpret_cast<const int*>(rec)[2 + KB + q];
+          if (idx != INT_MAX) l.insert(rec[2 + q], idx);
         }
       }
     }
-    __syncwarp();
+    if (lpr == 4) {   // warp-uniform
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        const float Mo = __shfl_xor_sync(0xffffffffu, M, o), So = __shfl_xor_sync(0xffffffffu, S, o);
+        const float Mn = fmaxf(M, Mo);
+        S = (M == -INFINITY ? 0.f : S * __expf(M - Mn)) + (Mo == -INFINITY ? 0.f : So * __expf(Mo - Mn));
+        M = Mn;
+        float ov[KB];
+        int oi[KB];
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+          ov[q] = __shfl_xor_sync(0xffffffffu, l.v[q], o);
+          oi[q] = __shfl_xor_sync(0xffffffffu, l.i[q], o);
+        }
+#pragma unroll
+        for (int q = 0; q < KB; ++q)
+          if (oi[q] != INT_MAX) l.insert(ov[q], oi[q]);
+      }
+    }
+    if (b < sl.rpv && sub == 0) {
+      float* out = row_rec_all[warp][b];
+      out[0] = M;
+      out[1] = S;
+#pragma unroll
+      for (int q = 0; q < KB; ++q) {
+        out[2 + q] = l.v[q];
+        reinterpret_cast<int*>(out)[2 + KB + q] = l.i[q];
+      }
+    }
   }
+  __syncwarp();
 
   TopList<KB> mine;
   mine.init();
   for (int c = lane; c < K * KB; c += 32) {
     const int b = c / KB, q = c - b * KB;
     if (step == 1 && b > 0) continue;
-    const int r = v * K + b;
-    if (step > 1 && st.cur_tok[r] == CARE_EOS) {
+    const float score_b = step > 1 ? row_score_all[warp][b] : 0.f;
+    if (step > 1 && row_tok_all[warp][b] == CARE_EOS) {
       if (q < V) mine.insert(-1e20f, b * V + q);   // the whole row is -1e20 (Beam.py:52-54)
       continue;
     }
-    const float* rec = st.scratch + (int64_t)r * (2 + 2 * KB);
+    const float* rec = rec_base + b * (2 + 2 * KB);
     const int tok = reinterpret_cast<const int*>(rec)[2 + KB + q];
     if (tok == INT_MAX) continue;
     float val = (rec[2 + q] - rec[0]) - logf(rec[1]);
-    if (step > 1) val += st.scores[r];
+    if (step > 1) val += score_b;
     mine.insert(val, b * V + tok);
   }
   float ov[KB];
@@ -452,7 +440,6 @@ beam_update_kernel(const care_beam_state st, const SegLayout sl, int step, int m
       fin_i[q] = oi[q];
     }
   }
-  for (int idx = lane; idx < K * T; idx += 32) old_anc[idx] = st.anc[(int64_t)v * K * T + idx];
   __syncwarp();
 
   // ancestry: new_anc[b'][p] = old_anc[parent(b')][p] for p < step-1, new_anc[b'][step-1] = parent(b')
@@ -482,7 +469,7 @@ beam_update_kernel(const care_beam_state st, const SegLayout sl, int step, int m
   }
   int vdone = 0;
   if (lane == 0) {
-    int count = st.fin_count[v];
+    int count = fin_count0;
     bool done = false;
     for (int i = 0; i < K && !done; ++i) {  // Beam.py:72-76
       const int fi = fin_i[i];
@@ -656,7 +643,7 @@ static int check_state(const care_beam_state* st, const char* who) {
 }  // namespace beam
 
 namespace vb {  // vocab_beam.cu
-void seg_layout(const care_ctx* ctx, int R, int V, int* n_tiles, int64_t* T, int64_t* G, int* row_shift);
+void seg_layout(const care_ctx* ctx, int R, int V, int* n_tiles, int64_t* T, int64_t* G, int* row_shift, int* split);
 int nseg_for(const care_ctx* ctx, int R, int V);
 }
 }  // namespace care
@@ -745,7 +732,7 @@ static int beam_step_partials_impl(care_ctx* ctx, const care_beam_state* st, con
   sl.partials = partials;
   sl.nseg = nseg;
   sl.rpv = rpv;
-  vb::seg_layout(ctx, st->B * rpv, st->V, &sl.n_tiles, &sl.T, &sl.G, &sl.row_shift);
+  vb::seg_layout(ctx, st->B * rpv, st->V, &sl.n_tiles, &sl.T, &sl.G, &sl.row_shift, &sl.split);
   // the next step's prologue rides along: its input rows when the caller armed them (care_ctx_set_next_step), the
   // live-slot record when the next self-attention will be the chunk stream over this ctx's record table
   beam::NextStep ns{};

@@ -156,6 +156,15 @@ struct care_ctx {
   // clusters only, 1 = pairs whenever such a cluster fits the device, 2 (default) = pick per (M, N, K) by timing both once
   // (option "gemm_ln_pair", env CARE_B200_GEMM_LN_PAIR)
   int gemm_ln_pair = 2;
+  // L2 eviction priorities of the TMA loads (option "l2_hints", env CARE_B200_L2_HINTS): bit 0 = weight tiles evict_last,
+  // bit 1 = cross-attention K/V tiles evict_first (default: measured 8.62 -> 8.39 ms per 512-video shard, 54.6 -> 53.9 ms per 4096
+  // videos; bit 0 measured neutral)
+  int l2_hints = 2;
+  // fused vocabulary kernel, epilogue schedule (option "vocab_split"): 0 = the two epilogue groups take alternate tiles,
+  // 1 = both fold every tile (column halves), 2 (default) = column halves when a run has fewer than vocab_split_tiles
+  // tiles (option "vocab_split_tiles")
+  int vocab_split = 2;
+  int vocab_split_tiles = 24;
   int vocab_2sm = 1;   // fused vocabulary kernel on CTA pairs when the shape has >= two waves of pair tiles
   // per-shape GEMM variant picks; contexts that must launch identical kernels (the lanes of one decode) share one
   // table (care_ctx_share_tuning)
@@ -180,8 +189,9 @@ namespace care {
 struct EarlyExit {
   const int32_t* counter;
   int target;
+  int l2_hints;   // ctx->l2_hints: bit 0 = weight tiles are loaded evict_last, bit 1 = cross-attention K/V tiles evict_first
 };
-inline EarlyExit early_exit_of(const care_ctx* ctx) { return EarlyExit{ctx->skip_counter, ctx->skip_target}; }
+inline EarlyExit early_exit_of(const care_ctx* ctx) { return EarlyExit{ctx->skip_counter, ctx->skip_target, ctx->l2_hints}; }
 
 int get_tmap_bf16(care_ctx* ctx, const void* ptr, int rank, const uint64_t* gdim, const uint64_t* gstride_bytes,
                   const uint32_t* box, CUtensorMap* out);

@@ -369,6 +369,7 @@ gemm_add_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
+      const uint64_t pol_w = l2_policy(ee.l2_hints & 1);
       uint32_t it = 0;
       for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters) {
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
@@ -384,7 +385,7 @@ gemm_add_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
           } else {
             tma_load_2d(a_dst, &tma_a, full_bar(s), kb * BLOCK_K, m_blk * BLOCK_M);
           }
-          tma_load_2d(a_dst + A_BYTES, &tma_b, full_bar(s), kb * BLOCK_K, n_blk * BN);
+          tma_load_2d_hint(a_dst + A_BYTES, &tma_b, full_bar(s), kb * BLOCK_K, n_blk * BN, pol_w);
         }
       }
     }
@@ -579,6 +580,7 @@ gemm_add_ln_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer (every CTA): own 128 rows of A, own half of the pair's W tile =====
+      const uint64_t pol_w = l2_policy(ee.l2_hints & 1);
       uint32_t it = 0;
       for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters) {
         const int a_row = m_blk * PAIR_M + (int)half * BLOCK_M;
@@ -590,7 +592,7 @@ gemm_add_ln_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
           if (half == 0) mbar_expect_tx(full_bar(s), 2 * P_STAGE_BYTES);   // both CTAs' bytes land on the leader
           const uint32_t a_dst = smem_base + s * P_STAGE_BYTES;
           tma_load_2d_pair(a_dst, &tma_a, full_bar(s), kb * BLOCK_K, a_row);
-          tma_load_2d_pair(a_dst + A_BYTES, &tma_b, full_bar(s), kb * BLOCK_K, b_row);
+          tma_load_2d_cta2_hint(a_dst + A_BYTES, &tma_b, full_bar(s) & PEER_MASK, kb * BLOCK_K, b_row, pol_w);
         }
       }
     }

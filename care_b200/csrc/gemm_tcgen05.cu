@@ -108,6 +108,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
+      const uint64_t pol_w = l2_policy(ee.l2_hints & 1);
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;  // n fastest: an A row block is read once
@@ -118,7 +119,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           mbar_expect_tx(full_bar(s), cfg::STAGE_BYTES);
           const uint32_t a_dst = smem_base + s * cfg::STAGE_BYTES;
           tma_load_2d(a_dst, &tma_a, full_bar(s), kb * BLOCK_K, m_blk * BLOCK_M);
-          tma_load_2d(a_dst + cfg::A_BYTES, &tma_b, full_bar(s), kb * BLOCK_K, n_blk * BN);
+          tma_load_2d_hint(a_dst + cfg::A_BYTES, &tma_b, full_bar(s), kb * BLOCK_K, n_blk * BN, pol_w);
         }
       }
     }

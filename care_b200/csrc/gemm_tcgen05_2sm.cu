@@ -130,6 +130,7 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer (both CTAs): own 128 rows of A, own half of the W tile =====
+      const uint64_t pol_w = l2_policy(ee.l2_hints & 1);
       uint32_t it = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
         const int m_pair = tile / n_tiles, n_blk = tile % n_tiles;
@@ -142,7 +143,7 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
           if (rank == 0) mbar_expect_tx(full_bar(s), 2 * STAGE_BYTES);   // both CTAs' bytes land on the leader
           const uint32_t a_dst = smem_base + s * STAGE_BYTES;
           tma_load_2d_2sm(a_dst, &tma_a, full_bar(s), kb * BLOCK_K, a_row);
-          tma_load_2d_2sm(a_dst + A_BYTES, &tma_b, full_bar(s), kb * BLOCK_K, b_row);
+          tma_load_2d_cta2_hint(a_dst + A_BYTES, &tma_b, full_bar(s) & PEER_MASK, kb * BLOCK_K, b_row, pol_w);
         }
       }
     }

@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(256) teacher_probs_kernel(const float* __restr
 
 // same from the fused vocabulary kernel's records (KB = 2); segment existence as in beam.cu
 __global__ void best_partials_kernel(const float* __restrict__ partials, int nseg, int n_tiles, int64_t T, int64_t G,
-                                     int row_shift, int rows, int32_t* __restrict__ idx, float* __restrict__ prob) {
+                                     int row_shift, int split, int rows, int32_t* __restrict__ idx,
+                                     float* __restrict__ prob) {
   constexpr int KB = 2, W = 2 + 2 * KB;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
@@ -150,7 +151,7 @@ __global__ void best_partials_kernel(const float* __restrict__ partials, int nse
       const int64_t start = (int64_t)c * T / G, end = (int64_t)(c + 1) * T / G;
       const int64_t lo = start > mlo ? start : mlo, hi = end < mhi ? end : mhi;
       for (int g = 0; g < 2; ++g) {
-        if (!(lo + ((g - (lo - start)) & 1) < hi)) continue;
+        if (!(lo + (split ? 0 : ((g - (lo - start)) & 1)) < hi)) continue;
         const float* rec = base + (2 * (c - c0) + g) * W;
         if (pass == 0) {
           const float v = rec[2];
@@ -255,7 +256,7 @@ __global__ void select_kernel(const int32_t* __restrict__ tokens, const float* _
 }  // namespace nar
 
 namespace vb {  // vocab_beam.cu
-void seg_layout(const care_ctx* ctx, int R, int V, int* n_tiles, int64_t* T, int64_t* G, int* row_shift);
+void seg_layout(const care_ctx* ctx, int R, int V, int* n_tiles, int64_t* T, int64_t* G, int* row_shift, int* split);
 }
 }  // namespace care
 
@@ -332,11 +333,11 @@ int care_nar_teacher_probs(care_ctx* ctx, const float* logits, int64_t ldv, cons
 int care_nar_best_partials(care_ctx* ctx, const float* partials, int nseg, int rows, int V, int32_t* idx,
                            float* prob, void* stream) {
   CARE_CHECK_ARG(ctx && partials && idx && prob && rows > 0 && V > 0, "care_nar_best_partials: bad args");
-  int n_tiles, row_shift;
+  int n_tiles, row_shift, split;
   int64_t T, G;
-  vb::seg_layout(ctx, rows, V, &n_tiles, &T, &G, &row_shift);
+  vb::seg_layout(ctx, rows, V, &n_tiles, &T, &G, &row_shift, &split);
   nar::best_partials_kernel<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, nseg, n_tiles, T, G,
-                                                                                  row_shift, rows, idx, prob);
+                                                                                  row_shift, split, rows, idx, prob);
   CARE_LAUNCH_CHECK(ctx);
   return 0;
 }

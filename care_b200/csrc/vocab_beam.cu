@@ -15,6 +15,13 @@
 // 2+2*KB-word record per row whenever it leaves an m-block: partials[row][segment], segment =
 // 2 * (this CTA's index - first CTA that touches the m-block) + group.  beam.cu merges the records
 // (and derives from the same arithmetic which segments exist).
+//
+// SPLIT schedule (short runs: strong-scaling shards and small batches): both groups work on EVERY tile, group g folding
+// columns [128 g, 128 g + 128) of it, so a tile's fold takes half as long.  The MMAs of tile i + 2 reuse the accumulator
+// of tile i and must wait for its fold: measured with clock stamps at 2560 rows (scripts/vb_trace.py), a 256-column
+// fold takes 11-15 k cycles (26 k for the first tile of a run, while the top-KB lists fill) against 9.4 k cycles of MMAs
+// per tile, and the tensor pipe idled a third of the kernel.  Records keep their shape: segment = 2 * run + g, where g
+// is now the column half; both segments of a run exist whenever the run touches the m-block.
 #include <cfloat>
 #include <climits>
 
@@ -43,22 +50,23 @@ __host__ __device__ inline int run_of_tile(int64_t t, int64_t T, int64_t G) { re
 
 // Folds one 128 x 256 accumulator tile (this thread's row = its TMEM lane) into the row state: running
 // max, running sum of exp, top-KB raw logits with their column ids.
-template <int KB>
-__device__ __forceinline__ void fold_tile(uint32_t tmem_tile, int n_blk, int N, float& run_m, float& run_s,
-                                          float (&tv)[KB], int (&ti)[KB]) {
+// EDGE: the tile holds the last vocabulary column (TMA zero-fills the columns past V; they must not take part).  Interior
+// tiles are instantiated without the per-element column test - it was a fifth of the loop's instructions.
+template <int KB, bool EDGE>
+__device__ __forceinline__ void fold_tile_impl(uint32_t tmem_tile, int n_blk, int N, float& run_m, float& run_s,
+                                               float (&tv)[KB], int (&ti)[KB], int c_begin, int c_end) {
   constexpr float LOG2E = 1.4426950408889634f;
 #pragma unroll 1
-for (int c = 0; c < BN / 32; ++c) {
+for (int c = c_begin; c < c_end; ++c) {
   const int col0 = n_blk * BN + c * 32;
-  if (col0 >= N) break;
+  if (EDGE && col0 >= N) break;
   uint32_t v[32];
   tmem_ld32(tmem_tile + c * 32, v);
   float x[32];
-  const bool edge = col0 + 32 > N;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     x[j] = __uint_as_float(v[j]);
-    if (edge && col0 + j >= N) x[j] = -INFINITY;   // TMA zero-filled columns past V
+    if (EDGE && col0 + j >= N) x[j] = -INFINITY;
   }
   float cm = x[0];
 #pragma unroll
@@ -105,6 +113,13 @@ for (int c = 0; c < BN / 32; ++c) {
 }
 
 template <int KB>
+__device__ __forceinline__ void fold_tile(uint32_t tmem_tile, int n_blk, int N, float& run_m, float& run_s,
+                                          float (&tv)[KB], int (&ti)[KB], int c_begin = 0, int c_end = BN / 32) {
+  if ((n_blk + 1) * BN > N) fold_tile_impl<KB, true>(tmem_tile, n_blk, N, run_m, run_s, tv, ti, c_begin, c_end);
+  else fold_tile_impl<KB, false>(tmem_tile, n_blk, N, run_m, run_s, tv, ti, c_begin, c_end);
+}
+
+template <int KB>
 __device__ __forceinline__ void flush_record(float* rec, float& run_m, float& run_s, float (&tv)[KB], int (&ti)[KB],
                                              bool write) {
   if (write) {
@@ -125,7 +140,7 @@ __device__ __forceinline__ void flush_record(float* rec, float& run_m, float& ru
   }
 }
 
-template <int KB>
+template <int KB, bool SPLIT>
 __global__ void __launch_bounds__(VB_THREADS, 1)
 vocab_beam_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                           float* __restrict__ partials, int nseg, int M, int N, int K, const EarlyExit ee) {
@@ -162,7 +177,7 @@ vocab_beam_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), EPI_WARPS);
+      mbar_init(tempty_bar(a), SPLIT ? 2 * EPI_WARPS : EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -181,6 +196,7 @@ vocab_beam_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
 
   if (warp == 0) {
     if (lane == 0) {
+      const uint64_t pol_w = l2_policy(ee.l2_hints & 1);
       uint32_t it = 0;
       for (int t = t_begin; t < t_end; ++t) {
         const int m_blk = t / n_tiles, n_blk = t - m_blk * n_tiles;
@@ -191,7 +207,7 @@ vocab_beam_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
           mbar_expect_tx(full_bar(s), cfg::STAGE_BYTES);
           const uint32_t a_dst = smem_base + s * cfg::STAGE_BYTES;
           tma_load_2d(a_dst, &tma_a, full_bar(s), kb * BLOCK_K, m_blk * BLOCK_M);
-          tma_load_2d(a_dst + cfg::A_BYTES, &tma_b, full_bar(s), kb * BLOCK_K, n_blk * BN);
+          tma_load_2d_hint(a_dst + cfg::A_BYTES, &tma_b, full_bar(s), kb * BLOCK_K, n_blk * BN, pol_w);
         }
       }
     }
@@ -235,18 +251,24 @@ vocab_beam_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
       ti[q] = INT_MAX;
     }
     uint32_t gcount = 0;
-    for (int t = t_begin + grp; t < t_end; t += 2, ++gcount) {
+    constexpr int STEP = SPLIT ? 1 : 2;
+    for (int t = t_begin + (SPLIT ? 0 : grp); t < t_end; t += STEP, ++gcount) {
       const int m_blk = t / n_tiles, n_blk = t - m_blk * n_tiles;
-      const uint32_t aph = gcount & 1u;
-      mbar_wait(tfull_bar(grp), aph);
+      const uint32_t acc = SPLIT ? (gcount & 1u) : (uint32_t)grp;
+      const uint32_t aph = SPLIT ? ((gcount >> 1) & 1u) : (gcount & 1u);
+      mbar_wait(tfull_bar(acc), aph);
       tc_fence_after();
       const int row = m_blk * BLOCK_M + ew * 32 + lane;
-      fold_tile<KB>(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + grp * BN, n_blk, N, run_m, run_s, tv, ti);
+      if constexpr (SPLIT)
+        fold_tile<KB>(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN, n_blk, N, run_m, run_s, tv, ti,
+                      grp * (BN / 64), (grp + 1) * (BN / 64));
+      else
+        fold_tile<KB>(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN, n_blk, N, run_m, run_s, tv, ti);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(grp));
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
       // this group's next tile is outside the m-block (or the run): flush the row record, start over
-      const bool last = (t + 2 >= t_end) || ((t + 2) / n_tiles != m_blk);
+      const bool last = (t + STEP >= t_end) || ((t + STEP) / n_tiles != m_blk);
       if (last) {
         const int seg = 2 * ((int)blockIdx.x - run_of_tile((int64_t)m_blk * n_tiles, T, G)) + grp;
         flush_record<KB>(partials + ((int64_t)row * nseg + seg) * (2 + 2 * KB), run_m, run_s, tv, ti, row < M);
@@ -316,7 +338,23 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
 }
 }  // namespace p2
 
-template <int KB>
+// Timeline instrumentation of the CTA-pair kernel (scripts/vb_trace.py; built only with -DCARE_VB_TRACE into
+// lib/libcare_b200_trace.so): SM clock stamps of the leader CTA's roles.  [cluster][role][event]: role 0 = kernel
+// (0 entry, 1 roles start, 2 exit), 1 = TMA producer (first k-block of each tile issued), 2 = MMA issuer (per tile:
+// accumulator free, first operands landed, last MMA issued), 3 / 4 = epilogue group 0 / 1, warp ew = 0 (per tile:
+// accumulator full, fold done).
+#ifdef CARE_VB_TRACE
+constexpr int VBT_EVENTS = 64;
+__device__ long long g_vb_trace[128][5][VBT_EVENTS];
+#define VBT(role, ev)                                                                                         \
+  do {                                                                                                        \
+    if (rank == 0 && cluster_id < 128 && (ev) < VBT_EVENTS) g_vb_trace[cluster_id][role][ev] = clock64();     \
+  } while (0)
+#else
+#define VBT(role, ev) do { } while (0)
+#endif
+
+template <int KB, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(VB_THREADS, 1)
 vocab_beam_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                       float* __restrict__ partials, int nseg, int M, int N, int K, const EarlyExit ee) {
@@ -343,6 +381,7 @@ vocab_beam_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
   const int64_t T = (int64_t)m_pairs * n_tiles, G = gridDim.x >> 1;
   const int t_begin = (int)((int64_t)cluster_id * T / G), t_end = (int)((int64_t)(cluster_id + 1) * T / G);
   const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  if (threadIdx.x == 0) VBT(0, 0);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
@@ -355,7 +394,7 @@ vocab_beam_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 2 * EPI_WARPS);
+      mbar_init(tempty_bar(a), SPLIT ? 4 * EPI_WARPS : 2 * EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -371,9 +410,11 @@ vocab_beam_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
   const uint32_t tmem_base = *tmem_slot_gen;
   pdl_wait();
   pdl_launch_dependents();
+  if (threadIdx.x == 0) VBT(0, 1);
 
   if (warp == 0) {
     if (lane == 0) {
+      const uint64_t pol_w = l2_policy(ee.l2_hints & 1);
       uint32_t it = 0;
       for (int t = t_begin; t < t_end; ++t) {
         const int m_pair = t / n_tiles, n_blk = t - m_pair * n_tiles;
@@ -383,10 +424,11 @@ vocab_beam_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
+          if (kb == 0) VBT(1, t - t_begin);
           if (rank == 0) mbar_expect_tx(full_bar(s), 2 * STAGE_BYTES);
           const uint32_t a_dst = smem_base + s * STAGE_BYTES;
           tma_load_2d_2sm(a_dst, &tma_a, full_bar(s), kb * BLOCK_K, a_row);
-          tma_load_2d_2sm(a_dst + A_BYTES, &tma_b, full_bar(s), kb * BLOCK_K, b_row);
+          tma_load_2d_cta2_hint(a_dst + A_BYTES, &tma_b, full_bar(s) & PEER_MASK, kb * BLOCK_K, b_row, pol_w);
         }
       }
     }
@@ -398,12 +440,14 @@ vocab_beam_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
         const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
         mbar_wait(tempty_bar(acc), aph ^ 1u);
         tc_fence_after();
+        VBT(2, 3 * (t - t_begin));
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
+          if (kb == 0) VBT(2, 3 * (t - t_begin) + 1);
           const uint32_t a_addr = smem_base + s * STAGE_BYTES;
           const uint64_t adesc = sw128_kmajor_desc(a_addr);
           const uint64_t bdesc = sw128_kmajor_desc(a_addr + A_BYTES);
@@ -413,6 +457,7 @@ vocab_beam_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
           commit_2sm_multicast(empty_bar(s));
         }
         commit_2sm_multicast(tfull_bar(acc));
+        VBT(2, 3 * (t - t_begin) + 2);
       }
     }
   } else if (warp >= 4) {
@@ -427,16 +472,25 @@ vocab_beam_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
       ti[q] = INT_MAX;
     }
     uint32_t gcount = 0;
-    for (int t = t_begin + grp; t < t_end; t += 2, ++gcount) {
+    constexpr int STEP = SPLIT ? 1 : 2;
+    for (int t = t_begin + (SPLIT ? 0 : grp); t < t_end; t += STEP, ++gcount) {
       const int m_pair = t / n_tiles, n_blk = t - m_pair * n_tiles;
-      mbar_wait(tfull_bar(grp), gcount & 1u);
+      const uint32_t acc = SPLIT ? (gcount & 1u) : (uint32_t)grp;
+      const uint32_t aph = SPLIT ? ((gcount >> 1) & 1u) : (gcount & 1u);
+      mbar_wait(tfull_bar(acc), aph);
       tc_fence_after();
+      if (ew == 0 && lane == 0) VBT(3 + grp, 2 * (int)gcount);
       const int row = m_pair * PAIR_M + (int)rank * BLOCK_M + ew * 32 + lane;
-      fold_tile<KB>(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + grp * BN, n_blk, N, run_m, run_s, tv, ti);
+      if constexpr (SPLIT)
+        fold_tile<KB>(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN, n_blk, N, run_m, run_s, tv, ti,
+                      grp * (BN / 64), (grp + 1) * (BN / 64));
+      else
+        fold_tile<KB>(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN, n_blk, N, run_m, run_s, tv, ti);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader(tempty_bar(grp));
-      const bool last = (t + 2 >= t_end) || ((t + 2) / n_tiles != m_pair);
+      if (ew == 0 && lane == 0) VBT(3 + grp, 2 * (int)gcount + 1);
+      if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
+      const bool last = (t + STEP >= t_end) || ((t + STEP) / n_tiles != m_pair);
       if (last) {
         const int seg = 2 * (cluster_id - run_of_tile((int64_t)m_pair * n_tiles, T, G)) + grp;
         flush_record<KB>(partials + ((int64_t)row * nseg + seg) * (2 + 2 * KB), run_m, run_s, tv, ti, row < M);
@@ -446,6 +500,7 @@ vocab_beam_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
 
   tc_fence_before();
   cluster_sync_all();
+  if (threadIdx.x == 0) VBT(0, 2);
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -457,6 +512,7 @@ vocab_beam_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
 // Which kernel serves (R, V) and how its tiles are cut into runs.  Deterministic in the shape, because the
 // consumers of the records (beam.cu, nar.cu) recompute it.
 struct Layout {
+  int split;       // both epilogue groups fold every tile (column halves) instead of alternate tiles
   int two_sm;      // CTA-pair kernel (256-row blocks) or single-CTA kernel (128-row blocks)
   int row_shift;   // log2(rows per block)
   int n_tiles;
@@ -479,15 +535,19 @@ static Layout layout_for(const care_ctx* ctx, int R, int V) {
     l.T = (int64_t)((R + BLOCK_M - 1) / BLOCK_M) * l.n_tiles;
     l.G = std::min<int64_t>(l.T, ctx->sm_count);
   }
+  // runs of a few tiles are bound by the latency of a tile's fold, long runs by its throughput (option "vocab_split":
+  // 0 = alternate tiles always, 1 = column halves always, 2 = column halves for runs shorter than vocab_split_tiles)
+  l.split = ctx->vocab_split == 1 || (ctx->vocab_split == 2 && l.T < (int64_t)ctx->vocab_split_tiles * l.G);
   return l;
 }
 
-void seg_layout(const care_ctx* ctx, int R, int V, int* n_tiles, int64_t* T, int64_t* G, int* row_shift) {
+void seg_layout(const care_ctx* ctx, int R, int V, int* n_tiles, int64_t* T, int64_t* G, int* row_shift, int* split) {
   const Layout l = layout_for(ctx, R, V);
   *n_tiles = l.n_tiles;
   *T = l.T;
   *G = l.G;
   *row_shift = l.row_shift;
+  *split = l.split;
 }
 
 bool uses_pairs(const care_ctx* ctx, int R, int V) { return layout_for(ctx, R, V).two_sm != 0; }
@@ -510,23 +570,22 @@ static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
                   int d, cudaStream_t stream) {
   using cfg = Cfg<BN>;
   const Layout l = layout_for(ctx, R, V);
-  static bool configured_all[64][2] = {{false, false}};   // per device: function attributes are per device
-  bool& configured = configured_all[ctx->device & 63][l.two_sm];
+  static bool configured_all[64] = {false};   // per device: function attributes are per device
+  bool& configured = configured_all[ctx->device & 63];
+  if (!configured) {
+    CARE_CUDA(cudaFuncSetAttribute(vocab_beam_2sm_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p2::SMEM_BYTES));
+    CARE_CUDA(cudaFuncSetAttribute(vocab_beam_2sm_kernel<KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p2::SMEM_BYTES));
+    CARE_CUDA(cudaFuncSetAttribute(vocab_beam_tcgen05_kernel<KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
+    CARE_CUDA(cudaFuncSetAttribute(vocab_beam_tcgen05_kernel<KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
+    configured = true;
+  }
   if (l.two_sm) {
-    auto kern = vocab_beam_2sm_kernel<KB>;
-    if (!configured) {
-      CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p2::SMEM_BYTES));
-      configured = true;
-    }
+    auto kern = l.split ? vocab_beam_2sm_kernel<KB, true> : vocab_beam_2sm_kernel<KB, false>;
     CARE_CUDA(launch_pdl(ctx, kern, dim3(2 * (int)l.G), dim3(VB_THREADS), p2::SMEM_BYTES, stream, ta, tb, partials, nseg, R, V,
                          d, early_exit_of(ctx)));
     ctx->last_vocab = "vocab_beam_2sm_kernel";
   } else {
-    auto kern = vocab_beam_tcgen05_kernel<KB>;
-    if (!configured) {
-      CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
-      configured = true;
-    }
+    auto kern = l.split ? vocab_beam_tcgen05_kernel<KB, true> : vocab_beam_tcgen05_kernel<KB, false>;
     CARE_CUDA(launch_pdl(ctx, kern, dim3((int)l.G), dim3(VB_THREADS), cfg::SMEM_BYTES, stream, ta, tb, partials, nseg, R, V, d,
                          early_exit_of(ctx)));
     ctx->last_vocab = "vocab_beam_tcgen05_kernel";
@@ -577,5 +636,14 @@ int care_vocab_beam_partials(care_ctx* ctx, const void* x, int64_t ldx, const vo
   if (K <= 5) return vb::launch<6>(ctx, ta, tb, partials, nseg, R, V, d, s);
   return vb::launch<9>(ctx, ta, tb, partials, nseg, R, V, d, s);
 }
+
+#ifdef CARE_VB_TRACE
+/* debug build only: copies the timeline stamps of the last vocab_beam_2sm_kernel launch ([128][5][64] int64) and clears them */
+int care_debug_vb_trace(long long* out_host) {
+  if (cudaMemcpyFromSymbol(out_host, vb::g_vb_trace, sizeof(vb::g_vb_trace)) != cudaSuccess) return -1;
+  static long long zeros[128 * 5 * vb::VBT_EVENTS] = {0};
+  return cudaMemcpyToSymbol(vb::g_vb_trace, zeros, sizeof(zeros)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 }  // extern "C"

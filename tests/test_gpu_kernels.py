@@ -586,11 +586,16 @@ def test_beam_step_and_finalize(env, K, V, topk):
             assert (out_tok[v, j, t:] == 0).all()
 
 
-@pytest.mark.parametrize("B,K,V,d", [(6, 5, 10547, 512), (300, 5, 14745, 1024), (7, 1, 9468, 512), (40, 3, 700, 768)])
-def test_fused_vocab_beam_matches_unfused(env, B, K, V, d):
+@pytest.mark.parametrize("split", [0, 1])
+@pytest.mark.parametrize("B,K,V,d", [(6, 5, 10547, 512), (300, 5, 14745, 1024), (7, 1, 9468, 512), (40, 3, 700, 768),
+                                     (512, 5, 14745, 1024), (33, 8, 2100, 512), (20, 5, 640, 512)])
+def test_fused_vocab_beam_matches_unfused(env, B, K, V, d, split):
     """care_vocab_beam_partials + care_beam_step_partials (logits never written) against care_gemm +
-    care_beam_step on the same inputs: same winners, same scores, same beam bookkeeping."""
+    care_beam_step on the same inputs: same winners, same scores, same beam bookkeeping.  Both epilogue schedules of
+    the vocabulary kernel (alternate tiles / column halves; V = 640 leaves the second column half of the last tile
+    without a single vocabulary column)."""
     lib, h, L = env
+    L.check(lib.care_ctx_set_option(h, b"vocab_split", split), "option")
     R, max_len = B * K, 8
     Tm, need = max_len - 1, K
     ldv = (V + 7) // 8 * 8
@@ -632,6 +637,7 @@ def test_fused_vocab_beam_matches_unfused(env, B, K, V, d):
             if clear.all():
                 assert torch.equal(a, b), (step, name)
         assert torch.isfinite(lse).all() and live.shape[0] == B
+    L.check(lib.care_ctx_set_option(h, b"vocab_split", 2), "option")
 
 
 def test_nar_teacher_probs(env):

@@ -247,17 +247,20 @@ def test_h16_exact_match_512(precision, population):
         json.dump(out, f, indent=1)
 
 
-def test_fused_vocab_records_direct():
+@pytest.mark.parametrize("R,split", [(20480, 0), (20480, 1), (2560, 0), (2560, 1), (133, 1)])
+def test_fused_vocab_records_direct(R, split):
     """The bench's largest single kernel checked directly (not through the unfused CUDA path): the
-    (max, sum-exp, top-(K+1)) records of care_vocab_beam_partials at R = 20480, V = 14745 against fp32 torch
-    logsumexp / topk of the same 16-bit inputs."""
+    (max, sum-exp, top-(K+1)) records of care_vocab_beam_partials at R = 20480 (one GPU) / 2560 (an 8-GPU shard),
+    V = 14745 against fp32 torch logsumexp / topk of the same 16-bit inputs; both epilogue schedules (alternate tiles,
+    column halves)."""
     import ctypes
     from care_b200 import _lib
     lib = _lib.load("fp16")
     h = ctypes.c_void_p()
     _lib.check(lib.care_ctx_create(ctypes.byref(h), 0), "ctx")
     try:
-        R, V, d, K = 20480, 14745, 1024, 5
+        V, d, K = 14745, 1024, 5
+        _lib.check(lib.care_ctx_set_option(h, b"vocab_split", split), "option")
         g = torch.Generator(device="cuda").manual_seed(3)
         x = torch.randn(R, d, device="cuda", generator=g).half()
         W = (torch.randn(V, d, device="cuda", generator=g) * 0.08).half()
