@@ -18,7 +18,9 @@ COLS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread"]
 # labels = the kernel names bench.py reports (care_ctx_last_kernel), so that its roofline records find their traffic
 LABELS = [("gemm_add_ln_pair_kernel<0>", "gemm_add_ln_pair_kernel<h16 residual>"),
-          ("gemm_add_ln_pair_kernel<1>", "gemm_add_ln_pair_kernel<f32 residual>"), ("gemm_add_ln_kernel<0>", "gemm_add_ln_kernel<h16 residual>"), ("gemm_add_ln_kernel<1>", "gemm_add_ln_kernel<f32 residual>"),
+          ("gemm_add_ln_pair_kernel<1>", "gemm_add_ln_pair_kernel<f32 residual>"),
+          (re.compile(r"gemm_add_ln_kernel<0\b"), "gemm_add_ln_kernel<h16 residual>"),
+          (re.compile(r"gemm_add_ln_kernel<1\b"), "gemm_add_ln_kernel<f32 residual>"), ("gemm_add_ln_kernel<0>", "gemm_add_ln_kernel<h16 residual>"), ("gemm_add_ln_kernel<1>", "gemm_add_ln_kernel<f32 residual>"),
           ("gemm_bf16_2sm_kernel<float>", "gemm_bf16_2sm_kernel<float>"), ("gemm_bf16_2sm_kernel", "gemm_bf16_2sm_kernel<h16>"),
           (re.compile(r"gemm_bf16_tcgen05_kernel<\d+, float>"), "gemm_bf16_tcgen05_kernel<float>"),
           ("gemm_bf16_tcgen05_kernel", "gemm_bf16_tcgen05_kernel<h16>"),
