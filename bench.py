@@ -462,11 +462,14 @@ def run_care_arm(args):
                     got += len(h)
                 return got
 
-            stream_steps(3)
-            sync_all()
             # a loader loop runs many batches; 32 keeps the one-off pipeline fill (the first H2D copy and the last
             # read-back + list building, ~32 ms together at 4096 videos) at ~1 ms per step
             e2e_stream_steps = max(args.steps, 32)
+            # warm-up: one stream of the same length (scripts/stream_probe.py: the first LONG stream of a process pays
+            # ~100 ms of pinned / staging allocations and ~40 ms more at its end, a 3-batch one does not pay all of it;
+            # later streams run at the resident rate + the pipeline fill)
+            stream_steps(e2e_stream_steps)
+            sync_all()
             t0 = time.perf_counter()
             got = stream_steps(e2e_stream_steps)
             torch.cuda.synchronize(dev)
