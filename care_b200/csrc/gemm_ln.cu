@@ -160,12 +160,17 @@ struct EpiCtx {
   int M, N;
   float eps;
   uint32_t ln_rank, ln_size, peer_stride, peer_offset;
+  // RT (residual tile staged by TMA, pair kernel with a 16-bit residual): the CTA's 128 x 256 residual tile as four
+  // SWIZZLE_128B boxes of 64 columns, the barrier its bytes complete on / the barrier that frees it, the tile's parity
+  const uint8_t* res_tile;
+  uint32_t res_full, res_empty, res_parity;
 };
 
-template <bool R32>
+template <bool R32, bool RT = false>
 __device__ __forceinline__ void ln_epilogue_tile(const EpiCtx& e, uint32_t taddr, int row0, uint32_t tfull, uint32_t stats,
                                                  uint32_t table_addr, uint8_t* table_gen, uint32_t aph, int grp, int lane,
                                                  uint32_t my_row) {
+  static_assert(!(R32 && RT), "the TMA-staged residual tile is 16-bit");
   constexpr int HALF = BN / 2;
   constexpr int NSUB = R32 ? 2 : 1;   // 64-byte sub-blocks of the residual per 32-column chunk
   const uint8_t* res_b = e.res_b;
@@ -180,29 +185,41 @@ __device__ __forceinline__ void ln_epilogue_tile(const EpiCtx& e, uint32_t taddr
   const float eps = e.eps;
   const uint32_t ln_rank = e.ln_rank, ln_size = e.ln_size, peer_stride = e.peer_stride, peer_offset = e.peer_offset;
   uint4 gn[NSUB][4];
+  if constexpr (!RT) {
 #pragma unroll
-  for (int sb = 0; sb < NSUB; ++sb) ldg_block(res_b + sb * 64, res_ld, row0, M, lane, gn[sb]);
-  // the rest of this thread's residual row slice -> L2 while the MMAs of the tile still run (the row was usually
-  // evicted by the attention kernel that ran in between); one 128-byte line per request
-  if (row0 + lane < M) {
-    const uint8_t* rp = res_b + (int64_t)(row0 + lane) * res_ld;
+    for (int sb = 0; sb < NSUB; ++sb) ldg_block(res_b + sb * 64, res_ld, row0, M, lane, gn[sb]);
+    // the rest of this thread's residual row slice -> L2 while the MMAs of the tile still run (the row was usually
+    // evicted by the attention kernel that ran in between); one 128-byte line per request
+    if (row0 + lane < M) {
+      const uint8_t* rp = res_b + (int64_t)(row0 + lane) * res_ld;
 #pragma unroll
-    for (int off = 128; off < HALF * (R32 ? 4 : 2); off += 128)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + off));
+      for (int off = 128; off < HALF * (R32 ? 4 : 2); off += 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + off));
+    }
   }
   mbar_wait(tfull, aph);
   tc_fence_after();
+  if constexpr (RT) mbar_wait(e.res_full, e.res_parity);
   // ---- pass 1: v = acc + bias + residual -> TMEM; row statistics ----
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
   for (int c = 0; c < HALF / 32; ++c) {
     uint4 rr[NSUB][4];
+    if constexpr (RT) {
+      // this thread's own row of the tile: 64 bytes of box (cc >> 1), 16-byte chunks XOR-swizzled by the row
+      const int cc = grp * (HALF / 32) + c;
+      const uint8_t* rowp = e.res_tile + (cc >> 1) * (BLOCK_M * 128) + my_row * 128;
 #pragma unroll
-    for (int sb = 0; sb < NSUB; ++sb) xp_to_rows(xp, lane, gn[sb], rr[sb]);
-    if (c + 1 < HALF / 32) {
+      for (int j = 0; j < 4; ++j)
+        rr[0][j] = *reinterpret_cast<const uint4*>(rowp + ((((cc & 1) * 4 + j) ^ (int)(my_row & 7u)) << 4));
+    } else {
 #pragma unroll
-      for (int sb = 0; sb < NSUB; ++sb)
-        ldg_block(res_b + (c + 1) * 32 * (R32 ? 4 : 2) + sb * 64, res_ld, row0, M, lane, gn[sb]);
+      for (int sb = 0; sb < NSUB; ++sb) xp_to_rows(xp, lane, gn[sb], rr[sb]);
+      if (c + 1 < HALF / 32) {
+#pragma unroll
+        for (int sb = 0; sb < NSUB; ++sb)
+          ldg_block(res_b + (c + 1) * 32 * (R32 ? 4 : 2) + sb * 64, res_ld, row0, M, lane, gn[sb]);
+      }
     }
     uint32_t v[32];
     tmem_ld32(taddr + c * 32, v);
@@ -228,6 +245,10 @@ __device__ __forceinline__ void ln_epilogue_tile(const EpiCtx& e, uint32_t taddr
       v[4 * q + 2] = __float_as_uint(x2); v[4 * q + 3] = __float_as_uint(x3);
     }
     tmem_st32(taddr + c * 32, v);
+  }
+  if constexpr (RT) {   // the residual tile is consumed: the next tile's may land while this one is normalised
+    __syncwarp();
+    if (lane == 0) mbar_arrive(e.res_empty);
   }
   tmem_st_wait();
   // ---- exchange the row statistics: the two column halves of this CTA through local slots and a named
@@ -472,11 +493,23 @@ gemm_add_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 // Barriers: full[s] in the pair's leader (even rank; both CTAs' TMA bytes complete there), empty[s] / tfull[a] in both
 // CTAs (multicast tcgen05.commit from the leader's MMA thread), tempty[a] in the leader (16 arrivals: 8 epilogue
 // warps of each CTA), stats[a] per CTA as above.
-constexpr int P_STAGES = 6;
+// With a 16-bit residual the CTA's 128 x 256 residual tile is staged by TMA (four SWIZZLE_128B boxes of 64 columns, 64 KB,
+// issued by the otherwise idle warp 3 while the tile's MMAs run) and the ring has 4 stages; the epilogue then reads its
+// row from shared memory instead of the coalesced-load + per-warp transposition chain whose global-load latency it could
+// not hide (8 epilogue warps, ~0.2 instructions per cycle and scheduler: ~9 us per tile against a 6.3 us K = 1024
+// mainloop).  An fp32 residual (128 KB per tile) keeps the register path and 6 stages.
 constexpr int P_B_BYTES = (BN / 2) * BLOCK_K * 2;
 constexpr int P_STAGE_BYTES = A_BYTES + P_B_BYTES;   // 32 KB per CTA and k-block
-constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 8 * XP_BYTES + STATS_BYTES + PARAM_BYTES + BAR_BYTES + 1024;
-static_assert(P_SMEM_BYTES <= 227 * 1024, "shared memory budget (pair kernel)");
+constexpr int RES_TILE_BYTES = BLOCK_M * BN * 2;     // 64 KB
+template <bool RT>
+struct PairCfg {
+  static constexpr int STAGES = RT ? 4 : 6;
+  static constexpr int RES_BYTES = RT ? RES_TILE_BYTES : 0;
+  static constexpr int SMEM_BYTES =
+      STAGES * P_STAGE_BYTES + RES_BYTES + 8 * XP_BYTES + STATS_BYTES + PARAM_BYTES + BAR_BYTES + 1024;
+};
+static_assert(PairCfg<true>::SMEM_BYTES <= 227 * 1024 && PairCfg<false>::SMEM_BYTES <= 227 * 1024,
+              "shared memory budget (pair kernel)");
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the lowest CTA-rank bit of a shared-window address -> pair leader
 
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -508,15 +541,18 @@ __device__ __forceinline__ void mbar_arrive_pair_leader(uint32_t bar) {
 template <bool R32>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_add_ln_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                        const float* __restrict__ bias, const void* __restrict__ residual, const float* __restrict__ gamma,
+                        const __grid_constant__ CUtensorMap tma_res, const float* __restrict__ bias, const void* __restrict__ residual, const float* __restrict__ gamma,
                         const float* __restrict__ beta, float eps, h16* __restrict__ out16, float* __restrict__ out32,
                         int M, int N, int K, const EarlyExit ee) {
   if (all_done(ee)) return;   // uniform over the grid
+  constexpr bool RT = !R32;
+  constexpr int P_STAGES = PairCfg<RT>::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - raw_addr);
-  const uint32_t xp_base = smem_base + P_STAGES * P_STAGE_BYTES;
+  const uint32_t res_base = smem_base + P_STAGES * P_STAGE_BYTES;   // 1024-byte aligned: SWIZZLE_128B boxes
+  const uint32_t xp_base = res_base + PairCfg<RT>::RES_BYTES;
   const uint32_t stats_base = xp_base + 8 * XP_BYTES;
   const uint32_t param_base = stats_base + STATS_BYTES;
   const uint32_t bar_base = param_base + PARAM_BYTES;
@@ -526,6 +562,7 @@ gemm_add_ln_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * P_STAGES + 2 + a); };
   auto stats_bar = [&](int p) { return bar_base + 8u * (2 * P_STAGES + 4 + p); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * P_STAGES + 6);
+  const uint32_t res_full_bar = bar_base + 8u * (2 * P_STAGES + 7), res_empty_bar = bar_base + 8u * (2 * P_STAGES + 8);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
   float* param_gen = reinterpret_cast<float*>(smem_gen + (param_base - smem_base));
 
@@ -544,6 +581,7 @@ gemm_add_ln_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+    if constexpr (RT) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_res)) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < P_STAGES; ++s) {
@@ -555,6 +593,8 @@ gemm_add_ln_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
       mbar_init(tempty_bar(a), 4 * EPI_WARPS);   // 8 epilogue warps of each CTA of the pair
       mbar_init(stats_bar(a), 1);
     }
+    mbar_init(res_full_bar, 1);
+    mbar_init(res_empty_bar, 2 * EPI_WARPS);   // the CTA's 8 epilogue warps
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -622,6 +662,21 @@ gemm_add_ln_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
         commit_pair(tfull_bar(acc), pair_mask);
       }
     }
+  } else if (warp == 3) {
+    if constexpr (RT) {
+      if (lane == 0) {
+        // ===== residual producer: this CTA's 128 x 256 tile of the residual, once the previous one is consumed =====
+        uint32_t tcount = 0;
+        for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters, ++tcount) {
+          mbar_wait(res_empty_bar, (tcount & 1u) ^ 1u);
+          mbar_expect_tx(res_full_bar, RES_TILE_BYTES);
+#pragma unroll
+          for (int b = 0; b < BN / BLOCK_K; ++b)
+            tma_load_2d(res_base + b * (BLOCK_M * 128), &tma_res, res_full_bar, n_blk * BN + b * BLOCK_K,
+                        m_blk * PAIR_M + (int)half * BLOCK_M);
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ===== epilogue (every CTA): its 128 rows x 256 columns, exactly as in the single-CTA kernel =====
     const int grp = (warp - 4) >> 2;
@@ -643,8 +698,9 @@ gemm_add_ln_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
       const int row0 = m_blk * PAIR_M + (int)half * BLOCK_M + ew * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + grp * HALF;
       if (warp == 4 && lane == 0) mbar_expect_tx(stats_bar(acc), (cn - 1) * STAT_SLOT);
-      EpiCtx ectx{res_b, res_ld, out16_b, out32_b, bias_s, gamma_s, beta_s, xp, M, N, eps, (uint32_t)n_blk, cn, 2u, half};
-      ln_epilogue_tile<R32>(ectx, taddr, row0, tfull_bar(acc), stats_bar(acc), stats_base + acc * N_SLOTS * STAT_SLOT,
+      EpiCtx ectx{res_b, res_ld, out16_b, out32_b, bias_s, gamma_s, beta_s, xp, M, N, eps, (uint32_t)n_blk, cn, 2u, half,
+                  smem_gen + (res_base - smem_base), res_full_bar, res_empty_bar, tcount & 1u};
+      ln_epilogue_tile<R32, RT>(ectx, taddr, row0, tfull_bar(acc), stats_bar(acc), stats_base + acc * N_SLOTS * STAT_SLOT,
                             smem_gen + (stats_base - smem_base) + acc * N_SLOTS * STAT_SLOT, aph, grp, lane, my_row);
       tc_fence_before();
       __syncwarp();
@@ -715,7 +771,8 @@ static int launch(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, c
 }
 
 template <bool R32>
-static int launch_pair(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const void* residual,
+static int launch_pair(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tres, const float* bias,
+                       const void* residual,
                        const float* gamma, const float* beta, float eps, void* out16, float* out32, int M, int N, int K,
                        cudaStream_t stream) {
   static bool configured_all[64] = {false};
@@ -723,7 +780,7 @@ static int launch_pair(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& 
   auto kern = gemm_add_ln_pair_kernel<R32>;
   const int cn = N / BN;
   if (!configured_all[ctx->device & 63]) {
-    CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+    CARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<!R32>::SMEM_BYTES));
     configured_all[ctx->device & 63] = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -735,7 +792,7 @@ static int launch_pair(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& 
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.blockDim = dim3(THREADS, 1, 1);
-  cfg.dynamicSmemBytes = P_SMEM_BYTES;
+  cfg.dynamicSmemBytes = PairCfg<!R32>::SMEM_BYTES;
   cfg.stream = stream;
   cfg.attrs = attr;
   cfg.numAttrs = ctx->pdl ? 2 : 1;
@@ -753,8 +810,8 @@ static int launch_pair(care_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& 
   const int m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int clusters = std::min(m_tiles, max_clusters);
   cfg.gridDim = dim3((unsigned)(clusters * 2 * cn), 1, 1);
-  CARE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, bias, residual, gamma, beta, eps, reinterpret_cast<h16*>(out16), out32,
-                               M, N, K, early_exit_of(ctx)));
+  CARE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tres, bias, residual, gamma, beta, eps, reinterpret_cast<h16*>(out16),
+                               out32, M, N, K, early_exit_of(ctx)));
   ctx->last_gemm = R32 ? "gemm_add_ln_pair_kernel<f32 residual>" : "gemm_add_ln_pair_kernel<h16 residual>";
   CARE_LAUNCH_CHECK(ctx);
   return 0;
@@ -772,8 +829,11 @@ static int run_variant(care_ctx* ctx, int pair, const void* A, int64_t lda, cons
     rc = get_tmap(ctx, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(BN / 2), &tb);
     if (rc) return rc;
     if (residual_dtype == CARE_F32)
-      return launch_pair<true>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, out32, M, N, K, s);
-    return launch_pair<false>(ctx, ta, tb, bias, residual, gamma, beta, eps, out16, nullptr, M, N, K, s);
+      return launch_pair<true>(ctx, ta, tb, ta, bias, residual, gamma, beta, eps, out16, out32, M, N, K, s);
+    CUtensorMap tres;   // the 16-bit residual [M, N] as 128-row x 64-column boxes
+    rc = get_tmap(ctx, residual, (uint64_t)M, (uint64_t)N, (uint64_t)N, BLOCK_M, &tres);
+    if (rc) return rc;
+    return launch_pair<false>(ctx, ta, tb, tres, bias, residual, gamma, beta, eps, out16, nullptr, M, N, K, s);
   }
   // the A tile is multicast inside the cluster when its 128 rows split evenly over the CTAs (d = 512, 1024)
   const bool mc = ctx->gemm_ln_multicast && (BLOCK_M % cn) == 0;

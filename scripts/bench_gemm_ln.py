@@ -33,7 +33,7 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     for M, N, K in [(20480, 1024, 1024), (20480, 1024, 4096), (2560, 1024, 1024), (2560, 1024, 4096), (10240, 1024, 1024),
                     (20480, 512, 512), (20480, 768, 768),
-                    (20480, 1024, 64), (20480, 1024, 256), (2560, 1024, 64)]   # K = 64: the epilogue alone:
+                    (20480, 1024, 64), (20480, 1024, 256), (2560, 1024, 64)]:   # K = 64: the epilogue alone
         nbuf = 6 if M > 4096 else 24
         A = [torch.randn(M, K, device="cuda").half() for _ in range(nbuf)]
         res = [torch.randn(M, N, device="cuda").half() for _ in range(nbuf)]
