@@ -103,6 +103,13 @@ int care_ctx_set_option(care_ctx* ctx, const char* name, int value);
  * "gemm_ln_pair": care_gemm_add_ln on CTA pairs (tcgen05 cta_group::2; clusters of 2 * N/256 CTAs over 256-row blocks):
  * 0 = single-CTA clusters only, 1 = pairs whenever such a cluster fits the device, 2 (default) = choose per (M, N, K) by
  * timing both once, as "gemm_2sm" does.
+ * "vocab_split": epilogue schedule of the fused vocabulary kernel (care_vocab_beam_partials): 0 = its two epilogue groups
+ * take alternate tiles, 1 = both fold every tile (128 columns each: half the latency per tile), 2 (default) = column
+ * halves when a CTA's run has fewer than "vocab_split_tiles" (default 24) tiles.  The record layout is the same; the
+ * consumers (care_beam_step_partials, care_nar_best_partials) derive the schedule from the shape and these options, so
+ * change them only between a producer / consumer pair.
+ * "l2_hints": L2 eviction priorities on TMA loads; bit 0 = weight tiles evict_last (measured neutral), bit 1 (default on)
+ * = cross-attention K/V tiles evict_first (the K/V stream no longer evicts what the following kernels re-read).
  * "fuse_info": 1 = the beam kernel also writes the next step's live-slot records (0, the default: a kernel of its
  * own before the self-attention; measured neutral to slightly slower when fused). */
 /* "vocab_2sm": 1 (default) = the fused vocabulary kernel runs on CTA pairs when the shape has at least two
