@@ -125,7 +125,8 @@ struct care_ctx {
   int compact_info_videos = 0;
   unsigned long long* self_attn_rows = nullptr;   // device counter: K/V cache rows read per video (counted by head 0)
   // 0: single-CTA tiles only, 1: CTA-pair (cta_group::2) tiles whenever the shape allows, 2 (default): pick per
-  // (M, N, K, out dtype) by timing both once on the first call with that shape (skipped while capturing)
+  // (M, N, K, out dtype) by timing the variants once on the first call with that shape (skipped while capturing);
+  // 4 / 5: clusters of 4 / 2 CTA pairs that share the A tile by TMA multicast (gemm_bf16_2sm_mc_kernel) whenever possible
   int gemm_2sm = 2;
   const char* last_gemm = "";    // variant names of the most recent launches (care_ctx_last_kernel)
   const char* last_vocab = "";

@@ -21,7 +21,7 @@
 namespace care {
 namespace tc2 {  // gemm_tcgen05_2sm.cu: returns 1 when the shape should use the single-CTA kernel
 int gemm_bf16_2sm(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
-                  int64_t ldc, int out_dtype, int M, int N, int n_store, int K, int act, cudaStream_t stream);
+                  int64_t ldc, int out_dtype, int M, int N, int n_store, int K, int act, cudaStream_t stream, int mc_pairs);
 }
 namespace smallm {  // gemm_smallm.cu: returns 1 when the shape is not covered (M > 16, ...)
 int gemm_bf16_smallm(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C,
@@ -313,20 +313,27 @@ int gemm_bf16(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t 
       if (cap != cudaStreamCaptureStatusNone) {
         choice = 0;   // cannot time inside a capture; not cached
       } else {
-        float best_ms[2] = {0.f, 0.f};
-        bool ok2 = true;
+        // variants: 0 = single-CTA tiles, 1 = CTA pairs, 2 = clusters of 4 pairs with the A tile multicast, 3 = of 2 pairs
+        constexpr int NV = 4;
+        static const int mc_of[NV] = {0, 0, 4, 2};
+        float best_ms[NV] = {0.f, 0.f, 0.f, 0.f};
+        bool ok[NV] = {true, true, true, true};
         cudaEvent_t e0, e1;
         CARE_CUDA(cudaEventCreate(&e0));
         CARE_CUDA(cudaEventCreate(&e1));
         const int saved = ctx->gemm_2sm;
-        for (int v = 0; v < 2 && ok2; ++v) {
-          ctx->gemm_2sm = v;
-          for (int rep = 0; rep < 4; ++rep) {   // rep 0 = warm-up
+        for (int v = 0; v < NV; ++v) {
+          if (v >= 2 && !ok[1]) {   // the shape does not suit pair tiles at all
+            ok[v] = false;
+            continue;
+          }
+          ctx->gemm_2sm = 0;
+          for (int rep = 0; rep < 4 && ok[v]; ++rep) {   // rep 0 = warm-up
             if (rep == 1) cudaEventRecord(e0, stream);
             int rc = 0;
-            if (v == 1) {
-              rc = tc2::gemm_bf16_2sm(ctx, A, lda, W, ldw, bias, C, ldc, out_dtype, M, N, n_store, K, act, stream);
-              if (rc == 1) ok2 = false;
+            if (v >= 1) {
+              rc = tc2::gemm_bf16_2sm(ctx, A, lda, W, ldw, bias, C, ldc, out_dtype, M, N, n_store, K, act, stream, mc_of[v]);
+              if (rc == 1) ok[v] = false;
             } else {
               rc = gemm_bf16(ctx, A, lda, W, ldw, bias, C, ldc, out_dtype, M, N, K, act, stream);
             }
@@ -336,9 +343,8 @@ int gemm_bf16(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t 
               cudaEventDestroy(e1);
               return rc;
             }
-            if (!ok2) break;
           }
-          if (!ok2) break;
+          if (!ok[v]) continue;
           cudaEventRecord(e1, stream);
           cudaEventSynchronize(e1);
           cudaEventElapsedTime(&best_ms[v], e0, e1);
@@ -346,11 +352,13 @@ int gemm_bf16(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t 
         ctx->gemm_2sm = saved;
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
-        choice = (ok2 && best_ms[1] < best_ms[0]) ? 1 : 0;
+        choice = 0;
+        for (int v = 1; v < NV; ++v)
+          if (ok[v] && best_ms[v] < best_ms[choice]) choice = v;
         if (ctx->debug)
-          fprintf(stderr, "[care_b200] gemm M=%d N=%d K=%d out=%s: single-CTA %.3f ms, CTA-pair %s -> %s\n", M, N, K,
-                  out_dtype == CARE_F32 ? "f32" : "bf16", best_ms[0] / 3.0f,
-                  ok2 ? (std::to_string(best_ms[1] / 3.0f) + " ms").c_str() : "n/a", choice ? "CTA-pair" : "single-CTA");
+          fprintf(stderr, "[care_b200] gemm M=%d N=%d K=%d out=%s: single-CTA %.3f ms, CTA-pair %.3f, 4-pair clusters %.3f, "
+                  "2-pair clusters %.3f (0 = n/a) -> variant %d\n", M, N, K, out_dtype == CARE_F32 ? "f32" : "bf16",
+                  best_ms[0] / 3.0f, best_ms[1] / 3.0f, best_ms[2] / 3.0f, best_ms[3] / 3.0f, choice);
         {
           std::lock_guard<std::mutex> g(ctx->tuning->mu);
           ctx->tuning->choice[key] = choice;
@@ -368,10 +376,17 @@ int gemm_bf16(care_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t 
       }
     }
     use_2sm = choice;
+  } else if (use_2sm == 4 || use_2sm == 5) {   // forced: clusters of 4 / 2 pairs (variant codes 2 / 3)
+    use_2sm -= 2;
   }
-  if (use_2sm == 1) {
-    const int rc2 = tc2::gemm_bf16_2sm(ctx, A, lda, W, ldw, bias, C, ldc, out_dtype, M, N, n_store, K, act, stream);
+  if (use_2sm >= 1) {   // 1: CTA pairs, 2 / 3: clusters of 4 / 2 pairs with the A tile multicast
+    const int rc2 = tc2::gemm_bf16_2sm(ctx, A, lda, W, ldw, bias, C, ldc, out_dtype, M, N, n_store, K, act, stream,
+                                       use_2sm == 2 ? 4 : (use_2sm == 3 ? 2 : 0));
     if (rc2 != 1) return rc2;
+    if (use_2sm > 1) {   // the cluster does not fit: plain pairs
+      const int rc3 = tc2::gemm_bf16_2sm(ctx, A, lda, W, ldw, bias, C, ldc, out_dtype, M, N, n_store, K, act, stream, 0);
+      if (rc3 != 1) return rc3;
+    }
   }
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   auto tiles = [&](int bn) { return m_tiles * ((N + bn - 1) / bn); };

@@ -93,8 +93,10 @@ int care_ctx_set_early_exit(care_ctx* ctx, const int32_t* counter, int target);
 /* implementation switches for A/B tests.  "attn_impl": 1 = TMA + tensor-core attention for T16
  * (default), 0 = the SIMT attention kernel for every dtype.  "gemm_2sm": 0 = single-CTA GEMM tiles
  * only, 1 = CTA-pair (tcgen05 cta_group::2) tiles whenever the shape allows, 2 (default) = choose per
- * (M, N, K, out dtype) by timing both variants ONCE, on the first care_gemm call with that shape - the
- * only place the library waits on the stream (never while the stream is being captured). */
+ * (M, N, K, out dtype) by timing the variants ONCE, on the first care_gemm call with that shape - the
+ * only place the library waits on the stream (never while the stream is being captured); 4 / 5 = clusters of
+ * 4 / 2 CTA pairs over neighbouring n-tiles of one 256-row block, the A tile multicast inside the cluster
+ * (also candidates of mode 2). */
 int care_ctx_set_option(care_ctx* ctx, const char* name, int value);
 /* "pdl": 1 (default) = the kernels of a decode step are launched with programmatic stream serialization: kernel
  * N+1 is scheduled while kernel N drains, runs its prologue and blocks in griddepcontrol.wait until N has completed.

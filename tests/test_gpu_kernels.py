@@ -120,8 +120,9 @@ def test_gemm_small_m_matches_tile_kernel(env, M, N, K, out_dtype):
                                    (9999, 2049, 512)])
 @pytest.mark.parametrize("out_dtype", [torch.float32, TH])
 def test_gemm_cta_pair_matches_single_cta(env, M, N, K, out_dtype):
-    """The CTA-pair (cta_group::2) GEMM and the single-CTA GEMM, each forced, against the fp32 product:
-    row / column tails, K not a multiple of the stage depth, both output types, bias + ReLU."""
+    """The CTA-pair (cta_group::2) GEMM, its cluster forms (4 / 2 pairs sharing the A tile by TMA multicast) and the
+    single-CTA GEMM, each forced, against the fp32 product: row / column tails (N = 2049: the last cluster has pairs
+    without a tile), K not a multiple of the stage depth, both output types, bias + ReLU."""
     lib, h, L = env
     g = torch.Generator(device="cuda").manual_seed(M + N)
     A = torch.randn(M, K, device="cuda", generator=g).to(TH)
@@ -134,9 +135,11 @@ def test_gemm_cta_pair_matches_single_cta(env, M, N, K, out_dtype):
     tol = 2e-3 if out_dtype == torch.float32 else 2e-2
     outs = []
     try:
-        for mode in (1, 0):
+        for mode in (1, 4, 5, 0):
             lib.care_ctx_set_option(h, b"gemm_2sm", mode)
             C = _gemm(env, H16, A, W, b, out_dtype, act)
+            ran = lib.care_ctx_last_kernel(h, b"gemm").decode()
+            assert ("_mc_" in ran) == (mode >= 4) and ("2sm" in ran) == (mode >= 1), (mode, ran)
             assert torch.isfinite(C.float()).all()
             assert (C[:, :N].float() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item()), mode
             if C.shape[1] > N:
@@ -144,7 +147,9 @@ def test_gemm_cta_pair_matches_single_cta(env, M, N, K, out_dtype):
             outs.append(C)
     finally:
         lib.care_ctx_set_option(h, b"gemm_2sm", 2)
-    assert (outs[0].float() - outs[1].float()).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+    for o in outs[1:]:
+        assert (outs[0].float() - o.float()).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])   # same MMAs in the same k order
 
 
 @pytest.mark.parametrize("bn", [64, 96, 128, 160, 192, 224, 256])
