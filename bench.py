@@ -458,8 +458,13 @@ def run_care_arm(args):
             def stream_steps(n):
                 got = 0
                 hook = gather_hook if world > 1 else None
+                marks = [time.perf_counter()]
                 for h, s_ in tr.translate_stream([model], ({"feats": host_feats} for _ in range(n)), device_hook=hook):
                     got += len(h)
+                    marks.append(time.perf_counter())
+                if os.environ.get("CARE_B200_DEBUG") and rank == 0:
+                    iv = ["%.2f" % ((b - a) * 1e3) for a, b in zip(marks, marks[1:])]
+                    sys.stderr.write("[bench] stream of %d: ms between results: %s\n" % (n, " ".join(iv)))
                 return got
 
             # a loader loop runs many batches; 32 keeps the one-off pipeline fill (the first H2D copy and the last

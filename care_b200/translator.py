@@ -4,6 +4,8 @@
 teacher_model_wrapper=)` returns `(hyps, scores)` in the reference's formats.  The whole decode runs
 on the device: beam state never visits the host until the final ids come back.
 """
+import gc
+
 import torch
 
 from .engine import carry_n_best, ensemble_ar_decode, hyps_from_device
@@ -36,6 +38,11 @@ class Translator_ARFormer(object):
         self.topk = opt.get("topk", 1)
         self.max_len = opt.get("max_len", 30)
         self.ar_token_id = opt.get("ar_token_id", None)   # alternative <bos> id (Translator.py:33,61)
+        # translate_stream builds thousands of small Python lists per batch; every ~70k of them the interpreter runs a full
+        # (generation-2) collection that walks every object of the process - 50-70 ms with a loaded model, six decodes of a
+        # 512-video shard during which nothing is enqueued.  gc.freeze() at the start of a stream moves what is alive at
+        # that point (model, workspaces, vocabulary) out of the collector's sight; opt["care_gc_freeze"] = False opts out.
+        self.gc_freeze = bool(opt.get("care_gc_freeze", True))
 
     # host-resident batches larger than this are decoded in chunks whose host->device copies overlap
     # the previous chunk's decode (the copy of 4096 videos' fp32 features is 1.4 GB)
@@ -98,6 +105,8 @@ class Translator_ARFormer(object):
         eng = model.engine()
         dev = eng.device
         n_mod = len(eng.modality)
+        if self.gc_freeze:
+            gc.freeze()
         main = torch.cuda.current_stream(dev)
         side = eng.copy_stream()
         staging = [None, None]
