@@ -40,6 +40,7 @@ _SIGNATURES = {
     "care_ctx_sm_count": (c_int, [c_void_p]),
     "care_ctx_share_tuning": (c_int, [c_void_p, c_void_p]),
     "care_ctx_set_next_step": (c_int, [c_void_p, POINTER(NextStep)]),
+    "care_ctx_request_records": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int]),
     "care_ctx_launch_count": (c_int64, [c_void_p]),
     "care_ctx_last_kernel": (c_char_p, [c_void_p, c_char_p]),
     "care_ctx_set_early_exit": (c_int, [c_void_p, c_void_p, c_int]),

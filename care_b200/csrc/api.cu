@@ -117,7 +117,7 @@ int care_ctx_create(care_ctx** out, int device) {
   if (const char* e = getenv("CARE_B200_VOCAB_SPLIT_TILES")) c->vocab_split_tiles = atoi(e);
   if (const char* e = getenv("CARE_B200_L2_HINTS")) c->l2_hints = atoi(e);
   if (const char* e = getenv("CARE_B200_GEMM_LN_PAIR")) c->gemm_ln_pair = atoi(e);
-  if (const char* e = getenv("CARE_B200_FUSE_INFO")) c->fuse_info = atoi(e) != 0;
+  if (const char* e = getenv("CARE_B200_FUSE_INFO")) c->fuse_info = atoi(e) == 1;   // 2: care_ctx_request_records (engine)
   if (const char* path = getenv("CARE_B200_GEMM_CHOICE_FILE")) {   // GEMM variants picked by an earlier run
     if (FILE* f = fopen(path, "r")) {
       unsigned long long key;
@@ -168,6 +168,23 @@ int care_ctx_set_next_step(care_ctx* ctx, const care_next_step* next) {
   CARE_CHECK_ARG(ctx != nullptr, "care_ctx_set_next_step: ctx is NULL");
   ctx->next_armed = next != nullptr;
   if (next != nullptr) ctx->next = *next;
+  return 0;
+}
+
+int care_ctx_request_records(care_ctx* ctx, const uint8_t* anc, int anc_stride, const int32_t* tok_hist, const int32_t* done,
+                             int B, int K, int H, int n_pos) {
+  CARE_CHECK_ARG(ctx != nullptr, "care_ctx_request_records: ctx is NULL");
+  ctx->rec_req_armed = anc != nullptr && tok_hist != nullptr && B > 0 && K > 0 && H > 0 && n_pos > 0;
+  if (ctx->rec_req_armed) {
+    ctx->rec_req.anc = anc;
+    ctx->rec_req.anc_stride = anc_stride;
+    ctx->rec_req.tok_hist = tok_hist;
+    ctx->rec_req.done = done;
+    ctx->rec_req.B = B;
+    ctx->rec_req.K = K;
+    ctx->rec_req.H = H;
+    ctx->rec_req.n_pos = n_pos;
+  }
   return 0;
 }
 
@@ -240,7 +257,7 @@ int care_ctx_set_option(care_ctx* ctx, const char* name, int value) {
     return 0;
   }
   if (strcmp(name, "fuse_info") == 0) {
-    ctx->fuse_info = value != 0;
+    ctx->fuse_info = value == 1;
     return 0;
   }
   if (strcmp(name, "pdl") == 0) {

@@ -145,6 +145,16 @@ struct care_ctx {
   // by default: measured neutral to slightly slower (4096 videos 51.2 -> 51.9 ms) - the one-warp-per-video beam kernel
   // is the latency-bound one, and with graphs + programmatic dependent launch a separate small launch costs little
   int fuse_info = 0;
+  // one-shot request armed by care_ctx_request_records: the next care_embed_ln launch also writes the live-slot records of
+  // the self-attention that follows it (extra CTAs of the same launch instead of a record kernel of its own)
+  struct RecordsReq {
+    const uint8_t* anc = nullptr;
+    int anc_stride = 0;
+    const int32_t* tok_hist = nullptr;
+    const int32_t* done = nullptr;
+    int B = 0, K = 0, H = 0, n_pos = 0;
+  } rec_req;
+  bool rec_req_armed = false;
   int info_ready_npos = -1;
   int info_ready_B = 0;
   const void* info_ready_anc = nullptr;

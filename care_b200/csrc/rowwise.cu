@@ -120,16 +120,36 @@ encoder_tail_kernel(const float* __restrict__ x, const float* __restrict__ ypre,
 
 // ---------------------------------------------------------------------------------------------
 // out[r] = LN(((word[tok] + pos[p]) + add[r/rpv]) + gsg[r/rpv])      (Embeddings.py:134-188)
+// the live-slot records of the step's self-attention, written by extra CTAs of the embedding launch (care_ctx_request_records)
+struct RecordsJob {
+  const uint8_t* anc;
+  const int32_t* tok_hist;
+  const int32_t* done;
+  uint32_t* info;      // NULL: no job
+  int anc_stride, tok_stride, B, K, n_pos;
+  int first_block;     // blocks >= first_block build records, one warp per video
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 embed_ln_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ positions, int position,
                 const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ add,
                 const float* __restrict__ gsg, int rpv, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float eps, int R, int d, T* __restrict__ out,
-                float* __restrict__ out32, const EarlyExit ee) {
+                float* __restrict__ out32, const RecordsJob job, const EarlyExit ee) {
   pdl_wait();   // first kernel of a step: the early-exit counter and the tokens come from the beam kernel just before
   pdl_launch_dependents();
   if (all_done(ee)) return;
+  if (job.info != nullptr && (int)blockIdx.x >= job.first_block) {
+    __shared__ uint32_t rec_all[8][attn_mma::INFO_WORDS];
+    const int warp = threadIdx.x >> 5;
+    const int v = ((int)blockIdx.x - job.first_block) * 8 + warp;
+    if (v >= job.B) return;
+    if (job.done != nullptr && job.done[v]) return;
+    attn_mma::warp_compact_record(job.anc, job.anc_stride, job.tok_hist, job.tok_stride, v, job.K, job.n_pos,
+                                  threadIdx.x & 31, rec_all[warp], job.info);
+    return;
+  }
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= R) return;
   const int vid = row / rpv;
@@ -251,14 +271,34 @@ int care_embed_ln(care_ctx* ctx, int dtype, const int32_t* tokens, const int32_t
                  "care_embed_ln: bad args");
   if (rw::check_d(d, "care_embed_ln")) return -1;
   cudaStream_t s = (cudaStream_t)stream;
-  const int grid = (R + 7) / 8;
+  int grid = (R + 7) / 8;
+  rw::RecordsJob job{};
+  if (ctx->rec_req_armed) {
+    ctx->rec_req_armed = false;
+    const care_ctx::RecordsReq& q = ctx->rec_req;
+    // the same conditions under which care_self_attn_step takes the chunk-stream kernel (attention_mma.cu: self_step)
+    const bool stream_kernel = dtype == CARE_H16 && q.K <= 8 && q.n_pos * q.K <= 160 && q.n_pos <= 64 &&
+                               (ctx->self_compact == 3 || (ctx->self_compact == 2 && q.n_pos >= 6 && q.B * q.H >= 1024)) &&
+                               ctx->compact_info != nullptr && q.B <= ctx->compact_info_videos &&
+                               (int64_t)q.anc_stride * q.B * q.K < (1LL << 31);
+    if (stream_kernel) {
+      job.anc = q.anc; job.tok_hist = q.tok_hist; job.done = q.done; job.info = ctx->compact_info;
+      job.anc_stride = q.anc_stride; job.tok_stride = (q.anc_stride + 1) * q.K;
+      job.B = q.B; job.K = q.K; job.n_pos = q.n_pos;
+      job.first_block = grid;
+      grid += (q.B + 7) / 8;
+      ctx->info_ready_npos = q.n_pos;
+      ctx->info_ready_B = q.B;
+      ctx->info_ready_anc = q.anc;
+    }
+  }
   if (dtype == CARE_F32)
     CARE_CUDA(launch_pdl(ctx, rw::embed_ln_kernel<float>, dim3(grid), dim3(256), 0, s, tokens, positions, position, word_emb,
-                         pos_emb, add_feats, gsg, rows_per_video, gamma, beta, eps, R, d, (float*)out, out32,
+                         pos_emb, add_feats, gsg, rows_per_video, gamma, beta, eps, R, d, (float*)out, out32, job,
                          early_exit_of(ctx)));
   else
     CARE_CUDA(launch_pdl(ctx, rw::embed_ln_kernel<h16>, dim3(grid), dim3(256), 0, s, tokens, positions, position, word_emb,
-                         pos_emb, add_feats, gsg, rows_per_video, gamma, beta, eps, R, d, (h16*)out, out32,
+                         pos_emb, add_feats, gsg, rows_per_video, gamma, beta, eps, R, d, (h16*)out, out32, job,
                          early_exit_of(ctx)));
   CARE_LAUNCH_CHECK(ctx);
   return 0;

@@ -104,8 +104,12 @@ class CareEngine:
         # default - measured slower (4096 videos 51.2 -> 51.8 ms, 512 videos 8.90 -> 9.29 ms): one warp per video
         # embeds its K rows one after the other, where embed_ln_kernel has a warp per row
         self.fuse_next_step = bool(int(opt.get("care_fuse_next_step", os.environ.get("CARE_B200_FUSE_NEXT", "0"))))
-        if opt.get("care_fuse_info") is not None:
-            check(self.lib.care_ctx_set_option(self.ctx, b"fuse_info", int(opt["care_fuse_info"])), "care_ctx_set_option")
+        # live-slot records of the stream self-attention: 0 = a kernel of their own, 1 = written by the previous step's beam
+        # kernel (measured slower), 2 = written by extra CTAs of the step's embedding launch (care_ctx_request_records)
+        fi = opt.get("care_fuse_info")
+        fi = int(os.environ.get("CARE_B200_FUSE_INFO", "2")) if fi is None else int(fi)
+        check(self.lib.care_ctx_set_option(self.ctx, b"fuse_info", fi), "care_ctx_set_option")
+        self.fuse_records = fi == 2
         self._x0_ready = None      # (t, R): x0 of step t was written by the previous step's beam kernel
         # step 1 of the beam search on one row per video (all K beams hold <bos>; 16-bit fused path)
         self.compact_first = bool(opt.get("care_compact_first_step", True))
@@ -569,6 +573,9 @@ class CareEngine:
             if self._x0_ready == (t, R):
                 self._x0_ready = None      # written by the beam kernel of step t - 1 (care_ctx_set_next_step)
             else:
+                if self.fuse_records:
+                    check(lib.care_ctx_request_records(ctx, ptr(bufs["anc"]), Tm, ptr(bufs["tok_hist"]), done, B, K, self.H, t),
+                          "care_ctx_request_records")
                 check(lib.care_embed_ln(ctx, dt, ptr(bufs["cur_tok"]), None, t - 1, ptr(w["word"]), ptr(w["pos"]), None,
                                         ptr(gsg), K, ptr(w["emb_g"]), ptr(w["emb_b"]), self.eps, R, d, ptr(x0), ptr(r0),
                                         st), "care_embed_ln")

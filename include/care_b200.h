@@ -59,6 +59,12 @@ int care_ctx_sm_count(const care_ctx* ctx);
  * (care_gemm), "vocab" (care_vocab_beam_partials) or "self_attn" (care_self_attn_step); bench.py labels its
  * roofline records with it */
 const char* care_ctx_last_kernel(const care_ctx* ctx, const char* family);
+/* Arms ONE request: the next care_embed_ln call on this ctx also writes the live-slot records of the chunk-stream
+ * self-attention (care_ctx_set_option "self_compact") for a prefix of n_pos positions of the beam state (anc [B, K, anc_stride],
+ * tok_hist [B, anc_stride + 1, K], done [B] or NULL) - extra CTAs of the same launch - and the care_self_attn_step that follows
+ * launches no record kernel.  Ignored (the record kernel runs as usual) when that self-attention would not use the records. */
+int care_ctx_request_records(care_ctx* ctx, const uint8_t* anc, int anc_stride, const int32_t* tok_hist, const int32_t* done,
+                             int B, int K, int H, int n_pos);
 /* Inputs of the NEXT decode step that the beam kernel can produce while it still holds the chosen tokens: the
  * decoder input rows x0[v*K + b] = LN(word[tok] + pos[step] + gsg[v]) (Embeddings.py:134-188; what care_embed_ln
  * computes in a launch of its own).  care_ctx_set_next_step arms ONE request: the next care_beam_step_partials /

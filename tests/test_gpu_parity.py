@@ -420,15 +420,22 @@ def test_next_step_prologue_in_the_beam_kernel_changes_nothing(name, stream):
     dev = [f.cuda() for f in feats]
     tr = care_b200.get_translator(opt)
     out, launches = {}, {}
-    for fuse in (False, True):
-        m = _gpu_model(dict(opt, care_fuse_next_step=fuse, care_fuse_info=int(fuse), care_cuda_graph=False), sd, "fp16")
+    for fuse in (False, True, "embed"):
+        # "embed": the records ride on the step's own embedding launch (care_ctx_request_records; the default)
+        fopt = dict(care_fuse_next_step=False, care_fuse_info=2) if fuse == "embed" else \
+            dict(care_fuse_next_step=fuse, care_fuse_info=int(fuse))
+        m = _gpu_model(dict(opt, care_cuda_graph=False, **fopt), sd, "fp16")
         n0 = m.engine().launch_count()
         out[fuse] = tr.translate_batch([m], {"feats": dev})
         launches[fuse] = m.engine().launch_count() - n0
-    assert out[True][0] == out[False][0]
-    assert out[True][1] == out[False][1]
+    for fuse in (True, "embed"):
+        assert out[fuse][0] == out[False][0]
+        assert out[fuse][1] == out[False][1]
     assert launches[True] < launches[False]
-    print("\n%s: launches per decode %d -> %d" % (name, launches[False], launches[True]))
+    if stream:
+        assert launches["embed"] < launches[False]
+    print("\n%s: launches per decode %d -> %d (beam kernel) / %d (embedding launch)" % (
+        name, launches[False], launches[True], launches["embed"]))
 
 
 def test_no_gpu_no_fallback_message():
